@@ -1,0 +1,261 @@
+"""ctypes wrapper over oracle/_build/libsvsdf_oracle.so — TEST INFRASTRUCTURE ONLY.
+
+Importers allowed: tests/, __graft_entry__.smoke(), bench.py (cpu_baseline / --impl reference legs).
+The product package (implicit_svsdf_planner_b200/) must never import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libsvsdf_oracle.so")
+_lib = None
+
+dp = C.POINTER(C.c_double)
+
+
+def build(force: bool = False) -> str:
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "svsdf_oracle.hpp", "minco_oracle.hpp", "shapes.hpp")]
+    stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        L.orc_create.restype = C.c_void_p
+        L.orc_create.argtypes = [C.c_char_p, dp, dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]
+        L.orc_destroy.argtypes = [C.c_void_p]
+        L.orc_set_threads.argtypes = [C.c_void_p, C.c_int]
+        L.orc_set_points.argtypes = [C.c_void_p, dp, C.c_int64, C.c_int]
+        L.orc_set_traj.argtypes = [C.c_void_p, C.c_int, dp, dp]
+        L.orc_traj_duration.restype = C.c_double
+        L.orc_traj_duration.argtypes = [C.c_void_p]
+        L.orc_traj_pos.argtypes = [C.c_void_p, C.c_double, dp]
+        L.orc_traj_vel.argtypes = [C.c_void_p, C.c_double, dp]
+        L.orc_sdf_at.restype = C.c_double
+        L.orc_sdf_at.argtypes = [C.c_void_p, dp, C.c_double]
+        L.orc_choice_t_init.restype = C.c_double
+        L.orc_choice_t_init.argtypes = [C.c_void_p, dp, C.c_double]
+        L.orc_gradient_descent.argtypes = [C.c_void_p, dp, C.c_double, C.c_double, C.c_double, dp, dp]
+        L.orc_count_evals.argtypes = [C.c_void_p, C.c_int]
+        L.orc_eval_count.restype = C.c_uint64
+        L.orc_eval_count.argtypes = [C.c_void_p]
+        L.orc_query_outer.argtypes = [C.c_void_p, C.c_int64, dp, dp, dp, dp]
+        L.orc_query.argtypes = [C.c_void_p, C.c_int64, dp, dp, dp, dp, C.POINTER(C.c_int)]
+        L.orc_cost_grad.restype = C.c_int64
+        L.orc_cost_grad.argtypes = [C.c_void_p, C.c_int, dp, dp, dp, dp, dp, dp]
+        L.orc_time_cost_grad.restype = C.c_double
+        L.orc_time_cost_grad.argtypes = [C.c_void_p, C.c_int, dp, dp, C.c_int, C.c_int, dp]
+        L.orc_shape_sdf.argtypes = [C.c_char_p, dp, dp, C.c_int, C.c_int64, dp, dp]
+        L.orc_shape_grad1.argtypes = [C.c_char_p, dp, dp, C.c_int, C.c_int64, dp, dp]
+        L.orc_minco_forward.argtypes = [dp, dp, C.c_int, dp, dp, dp, dp, dp, dp]
+        L.orc_minco_propagate.argtypes = [dp, dp, C.c_int, dp, dp, dp, dp, dp, dp]
+        L.orc_forward_T.argtypes = [C.c_int, dp, dp]
+        L.orc_backward_T.argtypes = [C.c_int, dp, dp]
+        L.orc_set_conditions.argtypes = [C.c_void_p, dp, dp, C.c_int]
+        L.orc_evaluate.restype = C.c_double
+        L.orc_evaluate.argtypes = [C.c_void_p, dp, dp, C.c_int]
+        L.orc_last_costs.argtypes = [C.c_void_p, dp]
+        L.orc_get_coeffs.argtypes = [C.c_void_p, dp, dp]
+        L.orc_lbfgs.restype = C.c_int
+        L.orc_lbfgs.argtypes = [C.c_void_p, dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, dp]
+        L.orc_max_threads.restype = C.c_int
+        L.orc_num_procs.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(dp) if a is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def shape_sdf(name, rel, poly_params=(0.0, 0.0, 0.0), polygon=None):
+    rel = _f64(rel).reshape(-1, 3)
+    out = np.empty(rel.shape[0])
+    pp = _f64(poly_params)
+    poly = _f64(polygon).reshape(-1) if polygon is not None else None
+    lib().orc_shape_sdf(name.encode(), _p(pp), _p(poly), 0 if poly is None else poly.size // 2, rel.shape[0], _p(rel), _p(out))
+    return out
+
+
+def shape_grad1(name, rel, poly_params=(0.0, 0.0, 0.0), polygon=None):
+    rel = _f64(rel).reshape(-1, 3)
+    out = np.empty((rel.shape[0], 3))
+    pp = _f64(poly_params)
+    poly = _f64(polygon).reshape(-1) if polygon is not None else None
+    lib().orc_shape_grad1(name.encode(), _p(pp), _p(poly), 0 if poly is None else poly.size // 2, rel.shape[0], _p(rel), _p(out))
+    return out
+
+
+def minco_forward(init_s, final_s, q, T):
+    """init_s/final_s: 3x3 numpy [dim, derivative]; q: 3x(N-1); returns b (6N x 3), energy, gdC (6N x 3), gdT."""
+    N = int(T.shape[0])
+    i_s = _f64(np.asarray(init_s).T).reshape(-1)  # column-major 3x3
+    f_s = _f64(np.asarray(final_s).T).reshape(-1)
+    qq = _f64(np.asarray(q).T).reshape(-1)  # column-major 3x(N-1)
+    TT = _f64(T)
+    b = np.empty(18 * N)
+    gdC = np.empty(18 * N)
+    gdT = np.empty(N)
+    e = C.c_double()
+    lib().orc_minco_forward(_p(i_s), _p(f_s), N, _p(qq), _p(TT), _p(b), C.cast(C.byref(e), dp), _p(gdC), _p(gdT))
+    return b.reshape(3, 6 * N).T.copy(), e.value, gdC.reshape(3, 6 * N).T.copy(), gdT
+
+
+def minco_propagate(init_s, final_s, q, T, gdC, gdT):
+    N = int(T.shape[0])
+    i_s = _f64(np.asarray(init_s).T).reshape(-1)
+    f_s = _f64(np.asarray(final_s).T).reshape(-1)
+    qq = _f64(np.asarray(q).T).reshape(-1)
+    TT = _f64(T)
+    gc = _f64(np.asarray(gdC).T).reshape(-1)
+    gt = _f64(gdT)
+    gq = np.empty(3 * (N - 1))
+    gT = np.empty(N)
+    lib().orc_minco_propagate(_p(i_s), _p(f_s), N, _p(qq), _p(TT), _p(gc), _p(gt), _p(gq), _p(gT))
+    return gq.reshape(N - 1, 3).T.copy(), gT
+
+
+class Oracle:
+    """Handle on the CPU restatement of TrajOptimizer + SweptVolumeManager for one shape."""
+
+    def __init__(self, shape="star", poly_params=(0.0, 0.0, 0.0), weight_p=60.0, safety_hor=0.7, rho=3.8, threads=1, polygon=None):
+        pp = _f64(poly_params)
+        poly = _f64(polygon).reshape(-1) if polygon is not None else None
+        self.h = lib().orc_create(shape.encode(), _p(pp), _p(poly), 0 if poly is None else poly.size // 2, weight_p, safety_hor, rho, threads)
+        self.N = 0
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().orc_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def set_threads(self, n):
+        lib().orc_set_threads(self.h, int(n))
+
+    def set_points(self, pts):
+        pts = _f64(pts)
+        lib().orc_set_points(self.h, _p(pts), pts.shape[0], pts.shape[1])
+        self.P = pts.shape[0]
+
+    def set_traj(self, T, coeffs_colmajor):
+        T = _f64(T)
+        c = _f64(coeffs_colmajor).reshape(-1)
+        self.N = T.shape[0]
+        lib().orc_set_traj(self.h, self.N, _p(T), _p(c))
+
+    def duration(self):
+        return lib().orc_traj_duration(self.h)
+
+    def traj_pos(self, t):
+        out = np.empty(3)
+        lib().orc_traj_pos(self.h, float(t), _p(out))
+        return out
+
+    def traj_vel(self, t):
+        out = np.empty(3)
+        lib().orc_traj_vel(self.h, float(t), _p(out))
+        return out
+
+    def sdf_at(self, p, t):
+        p = _f64(p)
+        return lib().orc_sdf_at(self.h, _p(p), float(t))
+
+    def choice_t_init(self, p, dt=0.15):
+        p = _f64(p)
+        return lib().orc_choice_t_init(self.h, _p(p), dt)
+
+    def gradient_descent(self, p, tmin, tmax, x0):
+        p = _f64(p)
+        fx = C.c_double()
+        x = C.c_double()
+        lib().orc_gradient_descent(self.h, _p(p), tmin, tmax, x0, C.cast(C.byref(fx), dp), C.cast(C.byref(x), dp))
+        return fx.value, x.value
+
+    def count_evals(self, on=True):
+        lib().orc_count_evals(self.h, 1 if on else 0)
+
+    def eval_count(self):
+        return int(lib().orc_eval_count(self.h))
+
+    def query_outer(self, pts):
+        pts = _f64(pts).reshape(-1, 3)
+        n = pts.shape[0]
+        sdf, ts, g = np.empty(n), np.empty(n), np.empty((n, 3))
+        lib().orc_query_outer(self.h, n, _p(pts), _p(sdf), _p(ts), _p(g))
+        return sdf, ts, g
+
+    def query(self, pts):
+        pts = _f64(pts).reshape(-1, 3)
+        n = pts.shape[0]
+        sdf, ts, g = np.empty(n), np.empty(n), np.empty((n, 3))
+        rounds = np.zeros(n, dtype=np.int32)
+        lib().orc_query(self.h, n, _p(pts), _p(sdf), _p(ts), _p(g), rounds.ctypes.data_as(C.POINTER(C.c_int)))
+        return sdf, ts, g, rounds
+
+    def cost_grad(self, T, coeffs_colmajor, cost0=0.0, gradT0=None, gradC0=None, per_point=False):
+        T = _f64(T)
+        c = _f64(coeffs_colmajor).reshape(-1)
+        N = T.shape[0]
+        cost = C.c_double(cost0)
+        gT = np.zeros(N) if gradT0 is None else _f64(gradT0).copy()
+        gC = np.zeros(18 * N) if gradC0 is None else _f64(gradC0).reshape(-1).copy()
+        pp = np.empty((self.P, 7)) if per_point else None
+        inside = lib().orc_cost_grad(self.h, N, _p(T), _p(c), C.cast(C.byref(cost), dp), _p(gT), _p(gC), _p(pp))
+        return cost.value, gT, gC, pp, int(inside)
+
+    def time_cost_grad(self, T, coeffs_colmajor, warm=1, reps=3):
+        T = _f64(T)
+        c = _f64(coeffs_colmajor).reshape(-1)
+        cost = C.c_double()
+        sec = lib().orc_time_cost_grad(self.h, T.shape[0], _p(T), _p(c), warm, reps, C.cast(C.byref(cost), dp))
+        return sec, cost.value
+
+    def set_conditions(self, init_s, final_s, N):
+        i_s = _f64(np.asarray(init_s).T).reshape(-1)
+        f_s = _f64(np.asarray(final_s).T).reshape(-1)
+        self.N = N
+        lib().orc_set_conditions(self.h, _p(i_s), _p(f_s), N)
+
+    def evaluate(self, x):
+        x = _f64(x)
+        g = np.empty_like(x)
+        f = lib().orc_evaluate(self.h, _p(x), _p(g), x.shape[0])
+        return f, g
+
+    def last_costs(self):
+        out = np.empty(3)
+        lib().orc_last_costs(self.h, _p(out))
+        return out
+
+    def get_coeffs(self):
+        T = np.empty(self.N)
+        b = np.empty(18 * self.N)
+        lib().orc_get_coeffs(self.h, _p(T), _p(b))
+        return T, b
+
+    def lbfgs(self, x0, mem_size=16, past=3, delta=1e-6, g_epsilon=0.0, max_iterations=0, min_step=1e-32):
+        x = _f64(x0).copy()
+        stats = np.zeros(4)
+        ret = lib().orc_lbfgs(self.h, _p(x), x.shape[0], mem_size, past, delta, g_epsilon, max_iterations, min_step, _p(stats))
+        return ret, x, dict(f=stats[0], iters=int(stats[1]), evals=int(stats[2]), seconds=stats[3])
+
+
+def num_procs():
+    return lib().orc_num_procs()
