@@ -1,0 +1,413 @@
+"""Python binding (ctypes) over the C ABI of libsvsdf_b200.so (include/svsdf.h).
+
+The classes mirror the reference's call surface for this path so tests read like the reference's usage:
+
+* ``SweptVolumeManager``  — ``updateTraj``, ``getTrueSDFofSweptVolume``, ``getSDFofSweptVolume``
+  (src/swept_volume/include/swept_volume/sw_manager.hpp:376-385, 844-866, 916-1018) and the shape functor
+  ``getonlySDF`` / ``getonlyGrad1`` (src/utils/include/utils/Shape.hpp:266-270).
+* ``TrajOptimizer`` — ``setParam`` (via the constructor), ``parallel_points``, ``costFunction`` (=
+  ``costFunctionLmbmParallel``), ``addSaftyPenaOnSweptVolumeParallelTrueSDF``, ``optimize_traj``
+  (src/planner_algorithm/include/planner_algorithm/back_end_optimizer.hpp:344-408, 774-869, 877-945;
+  src/planner_algorithm/src/back_end_optimizer.cpp:3-97).
+
+There is no CPU fallback: if the CUDA library is missing or no B200 is visible, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsvsdf_b200.so")
+_lib = None
+
+dp = C.POINTER(C.c_double)
+
+
+class SvsdfError(RuntimeError):
+    pass
+
+
+class _Config(C.Structure):
+    _fields_ = [
+        ("shape", C.c_char_p),
+        ("poly_params", C.c_double * 3),
+        ("weight_p", C.c_double),
+        ("safety_hor", C.c_double),
+        ("rho", C.c_double),
+        ("device", C.c_int),
+        ("strict_fp", C.c_int),
+        ("polygon_xy", dp),
+        ("polygon_n", C.c_int),
+    ]
+
+
+class LbfgsParams(C.Structure):
+    _fields_ = [
+        ("mem_size", C.c_int),
+        ("past", C.c_int),
+        ("delta", C.c_double),
+        ("g_epsilon", C.c_double),
+        ("max_iterations", C.c_int),
+        ("max_linesearch", C.c_int),
+        ("min_step", C.c_double),
+        ("max_step", C.c_double),
+        ("f_dec_coeff", C.c_double),
+        ("s_curv_coeff", C.c_double),
+        ("cautious_factor", C.c_double),
+        ("machine_prec", C.c_double),
+    ]
+
+
+class OptStats(C.Structure):
+    _fields_ = [
+        ("final_cost", C.c_double),
+        ("iterations", C.c_int),
+        ("evaluations", C.c_int),
+        ("status", C.c_int),
+        ("seconds", C.c_double),
+        ("gpu_seconds", C.c_double),
+    ]
+
+
+PROGRESS_T = C.CFUNCTYPE(C.c_int, C.c_void_p, dp, C.c_int)
+
+# every symbol include/svsdf.h declares (tests check the library exports all of them)
+EXPORTED_SYMBOLS = [
+    "svsdf_default_config", "svsdf_create", "svsdf_destroy", "svsdf_last_error", "svsdf_shape_id",
+    "svsdf_set_points", "svsdf_set_points_device", "svsdf_set_traj", "svsdf_query", "svsdf_cost_grad",
+    "svsdf_set_boundary", "svsdf_evaluate", "svsdf_last_costs", "svsdf_get_traj", "svsdf_default_lbfgs_params",
+    "svsdf_optimize", "svsdf_minco_forward", "svsdf_minco_propagate", "svsdf_forward_T", "svsdf_backward_T",
+    "svsdf_shape_sdf", "svsdf_shape_grad1", "svsdf_cost_grad_device", "svsdf_kernel_launches",
+    "svsdf_executed_evals", "svsdf_fp64_peak", "svsdf_device_ptr_points",
+]
+
+
+def lib():
+    """Load libsvsdf_b200.so (built in-tree by ``python -m implicit_svsdf_planner_b200.build``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SvsdfError(
+            f"{LIB_PATH} not found: build it with `python -m implicit_svsdf_planner_b200.build` "
+            "(there is no CPU fallback for the SVSDF path)"
+        )
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.svsdf_default_config.argtypes = [C.POINTER(_Config)]
+    L.svsdf_create.argtypes = [C.POINTER(_Config), C.POINTER(vp)]
+    L.svsdf_destroy.argtypes = [vp]
+    L.svsdf_last_error.restype = C.c_char_p
+    L.svsdf_last_error.argtypes = [vp]
+    L.svsdf_shape_id.argtypes = [C.c_char_p]
+    L.svsdf_set_points.argtypes = [vp, dp, C.c_int64, C.c_int]
+    L.svsdf_set_points_device.argtypes = [vp, vp, C.c_int64]
+    L.svsdf_set_traj.argtypes = [vp, C.c_int, dp, dp]
+    L.svsdf_query.argtypes = [vp, C.c_int, dp, dp, C.c_int64, dp, dp, dp, dp, C.POINTER(C.c_int), C.c_int]
+    L.svsdf_cost_grad.argtypes = [vp, C.c_int, dp, dp, dp, dp, dp]
+    L.svsdf_set_boundary.argtypes = [vp, dp, dp, C.c_int]
+    L.svsdf_evaluate.restype = C.c_double
+    L.svsdf_evaluate.argtypes = [vp, dp, dp, C.c_int]
+    L.svsdf_last_costs.argtypes = [vp, dp]
+    L.svsdf_get_traj.argtypes = [vp, dp, dp]
+    L.svsdf_default_lbfgs_params.argtypes = [C.POINTER(LbfgsParams)]
+    L.svsdf_optimize.argtypes = [vp, dp, dp, dp, C.c_int, C.POINTER(LbfgsParams), vp, vp, dp, dp, C.POINTER(OptStats)]
+    L.svsdf_minco_forward.argtypes = [dp, dp, C.c_int, dp, dp, dp, dp, dp, dp]
+    L.svsdf_minco_propagate.argtypes = [dp, dp, C.c_int, dp, dp, dp, dp, dp, dp]
+    L.svsdf_forward_T.argtypes = [C.c_int, dp, dp]
+    L.svsdf_backward_T.argtypes = [C.c_int, dp, dp]
+    L.svsdf_shape_sdf.argtypes = [vp, C.c_int64, dp, dp]
+    L.svsdf_shape_grad1.argtypes = [vp, C.c_int64, dp, dp]
+    L.svsdf_cost_grad_device.argtypes = [vp, C.c_int, dp, dp, C.c_int, C.POINTER(C.c_float), dp]
+    L.svsdf_kernel_launches.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.svsdf_executed_evals.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64)]
+    L.svsdf_fp64_peak.argtypes = [vp, dp]
+    L.svsdf_device_ptr_points.argtypes = [vp, C.POINTER(vp)]
+    _lib = L
+    return L
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return a.ctypes.data_as(dp) if a is not None else None
+
+
+def _colmajor33(m):
+    return _f64(np.asarray(m, dtype=np.float64).T).reshape(-1)
+
+
+def default_lbfgs_params(**kw) -> LbfgsParams:
+    p = LbfgsParams()
+    lib().svsdf_default_lbfgs_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def minco_forward(init_s, final_s, q, T):
+    """Host MINCO_S3NU of the product. Returns b (6N x 3), energy, dE/dc (6N x 3), dE/dT (N)."""
+    T = _f64(T)
+    N = T.shape[0]
+    qq = _f64(np.asarray(q).T).reshape(-1)
+    b, gc, gt = np.empty(18 * N), np.empty(18 * N), np.empty(N)
+    e = C.c_double()
+    rc = lib().svsdf_minco_forward(_p(_colmajor33(init_s)), _p(_colmajor33(final_s)), N, _p(qq), _p(T), _p(b),
+                                   C.cast(C.byref(e), dp), _p(gc), _p(gt))
+    if rc:
+        raise SvsdfError(f"svsdf_minco_forward: {rc}")
+    return b.reshape(3, 6 * N).T.copy(), e.value, gc.reshape(3, 6 * N).T.copy(), gt
+
+
+def minco_propagate(init_s, final_s, q, T, gdC, gdT):
+    T = _f64(T)
+    N = T.shape[0]
+    qq = _f64(np.asarray(q).T).reshape(-1)
+    gc = _f64(np.asarray(gdC).T).reshape(-1)
+    gq, gT = np.empty(3 * (N - 1)), np.empty(N)
+    rc = lib().svsdf_minco_propagate(_p(_colmajor33(init_s)), _p(_colmajor33(final_s)), N, _p(qq), _p(T), _p(gc),
+                                     _p(_f64(gdT)), _p(gq), _p(gT))
+    if rc:
+        raise SvsdfError(f"svsdf_minco_propagate: {rc}")
+    return gq.reshape(N - 1, 3).T.copy(), gT
+
+
+def forward_T(tau):
+    tau = _f64(tau)
+    T = np.empty_like(tau)
+    lib().svsdf_forward_T(tau.shape[0], _p(tau), _p(T))
+    return T
+
+
+def backward_T(T):
+    T = _f64(T)
+    tau = np.empty_like(T)
+    lib().svsdf_backward_T(T.shape[0], _p(T), _p(tau))
+    return tau
+
+
+class Context:
+    """Owns one svsdf_ctx (one GPU, one stream)."""
+
+    def __init__(self, shape="star", poly_params=(0.0, 0.0, 0.0), weight_p=60.0, safety_hor=0.7, rho=3.8, device=0,
+                 strict_fp=False, polygon=None):
+        L = lib()
+        cfg = _Config()
+        L.svsdf_default_config(C.byref(cfg))
+        self._shape_b = (shape or "").encode()
+        cfg.shape = self._shape_b
+        cfg.poly_params = (C.c_double * 3)(*[float(v) for v in poly_params])
+        cfg.weight_p, cfg.safety_hor, cfg.rho = float(weight_p), float(safety_hor), float(rho)
+        cfg.device, cfg.strict_fp = int(device), int(bool(strict_fp))
+        self._poly = None
+        if polygon is not None:
+            self._poly = _f64(polygon).reshape(-1)
+            cfg.polygon_xy = _p(self._poly)
+            cfg.polygon_n = self._poly.size // 2
+        h = C.c_void_p()
+        rc = L.svsdf_create(C.byref(cfg), C.byref(h))
+        if rc != 0 or not h:
+            raise SvsdfError(f"svsdf_create failed with status {rc} (no usable sm_100 CUDA device? no CPU fallback)")
+        self.h = h
+        self.P = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().svsdf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise SvsdfError(f"{what}: status {rc}: {lib().svsdf_last_error(self.h).decode()}")
+
+    # ---- raw ABI wrappers ----
+    def set_points(self, pts):
+        pts = _f64(pts)
+        if pts.ndim != 2 or pts.shape[1] < 2:
+            raise ValueError("points must be P x (2|3)")
+        self._ck(lib().svsdf_set_points(self.h, _p(pts), pts.shape[0], pts.shape[1]), "svsdf_set_points")
+        self.P = pts.shape[0]
+
+    def set_points_device(self, dev_ptr: int, P: int):
+        self._ck(lib().svsdf_set_points_device(self.h, C.c_void_p(dev_ptr), P), "svsdf_set_points_device")
+        self.P = P
+
+    def points_device_ptr(self) -> int:
+        v = C.c_void_p()
+        self._ck(lib().svsdf_device_ptr_points(self.h, C.byref(v)), "svsdf_device_ptr_points")
+        return v.value or 0
+
+    def set_traj(self, T, coeffs_colmajor):
+        T = _f64(T)
+        c = _f64(coeffs_colmajor).reshape(-1)
+        self._ck(lib().svsdf_set_traj(self.h, T.shape[0], _p(T), _p(c)), "svsdf_set_traj")
+
+    def query(self, T, coeffs_colmajor, pts, outer_only=False):
+        T = _f64(T)
+        c = _f64(coeffs_colmajor).reshape(-1)
+        pts = _f64(pts).reshape(-1, 3)
+        n = pts.shape[0]
+        sdf, ts, g = np.empty(n), np.empty(n), np.empty((n, 3))
+        rounds = np.zeros(n, dtype=np.int32)
+        self._ck(lib().svsdf_query(self.h, T.shape[0], _p(T), _p(c), n, _p(pts), _p(sdf), _p(ts), _p(g),
+                                   rounds.ctypes.data_as(C.POINTER(C.c_int)), int(bool(outer_only))), "svsdf_query")
+        return sdf, ts, g, rounds
+
+    def cost_grad(self, T, coeffs_colmajor, cost0=0.0, gradT0=None, gradC0=None):
+        T = _f64(T)
+        c = _f64(coeffs_colmajor).reshape(-1)
+        N = T.shape[0]
+        cost = C.c_double(cost0)
+        gT = np.zeros(N) if gradT0 is None else _f64(gradT0).copy()
+        gC = np.zeros(18 * N) if gradC0 is None else _f64(gradC0).reshape(-1).copy()
+        self._ck(lib().svsdf_cost_grad(self.h, N, _p(T), _p(c), C.cast(C.byref(cost), dp), _p(gT), _p(gC)),
+                 "svsdf_cost_grad")
+        return cost.value, gT, gC
+
+    def cost_grad_device(self, T, coeffs_colmajor, repeats=1, fetch=True):
+        """Device-resident evaluation; returns (ms per evaluation, out array [cost, gradC(18N), gradT(N), n_inside])."""
+        T = _f64(T)
+        c = _f64(coeffs_colmajor).reshape(-1)
+        N = T.shape[0]
+        ms = C.c_float()
+        out = np.empty(1 + 19 * N + 1) if fetch else None
+        self._ck(lib().svsdf_cost_grad_device(self.h, N, _p(T), _p(c), repeats, C.byref(ms), _p(out)),
+                 "svsdf_cost_grad_device")
+        return ms.value, out
+
+    def set_boundary(self, init_s, final_s, N):
+        self._ck(lib().svsdf_set_boundary(self.h, _p(_colmajor33(init_s)), _p(_colmajor33(final_s)), N),
+                 "svsdf_set_boundary")
+
+    def evaluate(self, x):
+        x = _f64(x)
+        g = np.empty_like(x)
+        f = lib().svsdf_evaluate(self.h, _p(x), _p(g), x.shape[0])
+        if not np.isfinite(f):
+            raise SvsdfError(f"svsdf_evaluate returned {f}: {lib().svsdf_last_error(self.h).decode()}")
+        return f, g
+
+    def last_costs(self):
+        out = np.empty(3)
+        lib().svsdf_last_costs(self.h, _p(out))
+        return out
+
+    def get_traj(self, N):
+        T, b = np.empty(N), np.empty(18 * N)
+        self._ck(lib().svsdf_get_traj(self.h, _p(T), _p(b)), "svsdf_get_traj")
+        return T, b
+
+    def optimize(self, init_s, final_s, x0, N, params: LbfgsParams | None = None, progress=None):
+        x = _f64(x0).copy()
+        T, b = np.empty(N), np.empty(18 * N)
+        st = OptStats()
+        cb = PROGRESS_T(progress) if progress is not None else None
+        rc = lib().svsdf_optimize(self.h, _p(_colmajor33(init_s)), _p(_colmajor33(final_s)), _p(x), N,
+                                  C.byref(params) if params is not None else None,
+                                  C.cast(cb, C.c_void_p) if cb is not None else None, None, _p(T), _p(b), C.byref(st))
+        stats = dict(final_cost=st.final_cost, iterations=st.iterations, evaluations=st.evaluations, status=st.status,
+                     seconds=st.seconds, gpu_seconds=st.gpu_seconds)
+        return rc, x, T, b, stats
+
+    def shape_sdf(self, rel):
+        rel = _f64(rel).reshape(-1, 3)
+        out = np.empty(rel.shape[0])
+        self._ck(lib().svsdf_shape_sdf(self.h, rel.shape[0], _p(rel), _p(out)), "svsdf_shape_sdf")
+        return out
+
+    def shape_grad1(self, rel):
+        rel = _f64(rel).reshape(-1, 3)
+        out = np.empty((rel.shape[0], 3))
+        self._ck(lib().svsdf_shape_grad1(self.h, rel.shape[0], _p(rel), _p(out)), "svsdf_shape_grad1")
+        return out
+
+    def kernel_launches(self) -> int:
+        n = C.c_int64()
+        lib().svsdf_kernel_launches(self.h, C.byref(n))
+        return n.value
+
+    def executed_evals(self, enable=True) -> int:
+        n = C.c_uint64()
+        self._ck(lib().svsdf_executed_evals(self.h, int(bool(enable)), C.byref(n)), "svsdf_executed_evals")
+        return n.value
+
+    def fp64_peak_tflops(self) -> float:
+        v = C.c_double()
+        self._ck(lib().svsdf_fp64_peak(self.h, C.cast(C.byref(v), dp)), "svsdf_fp64_peak")
+        return v.value
+
+
+class SweptVolumeManager:
+    """Mirror of the reference's SweptVolumeManager for the SVSDF queries (sw_manager.hpp)."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self._T = None
+        self._coeffs = None
+
+    def updateTraj(self, T, coeffs_colmajor):  # sw_manager.hpp:376-385
+        self._T, self._coeffs = _f64(T), _f64(coeffs_colmajor).reshape(-1)
+        self.ctx.set_traj(self._T, self._coeffs)
+
+    def getTrueSDFofSweptVolume(self, pos_eva):  # sw_manager.hpp:916-1018 (batched over points)
+        sdf, ts, g, rounds = self.ctx.query(self._T, self._coeffs, pos_eva, outer_only=False)
+        return sdf, ts, g, rounds
+
+    def getSDFofSweptVolume(self, pos_eva):  # sw_manager.hpp:844-866 (batched)
+        sdf, ts, g, _ = self.ctx.query(self._T, self._coeffs, pos_eva, outer_only=True)
+        return sdf, ts, g
+
+    def getonlySDF(self, pos_rel):  # Shape.hpp:266
+        return self.ctx.shape_sdf(pos_rel)
+
+    def getonlyGrad1(self, pos_rel):  # Shape.hpp:268
+        return self.ctx.shape_grad1(pos_rel)
+
+
+class TrajOptimizer:
+    """Mirror of the reference's TrajOptimizer for the back-end SVSDF cost (back_end_optimizer.hpp)."""
+
+    def __init__(self, shape="star", poly_params=(0.0, 0.0, 0.0), weight_p=60.0, safety_hor=0.7, rho=3.8, device=0,
+                 strict_fp=False, polygon=None):
+        self.ctx = Context(shape, poly_params, weight_p, safety_hor, rho, device, strict_fp, polygon)
+        self.sv_manager = SweptVolumeManager(self.ctx)
+        self._points = None
+        self.pieceN = 0
+
+    @property
+    def parallel_points(self):
+        return self._points
+
+    @parallel_points.setter
+    def parallel_points(self, pts):  # plan_manager.cpp:168-175
+        self._points = _f64(pts)
+        self.ctx.set_points(self._points)
+
+    @property
+    def parallel_points_num(self):
+        return 0 if self._points is None else self._points.shape[0]
+
+    def addSaftyPenaOnSweptVolumeParallelTrueSDF(self, T, coeffs_colmajor, cost=0.0, gradT=None, gradC=None):
+        return self.ctx.cost_grad(T, coeffs_colmajor, cost, gradT, gradC)
+
+    def setConditions(self, init_s, final_s, N):
+        self.pieceN = N
+        self.ctx.set_boundary(init_s, final_s, N)
+
+    def costFunction(self, x):  # costFunctionLmbmParallel
+        return self.ctx.evaluate(x)
+
+    def optimize_traj(self, init_s, final_s, opt_x, N, params=None, progress=None):
+        self.pieceN = N
+        return self.ctx.optimize(init_s, final_s, opt_x, N, params, progress)

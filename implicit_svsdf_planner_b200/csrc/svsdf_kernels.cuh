@@ -1,0 +1,902 @@
+// svsdf_kernels.cuh — sm_100a kernels for the SVSDF collision cost + gradient hot path.
+//
+// Replaces the OpenMP loop  TrajOptimizer::addSaftyPenaOnSweptVolumeParallelTrueSDF
+// (src/planner_algorithm/include/planner_algorithm/back_end_optimizer.hpp:774-869) and everything it calls in
+// SweptVolumeManager (src/swept_volume/include/swept_volume/sw_manager.hpp:465-474, 521-526, 538-581, 741-757,
+// 779-806, 844-866, 916-1018, 1249-1325).
+//
+// Mapping (one warp per query point):
+//   * the trajectory blob (durations, quintic coefficients, layer-1 time lattice and its pose table) is pulled
+//     into shared memory once per CTA with a TMA bulk copy (cp.async.bulk + mbarrier);
+//   * choiceTInit's four scan layers are evaluated 32 samples per round, one sample per lane, and reduced with
+//     a shuffle arg-min that keeps the reference's "first strict minimum wins" rule;
+//   * gradientDescent's inner loop (29 step halvings, each needing 3 SDF evaluations) is evaluated
+//     speculatively in parallel: lanes 30/31 compute the finite-difference slope, lanes 0-29 the candidates for
+//     both signs, and the first accepted halving is picked with a ballot — decisions are identical to the
+//     sequential loop given identical SDF values;
+//   * the FD gradient uses 4 lanes; the smoothed-L1 penalty and the chain rule to the 6x3 coefficient block are
+//     accumulated in per-warp shared-memory accumulators (no atomics), reduced per CTA in a fixed order and
+//     written as one partial per CTA; a tiny finalize kernel sums the partials in a fixed order, so results are
+//     bit-reproducible run to run.
+//   * points found inside the swept volume (sdf <= 0) are compacted in index order and handled by k_gsip, one
+//     CTA per point, ring samples spread over the CTA's warps.
+//
+// This file is compiled twice (see svsdf_kernels_fast.cu / svsdf_kernels_strict.cu): with FMA contraction
+// (default) and with -fmad=false ("strict": same rounding sequence as the CPU, used to debug parity).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "svsdf_shapes.cuh"
+#include "svsdf_types.h"
+
+#ifndef SVSDF_NS
+#error "define SVSDF_NS (fast|strict) before including svsdf_kernels.cuh"
+#endif
+
+namespace svsdf {
+namespace SVSDF_NS {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// ------------------------------------------------------------------------------------------------
+// Trajectory view over the shared-memory copy of the blob
+// ------------------------------------------------------------------------------------------------
+struct TrajView {
+    int N, K1;
+    double D;
+    const double *T;     // [N]
+    const double *c;     // [N][3][6] ascending powers
+    const double *lat;   // [K1]
+    const double *pose;  // [K1][4]  x, y, cos, sin
+};
+
+__device__ __forceinline__ TrajView make_view(const double *blob) {
+    TrajView tv;
+    tv.N = (int)blob[0];
+    tv.K1 = (int)blob[1];
+    tv.D = blob[2];
+    BlobLayout L = blob_layout(tv.N, tv.K1);
+    tv.T = blob + L.off_T;
+    tv.c = blob + L.off_c;
+    tv.lat = blob + L.off_lat;
+    tv.pose = blob + L.off_pose;
+    return tv;
+}
+
+// Trajectory<5>::locatePieceIdx (trajectory.hpp:498-516): subtract durations while t > dur (strict).
+__device__ __forceinline__ int locate_piece(const TrajView &tv, double &t) {
+    int idx = 0;
+#pragma unroll 1
+    for (; idx < tv.N; ++idx) {
+        double dur = tv.T[idx];
+        if (!(t > dur)) break;
+        t -= dur;
+    }
+    if (idx == tv.N) {
+        idx--;
+        t += tv.T[idx];
+    }
+    return idx;
+}
+
+// Piece<5>::getPos (trajectory.hpp:104-114): ascending powers with tn *= t (not Horner).
+__device__ __forceinline__ void traj_pos(const TrajView &tv, double t, double &x, double &y, double &yaw) {
+    int i = locate_piece(tv, t);
+    const double *c = tv.c + 18 * i;
+    x = 0.0; y = 0.0; yaw = 0.0;
+    double tn = 1.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        x += tn * c[k];
+        y += tn * c[6 + k];
+        yaw += tn * c[12 + k];
+        tn *= t;
+    }
+}
+
+// Piece<5>::getVel (trajectory.hpp:116-128)
+__device__ __forceinline__ void traj_vel(const TrajView &tv, double t, double &vx, double &vy, double &vw) {
+    int i = locate_piece(tv, t);
+    const double *c = tv.c + 18 * i;
+    vx = 0.0; vy = 0.0; vw = 0.0;
+    double tn = 1.0;
+#pragma unroll
+    for (int k = 1; k < 6; ++k) {
+        double f = (double)k * tn;
+        vx += f * c[k];
+        vy += f * c[6 + k];
+        vw += f * c[12 + k];
+        tn *= t;
+    }
+}
+
+// getStateOnTrajStamp (sw_manager.hpp:465-474) + posEva2Rel (:521-526): rel = Rz(yaw)^T (p - x)
+__device__ __forceinline__ void rel_from_pose(double px, double py, double x, double y, double cy, double sy,
+                                              double &rx, double &ry) {
+    double d0 = px - x, d1 = py - y;
+    rx = cy * d0 + sy * d1;
+    ry = -sy * d0 + cy * d1;
+}
+
+// getSDFAtTimeStamp<false> (sw_manager.hpp:741-757)
+template <int SHAPE, bool XFORM>
+__device__ __forceinline__ double eval_sdf(const TrajView &tv, const ShapeParams &S, double px, double py, double t) {
+    double x, y, yaw, sy, cy, rx, ry;
+    traj_pos(tv, t, x, y, yaw);
+    sincos(yaw, &sy, &cy);
+    rel_from_pose(px, py, x, y, cy, sy, rx, ry);
+    return dev::shape_sdf<SHAPE, XFORM>(S, rx, ry);
+}
+
+// Warp arg-min with the sequential loop's semantics: the FIRST index holding the minimum value wins, NaN never
+// wins (the reference's test is `dis < min_dis`).
+__device__ __forceinline__ void warp_argmin(double &f, int &k) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        double fo = __shfl_xor_sync(FULL, f, off);
+        int ko = __shfl_xor_sync(FULL, k, off);
+        bool take = (fo < f) || (fo == f && ko < k);
+        if (take) { f = fo; k = ko; }
+    }
+}
+
+struct OuterResult {
+    double sdf, tstar;
+    int evals;  // lane-evaluations executed (active lanes), for E_executed accounting
+};
+
+// getSDFofSweptVolume<false,*> (sw_manager.hpp:844-866) = choiceTInit (:538-581) + gradientDescent (:1249-1325),
+// executed cooperatively by one warp. All lanes return the same values.
+template <int SHAPE, bool XFORM>
+__device__ __forceinline__ OuterResult solve_outer(const TrajView &tv, const ShapeParams &S, double px, double py) {
+    const int lane = threadIdx.x & 31;
+    const double D = tv.D;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    int evals = 0;
+
+    // ---- choiceTInit layer 1: shared lattice t_k (accumulated 0.15 adds) with the pose table ----
+    double min_dis = 1e9, seed = 0.0;
+    for (int base = 0; base < tv.K1; base += 32) {
+        int k = base + lane;
+        double f = INF;
+        if (k < tv.K1) {
+            const double *ps = tv.pose + 4 * k;
+            double rx, ry;
+            rel_from_pose(px, py, ps[0], ps[1], ps[2], ps[3], rx, ry);
+            f = dev::shape_sdf<SHAPE, XFORM>(S, rx, ry);
+            if (!(f == f)) f = INF;
+        }
+        evals += min(32, tv.K1 - base);
+        int kb = k;
+        warp_argmin(f, kb);
+        if (f < min_dis) {
+            min_dis = f;
+            seed = tv.lat[kb];
+        }
+    }
+    // ---- layers 2..4: 21-sample windows around the seed, dt *= 0.1 each ----
+    double dt = 0.15;
+#pragma unroll 1
+    for (int layer = 2; layer <= 4; ++layer) {
+        dt *= 0.1;
+        double t = fmax(0.0, seed - 10 * dt);
+        double term = fmin(D, seed + 10 * dt);
+#pragma unroll 1
+        for (int i = 0; i < 21; ++i)
+            if (i < lane) t += dt;  // lane k holds t0 + dt added k times (same rounding as the loop)
+        bool valid = (lane <= 20) && (t <= term);
+        double f = eval_sdf<SHAPE, XFORM>(tv, S, px, py, t);
+        if (!valid || !(f == f)) f = INF;
+        evals += __popc(__ballot_sync(FULL, valid));
+        int kb = lane;
+        double tb = t;
+        warp_argmin(f, kb);
+        tb = __shfl_sync(FULL, t, kb);
+        if (f < min_dis) {
+            min_dis = f;
+            seed = tb;
+        }
+    }
+
+    // ---- gradientDescent: bounds [ts-3.4, ts+3.4] ∩ [0, D] (:856-857) ----
+    const double t_min = fmax(0.0, seed - 3.4);
+    const double t_max = fmin(seed + 3.4, D);
+    double x = seed, prev_x = 10000000.0;
+    // fx = f(x0): x0 is the scan's arg-min, so its value is min_dis (same function, same argument).
+    double fx = min_dis;
+    if (min_dis >= 1e9) {  // nothing was below the initial 1e9 (degenerate): evaluate like the reference does
+        fx = eval_sdf<SHAPE, XFORM>(tv, S, px, py, x);
+        evals += 1;
+    }
+    int iter = 0;
+    bool stop = false;
+#pragma unroll 1
+    while (iter < 1000 && !stop && fabs(x - prev_x) > 1e-16) {
+        prev_x = x;
+        // Round A: lanes 0-14: x - tau_j (sign +1), lanes 15-29: x + tau_j (sign -1), j = 0..14;
+        //          lane 30: t1 = max(0, x-1e-6), lane 31: t2 = min(D, x+1e-6)   (getSDF_DOTAtTimeStamp :798-806)
+        double tq;
+        {
+            int j = (lane < 15) ? lane : lane - 15;
+            double tau = scalbn(0.01, -j);  // alpha halved j times (exact)
+            double change = (lane < 15) ? -tau : tau;  // -tau * sign(g)
+            double xc = x + change;
+            xc = fmax(fmin(xc, t_max), t_min);
+            if (lane == 30) xc = fmax(0.0, x - 0.000001);
+            if (lane == 31) xc = fmin(D, x + 0.000001);
+            tq = xc;
+        }
+        double fq = eval_sdf<SHAPE, XFORM>(tv, S, px, py, tq);
+        evals += 32;
+        double f1 = __shfl_sync(FULL, fq, 30), f2 = __shfl_sync(FULL, fq, 31);
+        double g = (f2 - f1) * 500000;
+        int sgn = (int)(g > 0) - (int)(g < 0);
+        int jacc = -1;
+        double xacc = x, facc = fx;
+        if (sgn != 0) {
+            bool ok = (fq - fx) < 0;
+            unsigned m = __ballot_sync(FULL, ok);
+            unsigned grp = (sgn > 0) ? (m & 0x7fffu) : ((m >> 15) & 0x7fffu);
+            if (grp) {
+                jacc = __ffs(grp) - 1;
+                int src = (sgn > 0) ? jacc : jacc + 15;
+                xacc = __shfl_sync(FULL, tq, src);
+                facc = __shfl_sync(FULL, fq, src);
+            } else {
+                // Round B: halvings j = 15..28 in the known direction
+                int j = 15 + lane;
+                double tau = scalbn(0.01, -j);
+                double change = -tau * (double)sgn;
+                double xc = x + change;
+                xc = fmax(fmin(xc, t_max), t_min);
+                double fb = eval_sdf<SHAPE, XFORM>(tv, S, px, py, xc);
+                evals += 14;
+                bool okb = (lane < 14) && ((fb - fx) < 0);
+                unsigned mb = __ballot_sync(FULL, okb);
+                if (mb) {
+                    int src = __ffs(mb) - 1;
+                    jacc = 15 + src;
+                    xacc = __shfl_sync(FULL, xc, src);
+                    facc = __shfl_sync(FULL, fb, src);
+                }
+            }
+        }
+        if (jacc >= 0) {
+            x = xacc;
+            fx = facc;
+            iter += jacc + 1;
+        } else {
+            iter += 29;
+            stop = true;
+        }
+    }
+    OuterResult R;
+    R.sdf = fx;
+    R.tstar = x;
+    R.evals = evals;
+    return R;
+}
+
+// getGradPrelAtTimeStamp (sw_manager.hpp:779-795) -> getonlyGrad1: central FD, dx = 1e-6 in the body frame
+// (Shape.hpp:35-53), or the Polygon's analytic override (Shape.hpp:1508-1534). 4 lanes do the 4 evaluations.
+template <int SHAPE, bool XFORM>
+__device__ __forceinline__ void grad_prel(const TrajView &tv, const ShapeParams &S, double px, double py, double t,
+                                          double &gx, double &gy) {
+    const int lane = threadIdx.x & 31;
+    double x, y, yaw, sy, cy, rx, ry;
+    traj_pos(tv, t, x, y, yaw);
+    sincos(yaw, &sy, &cy);
+    rel_from_pose(px, py, x, y, cy, sy, rx, ry);
+    if (SHAPE == SH_POLYGON) {
+        dev::PolyHit H = dev::polygon_scan(S, rx, ry);
+        double vx = rx - H.cx, vy = ry - H.cy;
+        double z = vx * vx + vy * vy;
+        if (z > 0.0) {
+            double n = sqrt(z);
+            vx /= n; vy /= n;
+        }
+        if (H.rs % 2 != 0) { vx = -vx; vy = -vy; }
+        gx = vx; gy = vy;
+        return;
+    }
+    const double dx = 0.000001;
+    double qx = rx, qy = ry;
+    if (lane == 0) { qx -= dx; }
+    if (lane == 1) { qx -= dx; qx += 2 * dx; }
+    if (lane == 2) { qy -= dx; }
+    if (lane == 3) { qy -= dx; qy += 2 * dx; }
+    double f = dev::shape_sdf<SHAPE, XFORM>(S, qx, qy);
+    double f0 = __shfl_sync(FULL, f, 0), f1 = __shfl_sync(FULL, f, 1);
+    double f2 = __shfl_sync(FULL, f, 2), f3 = __shfl_sync(FULL, f, 3);
+    gx = (f1 - f0) / (2 * dx);
+    gy = (f3 - f2) / (2 * dx);
+}
+
+// smoothedL1 (back_end_optimizer.hpp:316-340), mu = 0.01
+__device__ __forceinline__ bool smoothed_l1(double x, double mu, double &f, double &df) {
+    if (x < 0.0) return false;
+    if (x > mu) {
+        f = x - 0.5 * mu;
+        df = 1.0;
+        return true;
+    }
+    const double xdmu = x / mu;
+    const double sqrxdmu = xdmu * xdmu;
+    const double mumxd2 = mu - 0.5 * x;
+    f = mumxd2 * sqrxdmu * xdmu;
+    df = sqrxdmu * ((-0.5) * xdmu + 3.0 * mumxd2 / mu);
+    return true;
+}
+
+// Per-point penalty and chain rule: the loop body of addSaftyPenaOnSweptVolumeParallelTrueSDF after the SDF
+// query (back_end_optimizer.hpp:797-854) with grad_cost_p_sw (:1031-1066).
+// In: world point p, sdf, t*, gradient g (body frame for sdf > 0; world-frame GSIP direction otherwise).
+// Out (uniform across the warp): piece index, beta0[6], G[3] = w_p * (d/dx, d/dy, d/dyaw), gdT, pena.
+struct Contribution {
+    int piece;
+    double s1;
+    double G[3];
+    double gdT, pena;
+    bool active;
+};
+__device__ __forceinline__ Contribution point_contribution(const TrajView &tv, const CostParams &cp, double px,
+                                                           double py, double sdf, double tstar, double gx,
+                                                           double gy) {
+    Contribution C;
+    double tl = tstar;
+    int i = locate_piece(tv, tl);
+    const double *c = tv.c + 18 * i;
+    double s1 = tl, s2 = s1 * s1, s3 = s2 * s1, s4 = s2 * s2, s5 = s4 * s1;
+    double b0[6] = {1.0, s1, s2, s3, s4, s5};
+    double b1[6] = {0.0, 1.0, 2.0 * s1, 3.0 * s2, 4.0 * s3, 5.0 * s4};
+    double pos[3], vel[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+            a += c[6 * d + q] * b0[q];
+            b += c[6 * d + q] * b1[q];
+        }
+        pos[d] = a;
+        vel[d] = b;
+    }
+    double yaw = pos[2], sy, cy;
+    sincos(yaw, &sy, &cy);
+    if (sdf < 0) {  // :832 world -> body
+        double g0 = cy * gx + sy * gy;
+        double g1 = -sy * gx + cy * gy;
+        gx = g0; gy = g1;
+    }
+    double sdf_cost = -1.0, sdf_out_grad = 0.0;
+    smoothed_l1(cp.safety_hor - sdf, 0.01, sdf_cost, sdf_out_grad);
+    C.piece = i;
+    C.s1 = s1;
+    C.G[0] = C.G[1] = C.G[2] = 0.0;
+    C.gdT = 0.0;
+    C.pena = 0.0;
+    C.active = false;
+    if (sdf_cost > 0) {
+        double rg0 = -(cy * gx + (-sy) * gy);
+        double rg1 = -(sy * gx + cy * gy);
+        double sg0 = -sdf_out_grad * rg0, sg1 = -sdf_out_grad * rg1;
+        double d0 = px - pos[0], d1 = py - pos[1];
+        double w0 = -sy * d0 + cy * d1;
+        double w1 = -cy * d0 + -sy * d1;
+        double gyaw = (-sdf_out_grad * gx) * w0 + (-sdf_out_grad * gy) * w1;
+        C.G[0] = cp.weight_p * sg0;
+        C.G[1] = cp.weight_p * sg1;
+        C.G[2] = cp.weight_p * gyaw;
+        C.pena = cp.weight_p * sdf_cost;
+        C.gdT = -(C.G[0] * vel[0] + C.G[1] * vel[1] + C.G[2] * vel[2]);
+        C.active = true;
+    }
+    return C;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA bulk copy of the trajectory blob into shared memory (cp.async.bulk + mbarrier)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tma_load_blob(double *smem_blob, const double *gmem_blob, int n_doubles,
+                                              uint64_t *bar) {
+    const uint32_t bar_a = smem_u32(bar);
+    const uint32_t bytes = (uint32_t)n_doubles * 8u;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_a), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                smem_u32(smem_blob)),
+            "l"(gmem_blob), "r"(bytes), "r"(bar_a)
+            : "memory");
+    }
+    // all threads wait on phase 0
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar_a), "r"(0)
+            : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_pose_table: (x, y, cos yaw, sin yaw) at the layer-1 lattice times, written into the blob in place.
+// The lattice and its poses are shared by every query point (choiceTInit layer 1 always scans 0..D in 0.15 s
+// steps), so they are computed once per evaluation instead of once per point.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_pose_table(double *blob) {
+    TrajView tv = make_view(blob);
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= tv.K1) return;
+    double x, y, yaw, sy, cy;
+    traj_pos(tv, tv.lat[k], x, y, yaw);
+    sincos(yaw, &sy, &cy);
+    double *ps = blob + blob_layout(tv.N, tv.K1).off_pose + 4 * k;
+    ps[0] = x; ps[1] = y; ps[2] = cy; ps[3] = sy;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: outer solve for every point (+ penalty, chain rule and CTA reduction for outside points)
+// dynamic smem: [ blob | 8 warps x (19N + 1) accumulators ]
+// ------------------------------------------------------------------------------------------------
+template <int SHAPE, bool XFORM>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+    k_outer(const __grid_constant__ KernelArgs A, const __grid_constant__ ShapeParams S) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t bar;
+    double *sblob = smem;
+    tma_load_blob(sblob, A.blob, A.blob_doubles, &bar);
+    const TrajView tv = make_view(sblob);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nacc = 19 * tv.N + 1;
+    double *acc = smem + A.blob_doubles + warp * nacc;  // [N][18] gdC, then [N] gdT-by-piece, then cost
+    if (A.want_reduce)
+        for (int e = lane; e < nacc; e += 32) acc[e] = 0.0;
+    __syncwarp();
+
+    const int64_t wstride = (int64_t)gridDim.x * kWarpsPerBlock;
+    unsigned long long my_evals = 0;
+    for (int64_t pt = (int64_t)blockIdx.x * kWarpsPerBlock + warp; pt < A.P; pt += wstride) {
+        const double px = __ldg(A.points_xy + 2 * pt), py = __ldg(A.points_xy + 2 * pt + 1);
+        OuterResult R = solve_outer<SHAPE, XFORM>(tv, S, px, py);
+        double gx, gy;
+        grad_prel<SHAPE, XFORM>(tv, S, px, py, R.tstar, gx, gy);
+        my_evals += (unsigned long long)R.evals + 4ull;
+        const bool inside = A.want_gsip && !(R.sdf > 0);  // getTrueSDFofSweptVolume: `if (argmin_dis > 0) return`
+        if (lane == 0) {
+            if (A.out_sdf) A.out_sdf[pt] = R.sdf;
+            if (A.out_tstar) A.out_tstar[pt] = R.tstar;
+            if (A.out_grad) { A.out_grad[3 * pt] = gx; A.out_grad[3 * pt + 1] = gy; A.out_grad[3 * pt + 2] = 0.0; }
+            if (A.out_rounds) A.out_rounds[pt] = 0;
+            if (A.inside_flag) A.inside_flag[pt] = inside ? 1 : 0;
+            if (inside && A.inside_tstar) A.inside_tstar[pt] = R.tstar;
+        }
+        if (A.want_reduce && !inside) {
+            Contribution C = point_contribution(tv, A.cp, px, py, R.sdf, R.tstar, gx, gy);
+            if (C.active) {
+                if (lane < 18) {
+                    int d = lane / 6, q = lane - 6 * d;
+                    double s1 = C.s1, s2 = s1 * s1, s3 = s2 * s1, s4 = s2 * s2, s5 = s4 * s1;
+                    double beta = (q == 0) ? 1.0 : (q == 1) ? s1 : (q == 2) ? s2 : (q == 3) ? s3 : (q == 4) ? s4 : s5;
+                    acc[C.piece * 18 + lane] += beta * C.G[d];
+                } else if (lane == 18) {
+                    acc[18 * tv.N + C.piece] += C.gdT;
+                } else if (lane == 19) {
+                    acc[19 * tv.N] += C.pena;
+                }
+                __syncwarp();
+            }
+        }
+    }
+    if (A.eval_counter && lane == 0) atomicAdd(A.eval_counter, my_evals);
+    if (A.want_reduce) {
+        __syncthreads();
+        const double *acc0 = smem + A.blob_doubles;
+        for (int e = threadIdx.x; e < nacc; e += blockDim.x) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < kWarpsPerBlock; ++w) s += acc0[w * nacc + e];
+            A.partials[(int64_t)blockIdx.x * nacc + e] = s;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_compact: ordered compaction of the inside flags (single CTA, 1024 threads) -> inside_list, n_inside
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_compact(const unsigned char *flag, int64_t P, int *list, int *n_out) {
+    __shared__ int wsum[32];
+    __shared__ int total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t chunk = (P + 1023) / 1024;
+    const int64_t beg = (int64_t)tid * chunk, end = (beg + chunk < P) ? beg + chunk : P;
+    int cnt = 0;
+    for (int64_t i = beg; i < end; ++i) cnt += flag[i] ? 1 : 0;
+    int inc = cnt;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        int v = __shfl_up_sync(FULL, inc, off);
+        if (lane >= off) inc += v;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int v = wsum[lane];
+        int vi = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            int u = __shfl_up_sync(FULL, vi, off);
+            if (lane >= off) vi += u;
+        }
+        wsum[lane] = vi - v;  // exclusive
+        if (lane == 31) total = vi;
+    }
+    __syncthreads();
+    int pos = wsum[warp] + inc - cnt;
+    for (int64_t i = beg; i < end; ++i)
+        if (flag[i]) list[pos++] = (int)i;
+    if (tid == 0) *n_out = total;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: interior branch of getTrueSDFofSweptVolume<true> (sw_manager.hpp:926-1017, SampleSet2D :41-124).
+// One CTA per inside point; the ring samples of a round are distributed over the CTA's warps, each warp
+// running a full outer solve on its sample.
+// dynamic smem: [ blob ]
+// ------------------------------------------------------------------------------------------------
+template <int SHAPE, bool XFORM>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+    k_gsip(const __grid_constant__ KernelArgs A, const __grid_constant__ ShapeParams S) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ double s_theta[24], s_val[24], s_ts[24];
+    double *sblob = smem;
+    tma_load_blob(sblob, A.blob, A.blob_doubles, &bar);
+    const TrajView tv = make_view(sblob);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double PI = 3.14159265358979323846;  // Shape.hpp:31
+    const int n_in = *A.n_inside;
+    unsigned long long my_evals = 0;
+
+    for (int slot = blockIdx.x; slot < n_in; slot += gridDim.x) {
+        const int pt = A.inside_list[slot];
+        const double px = __ldg(A.points_xy + 2 * (int64_t)pt), py = __ldg(A.points_xy + 2 * (int64_t)pt + 1);
+        const double ts0 = A.inside_tstar[pt];
+        // velocity at t* with the reference's fallback scan (:928-954); all threads redundantly
+        double vx, vy, vw;
+        traj_vel(tv, ts0, vx, vy, vw);
+        if (sqrt(vx * vx + vy * vy + vw * vw) < 0.01) {
+            if (ts0 < 0.1) {
+                for (double t_scan = ts0; t_scan <= tv.D; t_scan += 0.1) {
+                    traj_vel(tv, t_scan, vx, vy, vw);
+                    if (sqrt(vx * vx + vy * vy + vw * vw) >= 0.01) break;
+                }
+            } else if (ts0 > tv.D - 0.1) {
+                for (double t_scan = ts0; t_scan >= 0; t_scan -= 0.1) {
+                    traj_vel(tv, t_scan, vx, vy, vw);
+                    if (sqrt(vx * vx + vy * vy + vw * vw) >= 0.01) break;
+                }
+            }
+        }
+        // SampleSet2D::initSet (:74-103)
+        double r = 10.0;
+        double theta0 = atan2(vx, -vy);
+        if (theta0 < 0) theta0 += 2 * PI;
+        double theta_res = PI + 0.1;
+        double r_star = 0.0, real_t_star = 0.0, star_theta = 0.0;
+        int iter = 1, rounds = 0;
+        while (true) {
+            // getElements (:59-71): one ring (rk = 1.0), theta accumulated from theta0 while < theta0 + 2 PI
+            int ns = 0;
+            for (double th = theta0; th < theta0 + 2 * PI; th += theta_res) {
+                if (threadIdx.x == 0 && ns < 24) s_theta[ns] = th;
+                ns++;
+            }
+            if (ns > 24) ns = 24;  // cannot happen: theta_res >= 0.3 -> at most 21 samples
+            __syncthreads();
+            for (int k = warp; k < ns; k += kWarpsPerBlock) {
+                double th = s_theta[k];
+                double sn, cs;
+                sincos(th, &sn, &cs);
+                double yx = px + 1.0 * r * cs, yy = py + 1.0 * r * sn;  // CircleCoord2D::getPosition (:36-39)
+                OuterResult R = solve_outer<SHAPE, XFORM>(tv, S, yx, yy);
+                my_evals += (unsigned long long)R.evals;
+                if (lane == 0) { s_val[k] = R.sdf; s_ts[k] = R.tstar; }
+            }
+            __syncthreads();
+            double max_g = -100000;
+            for (int k = 0; k < ns; ++k) {
+                double cur = s_val[k];
+                if (cur > max_g) {
+                    max_g = cur;
+                    real_t_star = s_ts[k];
+                    star_theta = s_theta[k];
+                }
+            }
+            __syncthreads();  // everyone has read s_* before the next round overwrites them
+            r_star = r - max_g;
+            r = r_star;
+            rounds++;
+            if (iter > 8) break;
+            if (fabs(max_g) < 0.1) break;
+            theta_res /= (2 + 1);  // expandSet(2, theta*) (:105-123)
+            theta_res = fmax(0.3, theta_res);
+            theta0 = star_theta;
+            iter++;
+        }
+        double sn, cs;
+        sincos(star_theta, &sn, &cs);
+        double corx = px + 1.0 * r_star * cs, cory = py + 1.0 * r_star * sn;
+        double gx = corx - px, gy = cory - py;
+        double z = gx * gx + gy * gy;
+        if (z > 0) {
+            double n = sqrt(z);
+            gx /= n; gy /= n;
+        }
+        const double sdf = -r_star;
+        if (threadIdx.x == 0) {
+            if (A.out_sdf) A.out_sdf[pt] = sdf;
+            if (A.out_tstar) A.out_tstar[pt] = real_t_star;
+            if (A.out_grad) { A.out_grad[3 * pt] = gx; A.out_grad[3 * pt + 1] = gy; A.out_grad[3 * pt + 2] = 0.0; }
+            if (A.out_rounds) A.out_rounds[pt] = rounds;
+        }
+        if (A.want_reduce && warp == 0) {
+            Contribution C = point_contribution(tv, A.cp, px, py, sdf, real_t_star, gx, gy);
+            double *o = A.gsip_contrib + 20 * (int64_t)slot;
+            if (lane < 18) {
+                int d = lane / 6, q = lane - 6 * d;
+                double s1 = C.s1, s2 = s1 * s1, s3 = s2 * s1, s4 = s2 * s2, s5 = s4 * s1;
+                double beta = (q == 0) ? 1.0 : (q == 1) ? s1 : (q == 2) ? s2 : (q == 3) ? s3 : (q == 4) ? s4 : s5;
+                o[1 + lane] = C.active ? beta * C.G[d] : 0.0;
+            } else if (lane == 18) {
+                o[19] = C.active ? C.gdT : 0.0;
+            } else if (lane == 19) {
+                o[0] = C.active ? C.pena : 0.0;
+                A.gsip_piece[slot] = C.piece;
+            }
+        }
+    }
+    if (A.eval_counter && lane == 0) atomicAdd(A.eval_counter, my_evals);
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_finalize: fixed-order sum of the K1 CTA partials and the K2 per-point contributions.
+// out: [0] cost, [1 .. 18N] gradC in Eigen column-major order (d*6N + 6i + q), [1+18N .. 1+19N) gradT with the
+// reference's rule gradT(j) += gdT for all j < piece (back_end_optimizer.hpp:859-862), [1+19N] n_inside.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_finalize(const double *partials, int n_blocks, int N, const int *n_inside,
+                                                  const double *gsip_contrib, const int *gsip_piece, double *out) {
+    extern __shared__ double sred[];  // 19N + 1 totals in accumulator order
+    const int nacc = 19 * N + 1;
+    const int n_in = n_inside ? *n_inside : 0;
+    for (int e = threadIdx.x; e < nacc; e += blockDim.x) {
+        double s = 0.0;
+        for (int b = 0; b < n_blocks; ++b) s += partials[(int64_t)b * nacc + e];
+        // K2 contributions, in ascending point order (inside_list is sorted)
+        if (e < 18 * N) {
+            int piece = e / 18, within = e - 18 * piece;
+            for (int k = 0; k < n_in; ++k)
+                if (gsip_piece[k] == piece) s += gsip_contrib[20 * (int64_t)k + 1 + within];
+        } else if (e < 19 * N) {
+            int piece = e - 18 * N;
+            for (int k = 0; k < n_in; ++k)
+                if (gsip_piece[k] == piece) s += gsip_contrib[20 * (int64_t)k + 19];
+        } else {
+            for (int k = 0; k < n_in; ++k) s += gsip_contrib[20 * (int64_t)k];
+        }
+        sred[e] = s;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nacc; e += blockDim.x) {
+        if (e < 18 * N) {
+            int piece = e / 18, within = e - 18 * piece;
+            int d = within / 6, q = within - 6 * d;
+            out[1 + d * 6 * N + 6 * piece + q] = sred[e];
+        } else if (e < 19 * N) {
+            int j = e - 18 * N;
+            double s = 0.0;
+            for (int i = j + 1; i < N; ++i) s += sred[18 * N + i];
+            out[1 + 18 * N + j] = s;
+        } else {
+            out[0] = sred[e];
+        }
+    }
+    if (threadIdx.x == 0) out[1 + 19 * N] = (double)n_in;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Shape-functor batch kernels (BasicShape::getonlySDF / getonlyGrad1 over arrays of body-frame points)
+// ------------------------------------------------------------------------------------------------
+template <int SHAPE, bool XFORM>
+__global__ void k_shape_sdf(const __grid_constant__ ShapeParams S, const double *rel_xy, int64_t n, double *out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = dev::shape_sdf<SHAPE, XFORM>(S, rel_xy[2 * i], rel_xy[2 * i + 1]);
+}
+template <int SHAPE, bool XFORM>
+__global__ void k_shape_grad(const __grid_constant__ ShapeParams S, const double *rel_xy, int64_t n, double *out3) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double rx = rel_xy[2 * i], ry = rel_xy[2 * i + 1];
+    double gx, gy;
+    if (SHAPE == SH_POLYGON) {
+        dev::PolyHit H = dev::polygon_scan(S, rx, ry);
+        double vx = rx - H.cx, vy = ry - H.cy;
+        double z = vx * vx + vy * vy;
+        if (z > 0.0) { double nn = sqrt(z); vx /= nn; vy /= nn; }
+        if (H.rs % 2 != 0) { vx = -vx; vy = -vy; }
+        gx = vx; gy = vy;
+    } else {
+        const double dx = 0.000001;
+        double t0 = rx, t1 = ry;
+        t0 -= dx;
+        double sdfold = dev::shape_sdf<SHAPE, XFORM>(S, t0, t1);
+        t0 += 2 * dx;
+        double gradx = dev::shape_sdf<SHAPE, XFORM>(S, t0, t1) - sdfold;
+        t0 = rx;
+        t1 -= dx;
+        sdfold = dev::shape_sdf<SHAPE, XFORM>(S, t0, t1);
+        t1 += 2 * dx;
+        double grady = dev::shape_sdf<SHAPE, XFORM>(S, t0, t1) - sdfold;
+        gx = gradx / (2 * dx);
+        gy = grady / (2 * dx);
+    }
+    out3[3 * i] = gx; out3[3 * i + 1] = gy; out3[3 * i + 2] = 0.0;
+}
+
+// FP64 FMA peak micro-benchmark (roofline denominator; MEASURED_PEAKS.json has no FP64 figure)
+__global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-6;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host-side launchers (shape dispatch)
+// ------------------------------------------------------------------------------------------------
+struct LaunchCfg {
+    int grid_outer, grid_gsip;
+    size_t smem_outer, smem_gsip;
+    cudaStream_t stream;
+};
+
+template <int SHAPE, bool XFORM>
+static cudaError_t launch_shape(const KernelArgs &A, const ShapeParams &S, const LaunchCfg &cfg, int N) {
+    cudaError_t e;
+    static bool attr_set = false;
+    if (!attr_set) {
+        e = cudaFuncSetAttribute(k_outer<SHAPE, XFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_gsip<SHAPE, XFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    k_outer<SHAPE, XFORM><<<cfg.grid_outer, kWarpsPerBlock * 32, cfg.smem_outer, cfg.stream>>>(A, S);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (A.want_gsip) {
+        k_compact<<<1, 1024, 0, cfg.stream>>>(A.inside_flag, A.P, A.inside_list, A.n_inside);
+        k_gsip<SHAPE, XFORM><<<cfg.grid_gsip, kWarpsPerBlock * 32, cfg.smem_gsip, cfg.stream>>>(A, S);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    (void)N;
+    return cudaSuccess;
+}
+
+template <bool XFORM>
+static cudaError_t dispatch(const KernelArgs &A, const ShapeParams &S, const LaunchCfg &cfg, int N) {
+    switch (S.id) {
+#define SVSDF_CASE(ID) \
+    case ID: return launch_shape<ID, XFORM>(A, S, cfg, N);
+        SVSDF_CASE(SH_STAR)
+        SVSDF_CASE(SH_HORSESHOE)
+        SVSDF_CASE(SH_PIE)
+        SVSDF_CASE(SH_PIE2)
+        SVSDF_CASE(SH_ARC)
+        SVSDF_CASE(SH_TUNNEL)
+        SVSDF_CASE(SH_CUTDISK)
+        SVSDF_CASE(SH_TRAPEZOID)
+        SVSDF_CASE(SH_RHOMBUS)
+        SVSDF_CASE(SH_HEART)
+        SVSDF_CASE(SH_ROUNDEDX)
+        SVSDF_CASE(SH_BIGX)
+        SVSDF_CASE(SH_ROUNDEDCROSS)
+        SVSDF_CASE(SH_VESICA)
+        SVSDF_CASE(SH_MOON)
+        SVSDF_CASE(SH_UNEVENCAPSULE)
+        SVSDF_CASE(SH_CIRCLE)
+#undef SVSDF_CASE
+        case SH_POLYGON: return launch_shape<SH_POLYGON, false>(A, S, cfg, N);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_pose_table(double *blob, int K1, cudaStream_t stream) {
+    k_pose_table<<<(K1 + 127) / 128, 128, 0, stream>>>(blob);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_cost_kernels(const KernelArgs &A, const ShapeParams &S, int N, int grid_outer, int grid_gsip,
+                                cudaStream_t stream) {
+    LaunchCfg cfg;
+    cfg.grid_outer = grid_outer;
+    cfg.grid_gsip = grid_gsip;
+    cfg.smem_outer = (size_t)(A.blob_doubles + kWarpsPerBlock * (19 * N + 1)) * sizeof(double);
+    cfg.smem_gsip = (size_t)A.blob_doubles * sizeof(double);
+    cfg.stream = stream;
+    return S.has_xform ? dispatch<true>(A, S, cfg, N) : dispatch<false>(A, S, cfg, N);
+}
+
+cudaError_t launch_finalize(const double *partials, int n_blocks, int N, const int *n_inside,
+                            const double *gsip_contrib, const int *gsip_piece, double *out, cudaStream_t stream) {
+    k_finalize<<<1, 256, (19 * N + 1) * sizeof(double), stream>>>(partials, n_blocks, N, n_inside, gsip_contrib,
+                                                                 gsip_piece, out);
+    return cudaGetLastError();
+}
+
+template <int SHAPE, bool XFORM>
+static cudaError_t launch_shape_fn(const ShapeParams &S, const double *rel_xy, int64_t n, double *out, int grad,
+                                   cudaStream_t stream) {
+    int grid = (int)((n + 255) / 256);
+    if (grad) k_shape_grad<SHAPE, XFORM><<<grid, 256, 0, stream>>>(S, rel_xy, n, out);
+    else k_shape_sdf<SHAPE, XFORM><<<grid, 256, 0, stream>>>(S, rel_xy, n, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_shape_eval(const ShapeParams &S, const double *rel_xy, int64_t n, double *out, int grad,
+                              cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    switch (S.id) {
+#define SVSDF_CASE(ID)                                                                              \
+    case ID:                                                                                        \
+        return S.has_xform ? launch_shape_fn<ID, true>(S, rel_xy, n, out, grad, stream)             \
+                           : launch_shape_fn<ID, false>(S, rel_xy, n, out, grad, stream);
+        SVSDF_CASE(SH_STAR)
+        SVSDF_CASE(SH_HORSESHOE)
+        SVSDF_CASE(SH_PIE)
+        SVSDF_CASE(SH_PIE2)
+        SVSDF_CASE(SH_ARC)
+        SVSDF_CASE(SH_TUNNEL)
+        SVSDF_CASE(SH_CUTDISK)
+        SVSDF_CASE(SH_TRAPEZOID)
+        SVSDF_CASE(SH_RHOMBUS)
+        SVSDF_CASE(SH_HEART)
+        SVSDF_CASE(SH_ROUNDEDX)
+        SVSDF_CASE(SH_BIGX)
+        SVSDF_CASE(SH_ROUNDEDCROSS)
+        SVSDF_CASE(SH_VESICA)
+        SVSDF_CASE(SH_MOON)
+        SVSDF_CASE(SH_UNEVENCAPSULE)
+        SVSDF_CASE(SH_CIRCLE)
+#undef SVSDF_CASE
+        case SH_POLYGON: return launch_shape_fn<SH_POLYGON, false>(S, rel_xy, n, out, grad, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_fp64_peak(double *out, int grid, int iters, cudaStream_t stream) {
+    k_fp64_peak<<<grid, 256, 0, stream>>>(out, iters);
+    return cudaGetLastError();
+}
+
+// occupancy query used by the host to size the grids (CTAs per SM for k_outer of this shape is not needed to be
+// exact: we size for 2 resident CTAs per SM and let the hardware queue the rest)
+
+}  // namespace SVSDF_NS
+}  // namespace svsdf

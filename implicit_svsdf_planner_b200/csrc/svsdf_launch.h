@@ -1,0 +1,24 @@
+// svsdf_launch.h — host-callable launchers exported by the two kernel translation units
+// (svsdf_kernels_fast.cu: FMA contraction on; svsdf_kernels_strict.cu: -fmad=false).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "svsdf_types.h"
+
+namespace svsdf {
+#define SVSDF_DECLARE_LAUNCHERS(NS)                                                                              \
+    namespace NS {                                                                                               \
+    cudaError_t launch_pose_table(double *blob, int K1, cudaStream_t stream);                                    \
+    cudaError_t launch_cost_kernels(const KernelArgs &A, const ShapeParams &S, int N, int grid_outer,            \
+                                    int grid_gsip, cudaStream_t stream);                                         \
+    cudaError_t launch_finalize(const double *partials, int n_blocks, int N, const int *n_inside,                \
+                                const double *gsip_contrib, const int *gsip_piece, double *out,                  \
+                                cudaStream_t stream);                                                            \
+    cudaError_t launch_shape_eval(const ShapeParams &S, const double *rel_xy, int64_t n, double *out, int grad,  \
+                                  cudaStream_t stream);                                                          \
+    cudaError_t launch_fp64_peak(double *out, int grid, int iters, cudaStream_t stream);                         \
+    }
+SVSDF_DECLARE_LAUNCHERS(fast)
+SVSDF_DECLARE_LAUNCHERS(strict)
+#undef SVSDF_DECLARE_LAUNCHERS
+}  // namespace svsdf

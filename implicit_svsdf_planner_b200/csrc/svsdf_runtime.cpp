@@ -1,0 +1,808 @@
+// svsdf_runtime.cpp — host runtime and C ABI (include/svsdf.h) of libsvsdf_b200.so.
+//
+// Owns the device buffers (query points resident in HBM, trajectory blob, per-CTA partials, inside-point lists),
+// the CUDA stream, pinned staging memory, the host MINCO spline and the host L-BFGS; launches the sm_100a kernels
+// of svsdf_kernels.cuh.  There is deliberately no CPU implementation of the hot path in this library: if CUDA is
+// unavailable svsdf_create fails.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/svsdf.h"
+#include "host/lbfgs.hpp"
+#include "host/minco.hpp"
+#include "svsdf_launch.h"
+#include "svsdf_types.h"
+
+using namespace svsdf;
+
+struct svsdf_ctx {
+    svsdf_config cfg;
+    std::string shape_name;
+    ShapeParams shape;
+    CostParams cp;
+    double rho = 3.8;
+    int device = 0;
+    bool strict = false;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    int64_t launches = 0;
+
+    // query points
+    double *d_points = nullptr;  // packed xy
+    bool own_points = true;
+    int64_t P = 0;
+    int64_t cap_points = 0;
+    // scratch sized by P
+    unsigned char *d_flag = nullptr;
+    double *d_inside_tstar = nullptr;
+    int *d_inside_list = nullptr;
+    double *d_gsip_contrib = nullptr;
+    int *d_gsip_piece = nullptr;
+    int64_t cap_scratch = 0;
+    int *d_n_inside = nullptr;
+    unsigned long long *d_eval_counter = nullptr;
+    bool count_evals = false;
+    // trajectory blob
+    double *d_blob = nullptr;
+    int cap_blob = 0;
+    double *h_blob = nullptr;  // pinned
+    int cap_hblob = 0;
+    BlobLayout layout{};
+    int traj_N = 0;
+    double traj_D = 0.0;
+    // reduction
+    double *d_partials = nullptr;
+    int64_t cap_partials = 0;
+    double *d_out = nullptr;  // 1 + 19N + 1
+    double *h_out = nullptr;  // pinned
+    int cap_out = 0;
+    // query scratch (per-point outputs)
+    double *d_q_points = nullptr, *d_q_sdf = nullptr, *d_q_ts = nullptr, *d_q_grad = nullptr;
+    int *d_q_rounds = nullptr;
+    int64_t cap_q = 0;
+    double *h_stage = nullptr;  // pinned staging for points upload / results download
+    size_t cap_stage = 0;
+
+    // optimiser state (R3/R4)
+    host::MincoS3NU minco;
+    int pieceN = 0;
+    bool have_boundary = false;
+    std::vector<double> times, gradByTimes, partialGradByTimes, partialGradByCoeffs, gradByPoints;
+    double cost_pos = 0, cost_other = 0, cost_total = 0;
+    int n_evaluate = 0;
+    double gpu_ms_total = 0.0;
+    bool time_kernels = false;
+    int last_status = 0;
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                        \
+            return SVSDF_ERR_CUDA;                                                                 \
+        }                                                                                          \
+    } while (0)
+
+const char *kShapeNames[] = {"star",      "sdHorseshoe", "sdPie",      "sdPie2", "sdArc",          "sdTunnel",
+                             "sdCutDisk", "sdTrapezoid", "sdRhombus",  "sdHeart", "sdRoundedX",    "bigX",
+                             "sdRoundedCross", "sdOrientedVesica", "sdMoon", "sdUnevenCapsule"};
+
+int shape_id_from_name(const char *name) {
+    if (name) {
+        for (int i = 0; i < 16; ++i)
+            if (std::strcmp(name, kShapeNames[i]) == 0) return i;
+        if (std::strcmp(name, "Circle") == 0) return SH_CIRCLE;
+    }
+    return SH_POLYGON;  // sw_manager.hpp:363-372
+}
+
+// Host-side construction of the shape functor parameters (what the reference's shape constructors do:
+// Shape.hpp:281-294 base transform, and the per-class constant members).
+void build_shape(const svsdf_config &cfg, ShapeParams &S) {
+    std::memset(&S, 0, sizeof(S));
+    S.id = shape_id_from_name(cfg.shape);
+    const double PI = 3.14159265358979323846;  // Shape.hpp:31
+    const double yaw = (cfg.poly_params[2] * PI / 180.0);
+    S.trans[0] = cfg.poly_params[0];
+    S.trans[1] = cfg.poly_params[1];
+    S.rot[0] = std::cos(yaw);
+    S.rot[1] = -std::sin(yaw);
+    S.rot[2] = std::sin(yaw);
+    S.rot[3] = std::cos(yaw);
+    S.has_xform = !(S.trans[0] == 0.0 && S.trans[1] == 0.0 && S.rot[0] == 1.0 && S.rot[1] == 0.0 && S.rot[2] == 0.0 &&
+                    S.rot[3] == 1.0);
+    S.radius = 1.0;
+    switch (S.id) {
+        case SH_HORSESHOE: S.cst[0] = std::cos(20.5); S.cst[1] = std::sin(20.5); break;  // Shape.hpp:855
+        case SH_PIE: S.cst[0] = std::cos(43.0); S.cst[1] = std::sin(43.0); break;        // :1235
+        case SH_PIE2: S.cst[0] = std::cos(1.0); S.cst[1] = std::sin(1.0); break;         // :1276
+        case SH_ARC: S.cst[0] = std::sin(20.0); S.cst[1] = std::cos(20.0); break;        // :1320
+        case SH_CUTDISK: S.cst[0] = std::sqrt(5.0 * 5.0 - 2.0 * 2.0); break;             // :701
+        case SH_HEART: S.cst[0] = std::sqrt(2.0) / 4.0; break;                           // :946
+        case SH_VESICA: {                                                                // :1119-1128
+            const double ax = 2, ay = 4, bx = -2, by = -4, w = 0.8;
+            const double bax = bx - ax, bay = by - ay;
+            const double r = 0.5 * std::sqrt(bax * bax + bay * bay);
+            S.cst[0] = r;
+            S.cst[1] = 0.5 * (r * r - w * w) / w;
+            S.cst[2] = bax / r;
+            S.cst[3] = bay / r;
+            break;
+        }
+        case SH_MOON: {  // :1205-1206
+            const double d = 0.8, ra = 3.0, rb = 2.4;
+            const double a = (ra * ra - rb * rb + d * d) / (2.0 * d);
+            S.cst[0] = a;
+            S.cst[1] = std::sqrt(std::max(ra * ra - a * a, 0.0));
+            break;
+        }
+        case SH_UNEVENCAPSULE: {  // :535-536
+            const double b = (2.0 - 1.0) / 5.0;
+            S.cst[0] = b;
+            S.cst[1] = std::sqrt(1.0 - b * b);
+            break;
+        }
+        case SH_POLYGON: {
+            const double rect[8] = {6, -0.1, 6, 0.1, -6, 0.1, -6, -0.1};  // sw_manager.hpp:365-369
+            const double *xy = rect;
+            int n = 4;
+            if (cfg.polygon_xy && cfg.polygon_n >= 3 && cfg.polygon_n <= kMaxPolyEdges) {
+                xy = cfg.polygon_xy;
+                n = cfg.polygon_n;
+            }
+            S.poly_n = n;
+            for (int i = 0; i < n; ++i) {  // Polygon ctor, Shape.hpp:1429-1446
+                const int j = (i + 1) % n;
+                S.poly_sx[i] = xy[2 * i];
+                S.poly_sy[i] = xy[2 * i + 1];
+                S.poly_ex[i] = xy[2 * j];
+                S.poly_ey[i] = xy[2 * j + 1];
+            }
+            S.has_xform = 0;
+            break;
+        }
+        default: break;
+    }
+}
+
+int ensure_scratch(svsdf_ctx *ctx, int64_t P) {
+    if (P <= ctx->cap_scratch) return SVSDF_OK;
+    cudaFree(ctx->d_flag); cudaFree(ctx->d_inside_tstar); cudaFree(ctx->d_inside_list);
+    cudaFree(ctx->d_gsip_contrib); cudaFree(ctx->d_gsip_piece);
+    ctx->d_flag = nullptr; ctx->d_inside_tstar = nullptr; ctx->d_inside_list = nullptr;
+    ctx->d_gsip_contrib = nullptr; ctx->d_gsip_piece = nullptr;
+    ctx->cap_scratch = 0;
+    int64_t cap = P + P / 8 + 1024;
+    CK(cudaMalloc(&ctx->d_flag, cap));
+    CK(cudaMalloc(&ctx->d_inside_tstar, cap * sizeof(double)));
+    CK(cudaMalloc(&ctx->d_inside_list, cap * sizeof(int)));
+    CK(cudaMalloc(&ctx->d_gsip_contrib, cap * 20 * sizeof(double)));
+    CK(cudaMalloc(&ctx->d_gsip_piece, cap * sizeof(int)));
+    ctx->cap_scratch = cap;
+    return SVSDF_OK;
+}
+
+int ensure_stage(svsdf_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->cap_stage) return SVSDF_OK;
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    ctx->h_stage = nullptr;
+    ctx->cap_stage = 0;
+    size_t cap = bytes + bytes / 4 + 4096;
+    CK(cudaMallocHost(&ctx->h_stage, cap));
+    ctx->cap_stage = cap;
+    return SVSDF_OK;
+}
+
+// updateTraj (sw_manager.hpp:376-385) + the layer-1 lattice of choiceTInit (:538-581): builds the blob in
+// pinned memory, uploads it and launches the pose-table kernel.
+int upload_traj(svsdf_ctx *ctx, int N, const double *T, const double *coeffs) {
+    if (N < 1 || N > kMaxPieces || !T || !coeffs) {
+        ctx->err = "svsdf: N out of range (1..64) or null trajectory";
+        return SVSDF_ERR_INVALID;
+    }
+    double D = 0.0;  // Trajectory::getTotalDuration (trajectory.hpp:410-419)
+    for (int i = 0; i < N; ++i) {
+        if (!(T[i] > 0.0) || !std::isfinite(T[i])) {
+            ctx->err = "svsdf: non-positive or non-finite piece duration";
+            return SVSDF_ERR_INVALID;
+        }
+        D += T[i];
+    }
+    if (!(D < kMaxDuration)) {
+        // The reference silently keeps the previous duration in this case (sw_manager.hpp:380); we refuse.
+        ctx->err = "svsdf: total duration >= 300 s is not supported (reference updateTraj ignores it)";
+        return SVSDF_ERR_INVALID;
+    }
+    // layer-1 lattice: for (t = 0; t <= D; t += 0.15)
+    int K1 = 0;
+    for (double t = 0.0; t <= D; t += 0.15) K1++;
+    BlobLayout L = blob_layout(N, K1);
+    if (L.total > ctx->cap_hblob) {
+        if (ctx->h_blob) cudaFreeHost(ctx->h_blob);
+        ctx->h_blob = nullptr;
+        ctx->cap_hblob = 0;
+        CK(cudaMallocHost(&ctx->h_blob, (size_t)(L.total + 1024) * sizeof(double)));
+        ctx->cap_hblob = L.total + 1024;
+    }
+    if (L.total > ctx->cap_blob) {
+        cudaFree(ctx->d_blob);
+        ctx->d_blob = nullptr;
+        ctx->cap_blob = 0;
+        CK(cudaMalloc(&ctx->d_blob, (size_t)(L.total + 1024) * sizeof(double)));
+        ctx->cap_blob = L.total + 1024;
+    }
+    double *h = ctx->h_blob;
+    std::memset(h, 0, (size_t)L.off_pose * sizeof(double));
+    h[0] = (double)N;
+    h[1] = (double)K1;
+    h[2] = D;
+    for (int i = 0; i < N; ++i) h[L.off_T + i] = T[i];
+    // coefficients: MINCO b (col-major 6N x 3) -> [piece][dim][power]  (minco.hpp:515-528 builds the same
+    // per-piece matrices, stored there highest power first)
+    for (int i = 0; i < N; ++i)
+        for (int d = 0; d < 3; ++d)
+            for (int k = 0; k < 6; ++k) h[L.off_c + 18 * i + 6 * d + k] = coeffs[(size_t)d * 6 * N + 6 * i + k];
+    {
+        int k = 0;
+        for (double t = 0.0; t <= D; t += 0.15) h[L.off_lat + k++] = t;
+    }
+    CK(cudaMemcpyAsync(ctx->d_blob, h, (size_t)L.off_pose * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    cudaError_t e = ctx->strict ? strict::launch_pose_table(ctx->d_blob, K1, ctx->stream)
+                                : fast::launch_pose_table(ctx->d_blob, K1, ctx->stream);
+    CK(e);
+    ctx->launches += 1;
+    ctx->layout = L;
+    ctx->traj_N = N;
+    ctx->traj_D = D;
+    return SVSDF_OK;
+}
+
+int grid_for(const svsdf_ctx *ctx, int64_t P) {
+    // one warp per point, 8 warps per CTA; cap the grid at 4 CTAs per SM worth of resident work so each warp
+    // strides over many points (load balance) and the number of partials stays small.
+    int64_t need = (P + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    int64_t cap = (int64_t)ctx->sm_count * 4;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+// Runs K1 (+compact, K2) (+finalize).  Inputs resident on the device.
+int run_kernels(svsdf_ctx *ctx, const double *d_points, int64_t P, bool reduce, bool gsip, double *o_sdf,
+                double *o_ts, double *o_grad, int *o_rounds) {
+    const int N = ctx->traj_N;
+    int rc = ensure_scratch(ctx, P);
+    if (rc) return rc;
+    const int grid = grid_for(ctx, P);
+    const int nacc = 19 * N + 1;
+    if (reduce) {
+        int64_t need = (int64_t)grid * nacc;
+        if (need > ctx->cap_partials) {
+            cudaFree(ctx->d_partials);
+            ctx->d_partials = nullptr;
+            ctx->cap_partials = 0;
+            CK(cudaMalloc(&ctx->d_partials, (size_t)(need + 4096) * sizeof(double)));
+            ctx->cap_partials = need + 4096;
+        }
+        if (nacc + 1 > ctx->cap_out) {
+            cudaFree(ctx->d_out);
+            if (ctx->h_out) cudaFreeHost(ctx->h_out);
+            ctx->d_out = nullptr; ctx->h_out = nullptr; ctx->cap_out = 0;
+            CK(cudaMalloc(&ctx->d_out, (size_t)(nacc + 64) * sizeof(double)));
+            CK(cudaMallocHost(&ctx->h_out, (size_t)(nacc + 64) * sizeof(double)));
+            ctx->cap_out = nacc + 64;
+        }
+    }
+    KernelArgs A;
+    std::memset(&A, 0, sizeof(A));
+    A.blob = ctx->d_blob;
+    A.blob_doubles = ctx->layout.total;
+    A.points_xy = d_points;
+    A.P = P;
+    A.cp = ctx->cp;
+    A.out_sdf = o_sdf; A.out_tstar = o_ts; A.out_grad = o_grad; A.out_rounds = o_rounds;
+    A.partials = ctx->d_partials;
+    A.want_reduce = reduce ? 1 : 0;
+    A.want_gsip = gsip ? 1 : 0;
+    A.inside_flag = ctx->d_flag;
+    A.inside_tstar = ctx->d_inside_tstar;
+    A.inside_list = ctx->d_inside_list;
+    A.n_inside = ctx->d_n_inside;
+    A.gsip_contrib = ctx->d_gsip_contrib;
+    A.gsip_piece = ctx->d_gsip_piece;
+    A.eval_counter = ctx->count_evals ? ctx->d_eval_counter : nullptr;
+    const int grid_gsip = ctx->sm_count * 2;
+    if (!gsip) CK(cudaMemsetAsync(ctx->d_n_inside, 0, sizeof(int), ctx->stream));
+    size_t smem = (size_t)(A.blob_doubles + kWarpsPerBlock * nacc) * sizeof(double);
+    if (smem > 200 * 1024) {
+        ctx->err = "svsdf: trajectory blob does not fit in shared memory";
+        return SVSDF_ERR_INVALID;
+    }
+    cudaError_t e = ctx->strict ? strict::launch_cost_kernels(A, ctx->shape, N, grid, grid_gsip, ctx->stream)
+                                : fast::launch_cost_kernels(A, ctx->shape, N, grid, grid_gsip, ctx->stream);
+    CK(e);
+    ctx->launches += gsip ? 3 : 1;
+    if (reduce) {
+        e = ctx->strict ? strict::launch_finalize(ctx->d_partials, grid, N, ctx->d_n_inside, ctx->d_gsip_contrib,
+                                                  ctx->d_gsip_piece, ctx->d_out, ctx->stream)
+                        : fast::launch_finalize(ctx->d_partials, grid, N, ctx->d_n_inside, ctx->d_gsip_contrib,
+                                                ctx->d_gsip_piece, ctx->d_out, ctx->stream);
+        CK(e);
+        ctx->launches += 1;
+    }
+    return SVSDF_OK;
+}
+
+// R1 on the context's points; result (1 + 19N + 1 doubles) lands in ctx->h_out after the stream sync.
+int cost_grad_raw(svsdf_ctx *ctx, int N, const double *T, const double *coeffs) {
+    if (!ctx->d_points || ctx->P < 0) {
+        ctx->err = "svsdf: query points not set";
+        return SVSDF_ERR_NOT_READY;
+    }
+    int rc = upload_traj(ctx, N, T, coeffs);
+    if (rc) return rc;
+    if (ctx->time_kernels) CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    rc = run_kernels(ctx, ctx->d_points, ctx->P, true, true, nullptr, nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    if (ctx->time_kernels) CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    const int nout = 1 + 19 * N + 1;
+    CK(cudaMemcpyAsync(ctx->h_out, ctx->d_out, (size_t)nout * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->time_kernels) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->gpu_ms_total += ms;
+    }
+    return SVSDF_OK;
+}
+
+double evaluate_impl(svsdf_ctx *ctx, const double *x, double *g, int n) {
+    const int N = ctx->pieceN;
+    if (!ctx->have_boundary || n != N + 3 * (N - 1)) {
+        ctx->err = "svsdf_evaluate: boundary conditions not set or wrong n";
+        ctx->last_status = SVSDF_ERR_NOT_READY;
+        return NAN;
+    }
+    ctx->n_evaluate++;
+    // forwardT / forwardP (back_end_optimizer.hpp:353-354)
+    for (int i = 0; i < N; ++i) ctx->times[i] = host::forwardT(x[i]);
+    const double *q = x + N;
+    ctx->minco.setParameters(q, ctx->times.data());
+    double cost = ctx->minco.getEnergy();
+    ctx->minco.getEnergyPartialGradByCoeffs(ctx->partialGradByCoeffs.data());
+    ctx->minco.getEnergyPartialGradByTimes(ctx->partialGradByTimes.data());
+    const double energy_cost = cost;
+    int rc = cost_grad_raw(ctx, N, ctx->times.data(), ctx->minco.getCoeffs());
+    if (rc) {
+        ctx->last_status = rc;
+        return NAN;
+    }
+    const double *o = ctx->h_out;
+    cost += o[0];
+    for (int e = 0; e < 18 * N; ++e) ctx->partialGradByCoeffs[e] += o[1 + e];
+    for (int i = 0; i < N; ++i) ctx->partialGradByTimes[i] += o[1 + 18 * N + i];
+    const double pos_cost = cost - energy_cost;
+    ctx->minco.propogateGrad(ctx->partialGradByCoeffs.data(), ctx->partialGradByTimes.data(),
+                             ctx->gradByPoints.data(), ctx->gradByTimes.data());
+    double tsum = 0.0;
+    for (int i = 0; i < N; ++i) tsum += ctx->times[i];
+    cost += ctx->rho * tsum;
+    for (int i = 0; i < N; ++i) ctx->gradByTimes[i] += ctx->rho;
+    ctx->cost_pos = pos_cost;
+    ctx->cost_other = cost - pos_cost;
+    ctx->cost_total = cost;
+    for (int i = 0; i < N; ++i) g[i] = host::backwardGradT(x[i], ctx->gradByTimes[i]);
+    for (int i = 0; i < 3 * (N - 1); ++i) g[N + i] = ctx->gradByPoints[i];
+    ctx->last_status = SVSDF_OK;
+    return cost;
+}
+
+}  // namespace
+
+extern "C" {
+
+void svsdf_default_config(svsdf_config *cfg) {
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->shape = "star";
+    cfg->weight_p = 60.0;
+    cfg->safety_hor = 0.7;
+    cfg->rho = 3.8;
+}
+
+int svsdf_shape_id(const char *name) { return shape_id_from_name(name); }
+
+int svsdf_create(const svsdf_config *cfg, svsdf_ctx **out) {
+    if (!cfg || !out) return SVSDF_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return SVSDF_ERR_CUDA;  // no CPU fallback
+    if (cfg->device < 0 || cfg->device >= ndev) return SVSDF_ERR_INVALID;
+    if (cfg->polygon_xy && (cfg->polygon_n < 3 || cfg->polygon_n > kMaxPolyEdges)) return SVSDF_ERR_INVALID;
+    svsdf_ctx *ctx = new svsdf_ctx();
+    ctx->cfg = *cfg;
+    ctx->shape_name = cfg->shape ? cfg->shape : "";
+    ctx->cfg.shape = ctx->shape_name.c_str();
+    build_shape(*cfg, ctx->shape);
+    ctx->cp.weight_p = cfg->weight_p;
+    ctx->cp.safety_hor = cfg->safety_hor;
+    ctx->rho = cfg->rho;
+    ctx->device = cfg->device;
+    ctx->strict = cfg->strict_fp != 0;
+    auto fail = [&](cudaError_t e) {
+        std::fprintf(stderr, "svsdf_create: %s\n", cudaGetErrorString(e));
+        svsdf_destroy(ctx);
+        return SVSDF_ERR_CUDA;
+    };
+    cudaError_t e;
+    if ((e = cudaSetDevice(ctx->device)) != cudaSuccess) return fail(e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, ctx->device)) != cudaSuccess) return fail(e);
+    if (prop.major < 10) {
+        std::fprintf(stderr, "svsdf_create: device sm_%d%d is not Blackwell (kernels are built for sm_100a only)\n",
+                     prop.major, prop.minor);
+        svsdf_destroy(ctx);
+        return SVSDF_ERR_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e);
+    if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return fail(e);
+    if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return fail(e);
+    if ((e = cudaMalloc(&ctx->d_n_inside, sizeof(int))) != cudaSuccess) return fail(e);
+    if ((e = cudaMalloc(&ctx->d_eval_counter, sizeof(unsigned long long))) != cudaSuccess) return fail(e);
+    cudaMemset(ctx->d_n_inside, 0, sizeof(int));
+    cudaMemset(ctx->d_eval_counter, 0, sizeof(unsigned long long));
+    *out = ctx;
+    return SVSDF_OK;
+}
+
+void svsdf_destroy(svsdf_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->own_points) cudaFree(ctx->d_points);
+    cudaFree(ctx->d_flag); cudaFree(ctx->d_inside_tstar); cudaFree(ctx->d_inside_list);
+    cudaFree(ctx->d_gsip_contrib); cudaFree(ctx->d_gsip_piece); cudaFree(ctx->d_n_inside);
+    cudaFree(ctx->d_eval_counter); cudaFree(ctx->d_blob); cudaFree(ctx->d_partials); cudaFree(ctx->d_out);
+    cudaFree(ctx->d_q_points); cudaFree(ctx->d_q_sdf); cudaFree(ctx->d_q_ts); cudaFree(ctx->d_q_grad);
+    cudaFree(ctx->d_q_rounds);
+    if (ctx->h_blob) cudaFreeHost(ctx->h_blob);
+    if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *svsdf_last_error(const svsdf_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int svsdf_set_points(svsdf_ctx *ctx, const double *pts, int64_t P, int stride) {
+    if (!ctx || P < 0 || stride < 2 || (P > 0 && !pts)) return SVSDF_ERR_INVALID;
+    if (P > 2000000000LL) { ctx->err = "svsdf: too many points"; return SVSDF_ERR_INVALID; }
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->own_points) { ctx->d_points = nullptr; ctx->own_points = true; ctx->cap_points = 0; }
+    if (P > ctx->cap_points) {
+        cudaFree(ctx->d_points);
+        ctx->d_points = nullptr;
+        ctx->cap_points = 0;
+        CK(cudaMalloc(&ctx->d_points, (size_t)(P + 1024) * 2 * sizeof(double)));
+        ctx->cap_points = P + 1024;
+    }
+    if (!ctx->d_points) {  // P == 0 and nothing allocated yet
+        CK(cudaMalloc(&ctx->d_points, 1024 * 2 * sizeof(double)));
+        ctx->cap_points = 1024;
+    }
+    int rc = ensure_stage(ctx, (size_t)P * 2 * sizeof(double));
+    if (rc) return rc;
+    double *h = ctx->h_stage;
+    for (int64_t i = 0; i < P; ++i) {  // pos_eva(2) = 0 (back_end_optimizer.hpp:791): only x, y are kept
+        h[2 * i] = pts[i * stride];
+        h[2 * i + 1] = pts[i * stride + 1];
+    }
+    CK(cudaMemcpyAsync(ctx->d_points, h, (size_t)P * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->P = P;
+    return ensure_scratch(ctx, P);
+}
+
+int svsdf_set_points_device(svsdf_ctx *ctx, const double *dev_xy, int64_t P) {
+    if (!ctx || P < 0 || (P > 0 && !dev_xy)) return SVSDF_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->own_points) cudaFree(ctx->d_points);
+    ctx->d_points = const_cast<double *>(dev_xy);
+    ctx->own_points = false;
+    ctx->cap_points = 0;
+    ctx->P = P;
+    return ensure_scratch(ctx, P);
+}
+
+int svsdf_device_ptr_points(svsdf_ctx *ctx, const double **dev_xy) {
+    if (!ctx || !dev_xy) return SVSDF_ERR_INVALID;
+    *dev_xy = ctx->d_points;
+    return SVSDF_OK;
+}
+
+int svsdf_set_traj(svsdf_ctx *ctx, int N, const double *T, const double *coeffs) {
+    if (!ctx) return SVSDF_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int rc = upload_traj(ctx, N, T, coeffs);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SVSDF_OK;
+}
+
+int svsdf_query(svsdf_ctx *ctx, int N, const double *T, const double *coeffs, int64_t P, const double *pts,
+                double *sdf, double *tstar, double *grad3, int *rounds, int outer_only) {
+    if (!ctx || P < 0 || (P > 0 && !pts)) return SVSDF_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int rc = upload_traj(ctx, N, T, coeffs);
+    if (rc) return rc;
+    if (P == 0) { CK(cudaStreamSynchronize(ctx->stream)); return SVSDF_OK; }
+    if (P > ctx->cap_q) {
+        cudaFree(ctx->d_q_points); cudaFree(ctx->d_q_sdf); cudaFree(ctx->d_q_ts); cudaFree(ctx->d_q_grad);
+        cudaFree(ctx->d_q_rounds);
+        ctx->d_q_points = ctx->d_q_sdf = ctx->d_q_ts = ctx->d_q_grad = nullptr;
+        ctx->d_q_rounds = nullptr;
+        ctx->cap_q = 0;
+        int64_t cap = P + 1024;
+        CK(cudaMalloc(&ctx->d_q_points, cap * 2 * sizeof(double)));
+        CK(cudaMalloc(&ctx->d_q_sdf, cap * sizeof(double)));
+        CK(cudaMalloc(&ctx->d_q_ts, cap * sizeof(double)));
+        CK(cudaMalloc(&ctx->d_q_grad, cap * 3 * sizeof(double)));
+        CK(cudaMalloc(&ctx->d_q_rounds, cap * sizeof(int)));
+        ctx->cap_q = cap;
+    }
+    rc = ensure_stage(ctx, (size_t)P * 5 * sizeof(double) + (size_t)P * sizeof(int));
+    if (rc) return rc;
+    double *h = ctx->h_stage;
+    for (int64_t i = 0; i < P; ++i) { h[2 * i] = pts[3 * i]; h[2 * i + 1] = pts[3 * i + 1]; }
+    CK(cudaMemcpyAsync(ctx->d_q_points, h, (size_t)P * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    rc = run_kernels(ctx, ctx->d_q_points, P, false, outer_only == 0, ctx->d_q_sdf, ctx->d_q_ts, ctx->d_q_grad,
+                     ctx->d_q_rounds);
+    if (rc) return rc;
+    double *h_sdf = h, *h_ts = h + P, *h_grad = h + 2 * P;
+    int *h_rounds = reinterpret_cast<int *>(h + 5 * P);
+    CK(cudaMemcpyAsync(h_sdf, ctx->d_q_sdf, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_ts, ctx->d_q_ts, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_grad, ctx->d_q_grad, (size_t)P * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_rounds, ctx->d_q_rounds, (size_t)P * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (sdf) std::memcpy(sdf, h_sdf, (size_t)P * sizeof(double));
+    if (tstar) std::memcpy(tstar, h_ts, (size_t)P * sizeof(double));
+    if (grad3) std::memcpy(grad3, h_grad, (size_t)P * 3 * sizeof(double));
+    if (rounds) std::memcpy(rounds, h_rounds, (size_t)P * sizeof(int));
+    return SVSDF_OK;
+}
+
+int svsdf_cost_grad(svsdf_ctx *ctx, int N, const double *T, const double *coeffs, double *cost_io,
+                    double *gradT_io, double *gradC_io) {
+    if (!ctx || !cost_io || !gradT_io || !gradC_io) return SVSDF_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int rc = cost_grad_raw(ctx, N, T, coeffs);
+    if (rc) return rc;
+    const double *o = ctx->h_out;
+    *cost_io += o[0];
+    for (int e = 0; e < 18 * N; ++e) gradC_io[e] += o[1 + e];
+    for (int i = 0; i < N; ++i) gradT_io[i] += o[1 + 18 * N + i];
+    if (!std::isfinite(o[0])) return SVSDF_ERR_NONFINITE;
+    return SVSDF_OK;
+}
+
+int svsdf_cost_grad_device(svsdf_ctx *ctx, int N, const double *T, const double *coeffs, int repeats,
+                           float *ms_per_eval, double *out_host) {
+    if (!ctx || repeats < 1) return SVSDF_ERR_INVALID;
+    if (!ctx->d_points) { ctx->err = "svsdf: query points not set"; return SVSDF_ERR_NOT_READY; }
+    CK(cudaSetDevice(ctx->device));
+    int rc = upload_traj(ctx, N, T, coeffs);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    for (int r = 0; r < repeats; ++r) {
+        rc = run_kernels(ctx, ctx->d_points, ctx->P, true, true, nullptr, nullptr, nullptr, nullptr);
+        if (rc) return rc;
+    }
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (ms_per_eval) *ms_per_eval = ms / repeats;
+    if (out_host) {
+        const int nout = 1 + 19 * N + 1;
+        CK(cudaMemcpy(out_host, ctx->d_out, (size_t)nout * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    return SVSDF_OK;
+}
+
+int svsdf_set_boundary(svsdf_ctx *ctx, const double *initS, const double *finalS, int N) {
+    if (!ctx || !initS || !finalS || N < 2 || N > kMaxPieces) return SVSDF_ERR_INVALID;
+    ctx->pieceN = N;
+    ctx->minco.setConditions(initS, finalS, N);
+    ctx->times.assign(N, 0.0);
+    ctx->gradByTimes.assign(N, 0.0);
+    ctx->partialGradByTimes.assign(N, 0.0);
+    ctx->partialGradByCoeffs.assign((size_t)18 * N, 0.0);
+    ctx->gradByPoints.assign((size_t)3 * (N - 1), 0.0);
+    ctx->have_boundary = true;
+    return SVSDF_OK;
+}
+
+double svsdf_evaluate(void *instance, const double *x, double *g, const int n) {
+    svsdf_ctx *ctx = static_cast<svsdf_ctx *>(instance);
+    if (!ctx || !x || !g) return NAN;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return NAN;
+    return evaluate_impl(ctx, x, g, n);
+}
+
+int svsdf_last_costs(const svsdf_ctx *ctx, double *out3) {
+    if (!ctx || !out3) return SVSDF_ERR_INVALID;
+    out3[0] = ctx->cost_pos; out3[1] = ctx->cost_other; out3[2] = ctx->cost_total;
+    return SVSDF_OK;
+}
+
+int svsdf_get_traj(const svsdf_ctx *ctx, double *T_out, double *coeffs_out) {
+    if (!ctx || !ctx->have_boundary) return SVSDF_ERR_NOT_READY;
+    if (T_out) std::memcpy(T_out, ctx->times.data(), sizeof(double) * ctx->pieceN);
+    if (coeffs_out) std::memcpy(coeffs_out, ctx->minco.getCoeffs(), sizeof(double) * 18 * ctx->pieceN);
+    return SVSDF_OK;
+}
+
+void svsdf_default_lbfgs_params(svsdf_lbfgs_params *p) {
+    host::LbfgsParams d;
+    p->mem_size = d.mem_size; p->past = d.past; p->delta = d.delta; p->g_epsilon = d.g_epsilon;
+    p->max_iterations = d.max_iterations; p->max_linesearch = d.max_linesearch; p->min_step = d.min_step;
+    p->max_step = d.max_step; p->f_dec_coeff = d.f_dec_coeff; p->s_curv_coeff = d.s_curv_coeff;
+    p->cautious_factor = d.cautious_factor; p->machine_prec = d.machine_prec;
+}
+
+int svsdf_optimize(svsdf_ctx *ctx, const double *initS, const double *finalS, double *opt_x, int N,
+                   const svsdf_lbfgs_params *params, svsdf_progress_t progress, void *user, double *T_out,
+                   double *coeffs_out, svsdf_opt_stats *stats) {
+    if (!ctx || !opt_x) return SVSDF_ERR_INVALID;
+    int rc = svsdf_set_boundary(ctx, initS, finalS, N);
+    if (rc) return rc;
+    svsdf_lbfgs_params dp;
+    svsdf_default_lbfgs_params(&dp);
+    if (!params) params = &dp;
+    host::LbfgsParams hp;
+    hp.mem_size = params->mem_size; hp.past = params->past; hp.delta = params->delta; hp.g_epsilon = params->g_epsilon;
+    hp.max_iterations = params->max_iterations; hp.max_linesearch = params->max_linesearch;
+    hp.min_step = params->min_step; hp.max_step = params->max_step; hp.f_dec_coeff = params->f_dec_coeff;
+    hp.s_curv_coeff = params->s_curv_coeff; hp.cautious_factor = params->cautious_factor;
+    hp.machine_prec = params->machine_prec;
+    const int n = N + 3 * (N - 1);
+    ctx->gpu_ms_total = 0.0;
+    ctx->time_kernels = true;
+    auto t0 = std::chrono::steady_clock::now();
+    host::Lbfgs solver(hp);
+    host::LbfgsResult R = solver.minimize(opt_x, n, svsdf_evaluate, ctx, progress, user);
+    auto t1 = std::chrono::steady_clock::now();
+    ctx->time_kernels = false;
+    // final trajectory from the returned iterate (optimize_traj_lmbm does the same on success and failure,
+    // back_end_optimizer.cpp:44-94)
+    for (int i = 0; i < N; ++i) ctx->times[i] = host::forwardT(opt_x[i]);
+    ctx->minco.setParameters(opt_x + N, ctx->times.data());
+    if (T_out) std::memcpy(T_out, ctx->times.data(), sizeof(double) * N);
+    if (coeffs_out) std::memcpy(coeffs_out, ctx->minco.getCoeffs(), sizeof(double) * 18 * N);
+    if (stats) {
+        stats->final_cost = R.f;
+        stats->iterations = R.iterations;
+        stats->evaluations = R.evaluations;
+        stats->status = R.status;
+        stats->seconds = std::chrono::duration<double>(t1 - t0).count();
+        stats->gpu_seconds = ctx->gpu_ms_total * 1e-3;
+    }
+    int ret = R.status;
+    if (ret == 0) ret = 1;  // back_end_optimizer.cpp:66-69
+    return ret;
+}
+
+int svsdf_minco_forward(const double *initS, const double *finalS, int N, const double *q, const double *T,
+                        double *coeffs_out, double *energy, double *gradC_out, double *gradT_out) {
+    if (!initS || !finalS || !q || !T || N < 2) return SVSDF_ERR_INVALID;
+    host::MincoS3NU m;
+    m.setConditions(initS, finalS, N);
+    m.setParameters(q, T);
+    if (coeffs_out) std::memcpy(coeffs_out, m.getCoeffs(), sizeof(double) * 18 * N);
+    if (energy) *energy = m.getEnergy();
+    if (gradC_out) m.getEnergyPartialGradByCoeffs(gradC_out);
+    if (gradT_out) m.getEnergyPartialGradByTimes(gradT_out);
+    return SVSDF_OK;
+}
+
+int svsdf_minco_propagate(const double *initS, const double *finalS, int N, const double *q, const double *T,
+                          const double *gradC, const double *gradT, double *gradQ_out, double *gradT_out) {
+    if (!initS || !finalS || !q || !T || !gradC || !gradT || !gradQ_out || !gradT_out || N < 2) return SVSDF_ERR_INVALID;
+    host::MincoS3NU m;
+    m.setConditions(initS, finalS, N);
+    m.setParameters(q, T);
+    m.propogateGrad(gradC, gradT, gradQ_out, gradT_out);
+    return SVSDF_OK;
+}
+
+void svsdf_forward_T(int n, const double *tau, double *T) { for (int i = 0; i < n; ++i) T[i] = host::forwardT(tau[i]); }
+void svsdf_backward_T(int n, const double *T, double *tau) { for (int i = 0; i < n; ++i) tau[i] = host::backwardT(T[i]); }
+
+static int shape_eval(svsdf_ctx *ctx, int64_t n, const double *rel, double *out, int grad) {
+    if (!ctx || n < 0 || (n > 0 && (!rel || !out))) return SVSDF_ERR_INVALID;
+    if (n == 0) return SVSDF_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int ow = grad ? 3 : 1;
+    int rc = ensure_stage(ctx, (size_t)n * (2 + ow) * sizeof(double));
+    if (rc) return rc;
+    double *d_in = nullptr, *d_out = nullptr;
+    CK(cudaMalloc(&d_in, (size_t)n * 2 * sizeof(double)));
+    if (cudaMalloc(&d_out, (size_t)n * ow * sizeof(double)) != cudaSuccess) { cudaFree(d_in); ctx->err = "cudaMalloc"; return SVSDF_ERR_CUDA; }
+    double *h = ctx->h_stage;
+    for (int64_t i = 0; i < n; ++i) { h[2 * i] = rel[3 * i]; h[2 * i + 1] = rel[3 * i + 1]; }
+    cudaError_t e = cudaMemcpyAsync(d_in, h, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+        e = ctx->strict ? strict::launch_shape_eval(ctx->shape, d_in, n, d_out, grad, ctx->stream)
+                        : fast::launch_shape_eval(ctx->shape, d_in, n, d_out, grad, ctx->stream);
+    ctx->launches += 1;
+    double *ho = h + 2 * n;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ho, d_out, (size_t)n * ow * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return SVSDF_ERR_CUDA; }
+    std::memcpy(out, ho, (size_t)n * ow * sizeof(double));
+    return SVSDF_OK;
+}
+int svsdf_shape_sdf(svsdf_ctx *ctx, int64_t n, const double *rel, double *sdf_out) { return shape_eval(ctx, n, rel, sdf_out, 0); }
+int svsdf_shape_grad1(svsdf_ctx *ctx, int64_t n, const double *rel, double *grad3_out) { return shape_eval(ctx, n, rel, grad3_out, 1); }
+
+int svsdf_kernel_launches(const svsdf_ctx *ctx, int64_t *count) {
+    if (!ctx || !count) return SVSDF_ERR_INVALID;
+    *count = ctx->launches;
+    return SVSDF_OK;
+}
+
+int svsdf_executed_evals(svsdf_ctx *ctx, int enable, uint64_t *count) {
+    if (!ctx) return SVSDF_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (count) {
+        unsigned long long v = 0;
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaMemcpy(&v, ctx->d_eval_counter, sizeof(v), cudaMemcpyDeviceToHost));
+        *count = v;
+    }
+    ctx->count_evals = enable != 0;
+    CK(cudaMemset(ctx->d_eval_counter, 0, sizeof(unsigned long long)));
+    return SVSDF_OK;
+}
+
+int svsdf_fp64_peak(svsdf_ctx *ctx, double *tflops) {
+    if (!ctx || !tflops) return SVSDF_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    const int grid = ctx->sm_count * 8, iters = 1 << 16;
+    double *d = nullptr;
+    CK(cudaMalloc(&d, (size_t)grid * 256 * sizeof(double)));
+    float best = 1e30f;
+    for (int r = 0; r < 5; ++r) {
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        cudaError_t e = fast::launch_fp64_peak(d, grid, iters, ctx->stream);
+        if (e != cudaSuccess) { cudaFree(d); ctx->err = cudaGetErrorString(e); return SVSDF_ERR_CUDA; }
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        if (r > 0 && ms < best) best = ms;
+        ctx->launches += 1;
+    }
+    cudaFree(d);
+    const double flops = 2.0 * 8.0 * (double)iters * (double)grid * 256.0;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    return SVSDF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,328 @@
+// svsdf_shapes.cuh — device-side robot-shape SDF functors (2-D, FP64), one template specialisation per
+// registry key of the reference (src/utils/include/utils/Shape.hpp; line of each value function cited).
+// Operation order follows the reference so that a -fmad=false build differs from the CPU only through
+// libm (sin/cos); every function takes the body-frame point AFTER the shape pre-transform.
+#pragma once
+#include "svsdf_types.h"
+
+namespace svsdf {
+namespace dev {
+
+__device__ __forceinline__ double clipd(double v, double lo, double hi) { return fmax(fmin(v, hi), lo); }
+__device__ __forceinline__ double len2(double x, double y) { return sqrt(x * x + y * y); }
+
+template <int SHAPE>
+struct ShapeFn;
+
+// star — Shape.hpp:584-601 (r = 2.8, rf = 0.6)
+template <>
+struct ShapeFn<SH_STAR> {
+    static __device__ __forceinline__ double sdf(const ShapeParams &, double px, double py) {
+        const double r = 2.8, rf = 0.6;
+        const double k1x = 0.809016994375, k1y = -0.587785252292;
+        const double k2x = -k1x, k2y = k1y;
+        px = fabs(px);
+        double m = 2.0 * fmax(k1x * px + k1y * py, 0.0);
+        px -= m * k1x;
+        py -= m * k1y;
+        m = 2.0 * fmax(k2x * px + k2y * py, 0.0);
+        px -= m * k2x;
+        py -= m * k2y;
+        px = fabs(px);
+        py -= r;
+        const double bax = rf * (-k1y) - 0.0, bay = rf * k1x - 1.0;
+        double h = clipd((px * bax + py * bay) / (bax * bax + bay * bay), 0.0, r);
+        double dx = px - bax * h, dy = py - bay * h;
+        return len2(dx, dy) * copysign(1.0, py * bax - px * bay);
+    }
+};
+
+// sdHorseshoe — Shape.hpp:870-891; cst = (cos 20.5, sin 20.5) computed on the host (:855)
+template <>
+struct ShapeFn<SH_HORSESHOE> {
+    static __device__ __forceinline__ double sdf(const ShapeParams &S, double px, double py) {
+        const double r = 1.5, wx = 1.55, wy = 0.20;
+        const double cx = S.cst[0], cy = S.cst[1];
+        px = fabs(px);
+        double l = len2(px, py);
+        double qx = -cx * px + cy * py;
+        double qy = cy * px + cx * py;
+        double px0 = qx;
+        if (px0 <= 0 && qy <= 0) qx = l * copysign(1.0, -cx);
+        if (px0 <= 0) qy = l;
+        qx = qx - wx;
+        qy = fabs(qy - r) - wy;
+        double tx = fmax(qx, 0.0), ty = fmax(qy, 0.0);
+        return len2(tx, ty) + fmin(0.0, fmax(qx, qy));
+    }
+};
+
+// sdPie / sdPie2 — Shape.hpp:1253-1260 / 1294-1301; cst = (cos 43, sin 43) / (cos 1, sin 1)
+__device__ __forceinline__ double sd_pie_c(double px, double py, double cx, double cy) {
+    const double r = 3.0;
+    px = fabs(px);
+    double l = len2(px, py) - r;
+    double k = clipd(px * cx + py * cy, 0.0, r);
+    double dx = px - cx * k, dy = py - cy * k;
+    double m = len2(dx, dy);
+    return fmax(l, m * copysign(1.0, cy * px - cx * py));
+}
+template <>
+struct ShapeFn<SH_PIE> {
+    static __device__ __forceinline__ double sdf(const ShapeParams &S, double px, double py) {
+        return sd_pie_c(px, py, S.cst[0], S.cst[1]);
+    }
+};
+template <>
+struct ShapeFn<SH_PIE2> {
+    static __device__ __forceinline__ double sdf(const ShapeParams &S, double px, double py) {
+        return sd_pie_c(px, py, S.cst[0], S.cst[1]);
+    }
+};
+
+// sdArc — Shape.hpp:1334-1343; cst = (sin 20, cos 20), ra = 2.3333, rb = 0.5
+template <>
+struct ShapeFn<SH_ARC> {
+    static __device__ __forceinline__ double sdf(const ShapeParams &S, double px, double py) {
+        const double scx = S.cst[0], scy = S.cst[1];
+        const double ra = 2.3333, rb = 0.5;
+        px = fabs(px);
+        bool cond = scy * px > scx * py;
+        double ax = px - scx * ra, ay = py - scy * ra;
+        double dist1 = len2(ax, ay);
+        double dist2 = fabs(len2(px, py) - ra);
+        return (cond ? dist1 : dist2) - rb;
+    }
+};
+
+// sdTunnel — Shape.hpp:642-658; wh = (2.5, 1.5)
+template <>
+struct ShapeFn<SH_TUNNEL> {
+    static __device__ __forceinline__ double sdf(const ShapeParams &, double px, double py) {
+        const double whx = 2.5, why = 1.5;
+        px = fabs(px);
+        py = -py;
+        double qx = px - whx, qy = py - why;
+        double mq = fmax(qx, 0.0);
+        double d1 = mq * mq + qy * qy;
+        qx = (py > 0.0) ? qx : len2(px, py) - whx;
+        double mqy = fmax(qy, 0.0);
+        double d2 = qx * qx + mqy * mqy;
+        double d = sqrt(fmin(d1, d2));
+        return (fmax(qx, qy) < 0.0) ? -d : d;
+    }
+};
+
+// sdCutDisk — Shape.hpp:698-711; r = 5, h = 2; cst[0] = sqrt(r*r - h*h)
+template <>
+struct ShapeFn<SH_CUTDISK> {
+    static __device__ __forceinline__ double sdf(const ShapeParams &S, double px, double py) {
+        const double r = 5.0, h = 2.0;
+        const double w = S.cst[0];
+        px = fabs(px);
+        double s = fmax((h - r) * px * px + w * w * (h + r - 2.0 * py), h * px - w * py);
+        if (s < 0.0) return len2(px, py) - r;
+        if (px < w) return h - py;
+        return len2(px - w, py - h);
+    }
+};
+
+// sdTrapezoid — Shape.hpp:754-767; r1 = 1, r2 = 3, he = 2
+template <>
+struct ShapeFn<SH_TRAPEZOID> {
+    static __device__ __forceinline__ double sdf(const ShapeParams &, double px, double py) {
+        const double r1 = 1.0, r2 = 3.0, he = 2.0;
+        const double k1x = r2, k1y = he;
+        const double k2x = r2 - r1, k2y = 2.0 * he;
+        px = fabs(px);
+        double cax = fmax(0.0, px - ((py < 0.0) ? r1 : r2));
+        double cay = fabs(py) - he;
+        double t = clipd(((k1x - px) * k2x + (k1y - py) * k2y) / (k2x * k2x + k2y * k2y), 0.0, 1.0);
+        double cbx = px - k1x + k2x * t;
+        double cby = py - k1y + k2y * t;
+        double s = (cbx < 0.0 && cay < 0.0) ? -1.0 : 1.0;
+        return s * sqrt(fmin(cax * cax + cay * cay, cbx * cbx + cby * cby));
+    }
+};
+
+// sdRhombus — Shape.hpp:809-826; b = (1, 4.5)
+template <>
+struct ShapeFn<SH_RHOMBUS> {
+    static __device__ __forceinline__ double sdf(const ShapeParams &, double px, double py) {
+        const double bx = 1.0, by = 4.5;
+        px = fabs(px);
+        py = fabs(py);
+        double mx = bx - 2.0 * px, my = by - 2.0 * py;
+        double dotp = bx * bx + by * by;
+        double h = clipd((mx * bx - my * by) / dotp, -1.0, 1.0);
+        double hx = 0.5 * bx, hy = 0.5 * by;
+        double dx = px - hx * (1.0 - h), dy = py - hy * (1.0 + h);
+        double d = len2(dx, dy);
+        double sign = signbit(px * by + py * bx - bx * by) ? -1.0 : 1.0;
+        return d * sign;
+    }
+};
+
+// sdHeart — Shape.hpp:939-952 (input / 4, output * 4); cst[0] = sqrt(2.0) / 4.0
+template <>
+struct ShapeFn<SH_HEART> {
+    static __device__ __forceinline__ double sdf(const ShapeParams &S, double px, double py) {
+        px = px / 4.0;
+        py = py / 4.0;
+        px = fabs(px);
+        if (py + px > 1.0) return 4 * (len2(px - 0.25, py - 0.75) - S.cst[0]);
+        double ax = px - 0.0, ay = py - 1.0;
+        double v1 = ax * ax + ay * ay;
+        double t = fmax(px + py, 0.0);
+        double bx = px - 0.5 * t, by = py - 0.5 * t;
+        double v2 = bx * bx + by * by;
+        return 4 * (sqrt(fmin(v1, v2)) * copysign(1.0, px - py));
+    }
+};
+
+// sdRoundedX / bigX — Shape.hpp:988-994 (w = 3, r = 0.25) / 1024-1030 (w = 5, r = 0.25)
+__device__ __forceinline__ double sd_roundedx_w(double px, double py, double w, double r) {
+    double ax = fabs(px), ay = fabs(py);
+    double m = (ax + ay > w) ? (w * 0.5) : (ax + ay) * 0.5;
+    return len2(ax - m, ay - m) - r;
+}
+template <>
+struct ShapeFn<SH_ROUNDEDX> {
+    static __device__ __forceinline__ double sdf(const ShapeParams &, double px, double py) {
+        return sd_roundedx_w(px, py, 3.0, 0.25);
+    }
+};
+template <>
+struct ShapeFn<SH_BIGX> {
+    static __device__ __forceinline__ double sdf(const ShapeParams &, double px, double py) {
+        return sd_roundedx_w(px, py, 5.0, 0.25);
+    }
+};
+
+// sdRoundedCross — Shape.hpp:1062-1075; h = 1, input / 2, output * 2
+template <>
+struct ShapeFn<SH_ROUNDEDCROSS> {
+    static __device__ __forceinline__ double sdf(const ShapeParams &, double px, double py) {
+        const double h = 1.0;
+        px = px / 2.0;
+        py = py / 2.0;
+        const double k = 0.5 * (h + 1.0 / h);
+        double ax = fabs(px), ay = fabs(py);
+        if (ax < 1.0 && ay < ax * (k - h) + h) return 2 * (k - len2(ax - 1.0, ay - k));
+        double d1x = ax - 0.0, d1y = ay - h;
+        double d2x = ax - 1.0, d2y = ay - 0.0;
+        return 2 * sqrt(fmin(d1x * d1x + d1y * d1y, d2x * d2x + d2y * d2y));
+    }
+};
+
+// sdOrientedVesica — Shape.hpp:1115-1146; a = (2,4), b = (-2,-4), w = 0.8
+// cst = (r, d, vx, vy) with r = 0.5*|b-a|, d = 0.5*(r*r - w*w)/w, v = (b-a)/r  (host-computed, same formulas)
+template <>
+struct ShapeFn<SH_VESICA> {
+    static __device__ __forceinline__ double sdf(const ShapeParams &S, double px, double py) {
+        const double w = 0.8;
+        const double r = S.cst[0], d = S.cst[1], vx = S.cst[2], vy = S.cst[3];
+        const double cx = 0.5 * (-2.0 + 2.0), cy = 0.5 * (-4.0 + 4.0);
+        px = px / 1.0;
+        py = py / 1.0;
+        double ux = px - cx, uy = py - cy;
+        double qx = 0.5 * fabs(vy * ux + vx * uy);
+        double qy = 0.5 * fabs(-vx * ux + vy * uy);
+        double hx, hy, hz;
+        if (r * qx < d * (qy - r)) {
+            hx = 0.0; hy = r; hz = 0.0;
+        } else {
+            hx = -d; hy = 0.0; hz = d + w;
+        }
+        return 1.0 * (len2(qx - hx, qy - hy) - hz);
+    }
+};
+
+// sdMoon — Shape.hpp:1202-1214; d = 0.8, ra = 3, rb = 2.4; cst = (a, b) host-computed
+template <>
+struct ShapeFn<SH_MOON> {
+    static __device__ __forceinline__ double sdf(const ShapeParams &S, double qx, double qy) {
+        const double d = 0.8, ra = 3.0, rb = 2.4;
+        const double a = S.cst[0], b = S.cst[1];
+        qy = fabs(qy);
+        bool cond = d * (qx * b - qy * a) > d * d * fmax(b - qy, 0.0);
+        double dist1 = len2(qx - a, qy - b);
+        double dist2 = fmax(len2(qx, qy) - ra, -len2(qx - d, qy - 0.0) + rb);
+        return cond ? dist1 : dist2;
+    }
+};
+
+// sdUnevenCapsule — Shape.hpp:531-543; r1 = 2, r2 = 1, h = 5; cst = (b, a) host-computed
+template <>
+struct ShapeFn<SH_UNEVENCAPSULE> {
+    static __device__ __forceinline__ double sdf(const ShapeParams &S, double px, double py) {
+        const double r1 = 2.0, r2 = 1.0, h = 5.0;
+        const double b = S.cst[0], a = S.cst[1];
+        px = fabs(px);
+        double k = px * (-b) + py * a;
+        if (k < 0.0) return len2(px, py) - r1;
+        if (k > a * h) return len2(px - 0.0, py - h) - r2;
+        return px * a + py * b - r1;
+    }
+};
+
+// Circle — Shape.hpp:476-480
+template <>
+struct ShapeFn<SH_CIRCLE> {
+    static __device__ __forceinline__ double sdf(const ShapeParams &S, double px, double py) {
+        return len2(px, py) - S.radius;
+    }
+};
+
+// Polygon fallback — Shape.hpp:1370-1400 (edge helpers), 1448-1476 (SDF), 1508-1534 (analytic gradient).
+// Ignores trans/Rotate, like the reference (:1451).
+struct PolyHit {
+    double dis, cx, cy;
+    int rs;
+};
+__device__ __forceinline__ PolyHit polygon_scan(const ShapeParams &S, double qx, double qy) {
+    const double PI = 3.14159265358979323846;
+    PolyHit H{1e9, 0.0, 0.0, 0};
+#pragma unroll 1
+    for (int i = 0; i < S.poly_n; ++i) {
+        double sx = S.poly_sx[i], sy = S.poly_sy[i], ex = S.poly_ex[i], ey = S.poly_ey[i];
+        double vx = ex - sx, vy = ey - sy;
+        double wx = qx - sx, wy = qy - sy;
+        double t = (wx * vx + wy * vy) / (vx * vx + vy * vy);
+        if (t < 0.0) t = 0.0;
+        else if (t > 1.0) t = 1.0;
+        double cx = sx + t * vx, cy = sy + t * vy;
+        double dis = len2(qx - cx, qy - cy);
+        if (dis < H.dis) {
+            H.dis = dis; H.cx = cx; H.cy = cy;
+        }
+        double ths = atan2(sy - qy, sx - qx), the = atan2(ey - qy, ex - qx);
+        ths = (ths < 0.0) ? (ths + 2 * PI) : ths;
+        the = (the < 0.0) ? (the + 2 * PI) : the;
+        double d1 = fabs(ths - the);
+        if (!(d1 < PI)) H.rs++;
+    }
+    return H;
+}
+template <>
+struct ShapeFn<SH_POLYGON> {
+    static __device__ __forceinline__ double sdf(const ShapeParams &S, double qx, double qy) {
+        PolyHit H = polygon_scan(S, qx, qy);
+        return (H.rs % 2 == 0) ? H.dis : -H.dis;
+    }
+};
+
+// ((pos_rel - trans) * Rotate).head(2): row-vector times matrix (Shape.hpp:281-294 and e.g. :586).
+// With has_xform == 0 (trans = 0, Rotate = I) the product is the identity bit-for-bit and is skipped.
+template <int SHAPE, bool XFORM>
+__device__ __forceinline__ double shape_sdf(const ShapeParams &S, double rx, double ry) {
+    if (SHAPE != SH_POLYGON && XFORM) {
+        double v0 = rx - S.trans[0], v1 = ry - S.trans[1];
+        rx = v0 * S.rot[0] + v1 * S.rot[2];
+        ry = v0 * S.rot[1] + v1 * S.rot[3];
+    }
+    return ShapeFn<SHAPE>::sdf(S, rx, ry);
+}
+
+}  // namespace dev
+}  // namespace svsdf

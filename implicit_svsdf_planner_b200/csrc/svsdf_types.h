@@ -1,0 +1,116 @@
+// svsdf_types.h — POD types shared by the host runtime and the sm_100a kernels.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SVSDF_HD __host__ __device__
+#else
+#define SVSDF_HD
+#endif
+
+namespace svsdf {
+
+// Shape registry ids. Keys mirror the reference's shapeConstructors map
+// (src/swept_volume/include/swept_volume/sw_manager.hpp:187-235); unknown names fall back to the
+// rectangle Polygon (sw_manager.hpp:363-372).
+enum ShapeId : int {
+    SH_STAR = 0,
+    SH_HORSESHOE,
+    SH_PIE,
+    SH_PIE2,
+    SH_ARC,
+    SH_TUNNEL,
+    SH_CUTDISK,
+    SH_TRAPEZOID,
+    SH_RHOMBUS,
+    SH_HEART,
+    SH_ROUNDEDX,
+    SH_BIGX,
+    SH_ROUNDEDCROSS,
+    SH_VESICA,
+    SH_MOON,
+    SH_UNEVENCAPSULE,
+    SH_CIRCLE,
+    SH_POLYGON,
+    SH_COUNT
+};
+
+constexpr int kMaxPolyEdges = 64;
+constexpr int kMaxPieces = 64;       // pieces per trajectory supported by the per-warp accumulators
+constexpr int kWarpsPerBlock = 8;    // K1/K2 block = 256 threads
+constexpr double kMaxDuration = 300.0;  // sw_manager.hpp:380: durations >= 300 s are not accepted by updateTraj
+
+// Parameters of the robot-shape SDF functor. Trigonometric constants the reference evaluates on the host
+// at construction (cos(20.5), sin(43) ... radians of the literal, Shape.hpp:855,1235,1276,1320) are
+// evaluated on the host here too and passed in, so host/device libm differences cannot enter.
+struct ShapeParams {
+    int id;
+    int has_xform;      // 0: trans == 0 and Rotate == I (all shipped yamls) -> pre-transform skipped (bit-exact)
+    double trans[2];    // poly_params[0..1]              (Shape.hpp:287)
+    double rot[4];      // Rotate(0,0),(0,1),(1,0),(1,1)  (Shape.hpp:288-294)
+    double cst[4];      // per-shape host-computed constants (see shape_registry.cpp)
+    double radius;      // Circle
+    int poly_n;         // Polygon edge count
+    int pad_;
+    double poly_sx[kMaxPolyEdges], poly_sy[kMaxPolyEdges], poly_ex[kMaxPolyEdges], poly_ey[kMaxPolyEdges];
+};
+
+// Trajectory blob: one contiguous, 16-byte aligned buffer that the kernels pull into shared memory with a
+// single TMA bulk copy (cp.async.bulk.shared::cluster.global).  All offsets are in doubles.
+//   [0]  header (4 doubles: N, K1, D, reserved)
+//   [4]  T[Npad]              piece durations (Npad = N rounded up to even)
+//   [..] c[N][3][6]           per piece, per dim (x,y,yaw), ascending powers (== MINCO b rows 6i..6i+5)
+//   [..] lat[K1pad]           layer-1 lattice times t_k = 0.15 accumulated k times (host, IEEE adds)
+//   [..] pose[K1][4]          (x, y, cos yaw, sin yaw) at lat[k]  — filled on device by k_pose_table
+struct BlobLayout {
+    int N, K1;
+    int off_T, off_c, off_lat, off_pose, total;  // in doubles; total is even (16-byte multiple)
+};
+
+SVSDF_HD inline BlobLayout blob_layout(int N, int K1) {
+    BlobLayout L;
+    L.N = N;
+    L.K1 = K1;
+    int Npad = (N + 1) & ~1;
+    int K1pad = (K1 + 1) & ~1;
+    L.off_T = 4;
+    L.off_c = L.off_T + Npad;
+    L.off_lat = L.off_c + 18 * N;
+    L.off_pose = L.off_lat + K1pad;
+    L.total = L.off_pose + 4 * K1;
+    L.total = (L.total + 1) & ~1;
+    return L;
+}
+
+// Penalty parameters (star.yaml: weight_p 60, safety_hor 0.7; smoothedL1 mu = 0.01 is a literal in the
+// reference, back_end_optimizer.hpp:1052)
+struct CostParams {
+    double weight_p;
+    double safety_hor;
+};
+
+// Kernel argument block
+struct KernelArgs {
+    const double *blob;        // trajectory blob (global)
+    int blob_doubles;
+    const double *points_xy;   // P x 2, packed (x, y)
+    int64_t P;
+    CostParams cp;
+    // per-point outputs (optional, may be null)
+    double *out_sdf, *out_tstar, *out_grad;   // grad: P x 3
+    int *out_rounds;                           // GSIP rounds per point (0 for outside points)
+    // reduction outputs
+    double *partials;          // [gridDim.x][19N+1] block partial sums (K1)
+    int want_reduce;
+    int want_gsip;             // 0: stop after the outer solve (getSDFofSweptVolume semantics)
+    // inside-point bookkeeping
+    unsigned char *inside_flag;  // P
+    double *inside_tstar;        // P (sparse: written for inside points only)
+    int *inside_list;            // compacted, ascending point index
+    int *n_inside;               // device scalar
+    double *gsip_contrib;        // [n_inside][20]: cost, 18 gdC entries ([d][q]), gdT
+    int *gsip_piece;             // [n_inside]
+    unsigned long long *eval_counter;  // optional: executed lane-evaluations (profiling builds)
+};
+
+}  // namespace svsdf

@@ -1,0 +1,166 @@
+/* svsdf.h — C ABI of libsvsdf_b200.so: the B200-native drop-in for the SVSDF collision cost + gradient path of
+ * ZJU-FAST-Lab/Implicit-SVSDF-Planner.  Plain pointers and sizes only; no C++/torch types cross this boundary.
+ * All matrices use the reference's memory layouts (Eigen default column-major) so a maintainer can pass
+ * `.data()` of the existing Eigen objects (see INTEGRATION.md for the binding stubs).
+ *
+ * Reference interfaces replaced (paths relative to /root/reference/src):
+ *   R1  TrajOptimizer::addSaftyPenaOnSweptVolumeParallelTrueSDF(void*, const VectorXd& T, const MatrixX3d& coeffs,
+ *         double& cost, VectorXd& gradT, MatrixX3d& gradC)
+ *         planner_algorithm/include/planner_algorithm/back_end_optimizer.hpp:774-869      -> svsdf_cost_grad
+ *   R2  SweptVolumeManager::getTrueSDFofSweptVolume<true>(pos_eva, time_seed_f, grad_prel, set_ts)
+ *         swept_volume/include/swept_volume/sw_manager.hpp:916-1018                        -> svsdf_query
+ *       SweptVolumeManager::getSDFofSweptVolume<false,true>  sw_manager.hpp:844-866         -> svsdf_query (outer_only=1)
+ *       SweptVolumeManager::updateTraj                      sw_manager.hpp:376-385         -> svsdf_set_traj
+ *   R3  TrajOptimizer::costFunctionLmbmParallel(void*, const double* x, double* g, int n)
+ *         back_end_optimizer.hpp:344-408; callback type lmbm_evaluate_t utils/include/utils/lmbm.h:206-209
+ *                                                                                          -> svsdf_evaluate
+ *   R4  TrajOptimizer::optimize_traj_lmbm(initS, finalS, opt_x, N, traj)
+ *         planner_algorithm/src/back_end_optimizer.cpp:3-97 (outer solver on the host)     -> svsdf_optimize
+ *   R5  shape::BasicShape::getonlySDF / getonlyGrad1 and the shapeConstructors registry
+ *         utils/include/utils/Shape.hpp:266-270, sw_manager.hpp:187-235,350-373            -> svsdf_shape_sdf/_grad1
+ *   R6  TrajOptimizer::setParam / parallel_points / parallel_points_num
+ *         back_end_optimizer.hpp:877-932, plan_manager/src/plan_manager.cpp:168-175         -> svsdf_create/_set_points
+ *   R7  MINCO_S3NU::setConditions, setParameters, getEnergy..., propogateGrad utils/include/utils/minco.hpp:397-655
+ *                                                                                          -> svsdf_minco_*
+ *
+ * Threading: a context is not thread-safe; use one context per CUDA stream / GPU (the reference has the same
+ * restriction: one optimisation per TrajOptimizer instance, back_end_optimizer.hpp:344-408 mutates members).
+ * Errors: every int-returning function returns SVSDF_OK (0) or a negative svsdf_status; no exceptions cross
+ * the ABI.  The library has no CPU fallback: without a usable CUDA device svsdf_create fails with
+ * SVSDF_ERR_CUDA.
+ */
+#ifndef SVSDF_H_
+#define SVSDF_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct svsdf_ctx svsdf_ctx;
+
+typedef enum {
+    SVSDF_OK = 0,
+    SVSDF_ERR_INVALID = -1,   /* bad argument (null pointer, N out of range, duration >= 300 s, ...) */
+    SVSDF_ERR_CUDA = -2,      /* CUDA runtime error or no device; see svsdf_last_error */
+    SVSDF_ERR_NOT_READY = -3, /* points / boundary conditions not set */
+    SVSDF_ERR_NONFINITE = -4  /* cost or gradient became NaN/Inf */
+} svsdf_status;
+
+/* Mirrors the subset of `struct Config` (utils/include/utils/config.hpp) the hot path reads. */
+typedef struct {
+    const char *shape;        /* registry key = basename of yaml `inputdata` ("star", "sdHorseshoe", ...);
+                                 unknown / NULL -> Polygon fallback (rectangle 12 x 0.2 unless polygon_xy given) */
+    double poly_params[3];    /* yaml poly_params: body-frame offset x, y and yaw (degrees) of the shape */
+    double weight_p;          /* yaml weight_p   (star.yaml: 60.0) */
+    double safety_hor;        /* yaml safety_hor (star.yaml: 0.7)  */
+    double rho;               /* yaml rho        (star.yaml: 3.8)  */
+    int device;               /* CUDA device ordinal */
+    int strict_fp;            /* 1: kernels compiled with -fmad=false (CPU-like rounding; slower) */
+    const double *polygon_xy; /* optional polygon vertices (x0,y0,x1,y1,...) for the fallback shape */
+    int polygon_n;            /* number of vertices (<= 64) */
+} svsdf_config;
+
+/* Fill a config with the reference's star.yaml defaults. */
+void svsdf_default_config(svsdf_config *cfg);
+
+int svsdf_create(const svsdf_config *cfg, svsdf_ctx **out);
+void svsdf_destroy(svsdf_ctx *ctx);
+const char *svsdf_last_error(const svsdf_ctx *ctx);
+/* Shape registry lookup: returns the internal id (>= 0); unknown names map to the Polygon fallback id. */
+int svsdf_shape_id(const char *name);
+
+/* R6: parallel_points.  pts: P rows of `stride` doubles (x, y, [z ...]); z is ignored like the reference
+ * does (back_end_optimizer.hpp:791).  Copies to device memory (host -> device inside this call). */
+int svsdf_set_points(svsdf_ctx *ctx, const double *pts, int64_t P, int stride);
+/* Same, but the points already live on the device as packed (x, y) pairs; no copy is made of host data. */
+int svsdf_set_points_device(svsdf_ctx *ctx, const double *dev_xy, int64_t P);
+
+/* R2: updateTraj.  T: N durations; coeffs: MINCO `b`, 6N x 3 column-major. */
+int svsdf_set_traj(svsdf_ctx *ctx, int N, const double *T, const double *coeffs);
+
+/* R2: per-point swept-volume SDF query on the trajectory given by (N, T, coeffs).
+ * pts: P x 3 (x, y, z) host doubles (z ignored).  Outputs (host, may be NULL): sdf[P], tstar[P], grad3[3P]
+ * (body-frame FD gradient for sdf > 0; world-frame unit direction for the interior branch, exactly what the
+ * reference returns), rounds[P] (GSIP rounds, 0 for outside points).  outer_only = 1 stops after
+ * getSDFofSweptVolume (no interior branch). */
+int svsdf_query(svsdf_ctx *ctx, int N, const double *T, const double *coeffs, int64_t P, const double *pts,
+                double *sdf, double *tstar, double *grad3, int *rounds, int outer_only);
+
+/* R1: accumulate the swept-volume penalty over the context's query points into cost / gradT[N] / gradC[6N x 3
+ * column-major] (they already hold the energy terms, as in the reference). */
+int svsdf_cost_grad(svsdf_ctx *ctx, int N, const double *T, const double *coeffs, double *cost_io,
+                    double *gradT_io, double *gradC_io);
+
+/* R3: boundary conditions (3x3 column-major: column k = k-th derivative of (x, y, yaw)) and piece count. */
+int svsdf_set_boundary(svsdf_ctx *ctx, const double *initS, const double *finalS, int N);
+/* R3: LMBM / L-BFGS compatible callback: x = [tau (N), xi (3(N-1))] -> cost, g.  `instance` is a svsdf_ctx*. */
+double svsdf_evaluate(void *instance, const double *x, double *g, const int n);
+/* Cost split of the last svsdf_evaluate: out3 = (cost_pos, cost_other, cost_total)  (back_end_optimizer.hpp:396-398) */
+int svsdf_last_costs(const svsdf_ctx *ctx, double *out3);
+/* Durations and MINCO coefficients of the last svsdf_evaluate (T_out[N], coeffs_out[18N] column-major). */
+int svsdf_get_traj(const svsdf_ctx *ctx, double *T_out, double *coeffs_out);
+
+/* Host L-BFGS parameters (utils/include/utils/lbfgs_ref.hpp:20-130; yaml: mem_size, past, min_step, g_epsilon). */
+typedef struct {
+    int mem_size;
+    int past;
+    double delta;
+    double g_epsilon;
+    int max_iterations;
+    int max_linesearch;
+    double min_step, max_step;
+    double f_dec_coeff, s_curv_coeff, cautious_factor, machine_prec;
+} svsdf_lbfgs_params;
+void svsdf_default_lbfgs_params(svsdf_lbfgs_params *p);
+
+typedef struct {
+    double final_cost;
+    int iterations;     /* accepted line-search steps */
+    int evaluations;    /* cost+gradient evaluations */
+    int status;         /* lbfgs_ref.hpp return code (0 convergence, 1 stop, <0 error) */
+    double seconds;     /* wall-clock of the whole optimisation */
+    double gpu_seconds; /* sum of device time of the cost kernels (CUDA events) */
+} svsdf_opt_stats;
+
+/* Progress / cancel hook, same contract as lmbm_progress_t (lmbm.h:211-213): non-zero return cancels. */
+typedef int (*svsdf_progress_t)(void *user, const double *x, const int k);
+
+/* R4: optimise opt_x in place from the given start (opt_x has N + 3(N-1) entries).  Returns >= 0 on success
+ * (0 is remapped to 1 like optimize_traj_lmbm does), negative solver code otherwise; the last iterate is
+ * returned either way.  T_out / coeffs_out (may be NULL) receive the final trajectory. */
+int svsdf_optimize(svsdf_ctx *ctx, const double *initS, const double *finalS, double *opt_x, int N,
+                   const svsdf_lbfgs_params *params, svsdf_progress_t progress, void *user, double *T_out,
+                   double *coeffs_out, svsdf_opt_stats *stats);
+
+/* R7: host MINCO_S3NU. q: 3 x (N-1) column-major. Outputs may be NULL. */
+int svsdf_minco_forward(const double *initS, const double *finalS, int N, const double *q, const double *T,
+                        double *coeffs_out, double *energy, double *gradC_out, double *gradT_out);
+int svsdf_minco_propagate(const double *initS, const double *finalS, int N, const double *q, const double *T,
+                          const double *gradC, const double *gradT, double *gradQ_out, double *gradT_out);
+/* tau <-> T maps (back_end_optimizer.hpp:199-289) */
+void svsdf_forward_T(int n, const double *tau, double *T);
+void svsdf_backward_T(int n, const double *T, double *tau);
+
+/* R5: shape functor over n body-frame points (rel: n x 3, z ignored by the 2-D shapes). */
+int svsdf_shape_sdf(svsdf_ctx *ctx, int64_t n, const double *rel, double *sdf_out);
+int svsdf_shape_grad1(svsdf_ctx *ctx, int64_t n, const double *rel, double *grad3_out);
+
+/* Device-resident evaluation for benchmarking and batch mode: runs R1 on the given trajectory with every input
+ * already in HBM, leaves the result on the device, and returns the device time of the kernels in milliseconds
+ * (CUDA events on the context's stream).  out_host (1 + 19N + 1 doubles: cost, gradC[18N] col-major, gradT[N],
+ * n_inside) may be NULL. */
+int svsdf_cost_grad_device(svsdf_ctx *ctx, int N, const double *T, const double *coeffs, int repeats,
+                           float *ms_per_eval, double *out_host);
+
+/* Measurement helpers */
+int svsdf_kernel_launches(const svsdf_ctx *ctx, int64_t *count);       /* kernels launched by this ctx so far */
+int svsdf_executed_evals(svsdf_ctx *ctx, int enable, uint64_t *count); /* lane-level SDF evaluations counter */
+int svsdf_fp64_peak(svsdf_ctx *ctx, double *tflops);                   /* measured DFMA peak (2 flop/FMA) */
+int svsdf_device_ptr_points(svsdf_ctx *ctx, const double **dev_xy);    /* device pointer of the packed points */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVSDF_H_ */
