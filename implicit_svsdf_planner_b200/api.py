@@ -73,6 +73,7 @@ class OptStats(C.Structure):
 
 
 PROGRESS_T = C.CFUNCTYPE(C.c_int, C.c_void_p, dp, C.c_int)
+EVAL_T = C.CFUNCTYPE(C.c_double, C.c_void_p, dp, dp, C.c_int)
 
 # every symbol include/svsdf.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = [
@@ -81,7 +82,7 @@ EXPORTED_SYMBOLS = [
     "svsdf_set_boundary", "svsdf_evaluate", "svsdf_last_costs", "svsdf_get_traj", "svsdf_default_lbfgs_params",
     "svsdf_optimize", "svsdf_minco_forward", "svsdf_minco_propagate", "svsdf_forward_T", "svsdf_backward_T",
     "svsdf_shape_sdf", "svsdf_shape_grad1", "svsdf_cost_grad_device", "svsdf_kernel_launches",
-    "svsdf_executed_evals", "svsdf_fp64_peak", "svsdf_device_ptr_points",
+    "svsdf_executed_evals", "svsdf_fp64_peak", "svsdf_device_ptr_points", "svsdf_lbfgs_minimize", "svsdf_last_kernel_ms",
 ]
 
 
@@ -115,6 +116,7 @@ def lib():
     L.svsdf_get_traj.argtypes = [vp, dp, dp]
     L.svsdf_default_lbfgs_params.argtypes = [C.POINTER(LbfgsParams)]
     L.svsdf_optimize.argtypes = [vp, dp, dp, dp, C.c_int, C.POINTER(LbfgsParams), vp, vp, dp, dp, C.POINTER(OptStats)]
+    L.svsdf_lbfgs_minimize.argtypes = [EVAL_T, vp, dp, C.c_int, C.POINTER(LbfgsParams), vp, vp, C.POINTER(OptStats)]
     L.svsdf_minco_forward.argtypes = [dp, dp, C.c_int, dp, dp, dp, dp, dp, dp]
     L.svsdf_minco_propagate.argtypes = [dp, dp, C.c_int, dp, dp, dp, dp, dp, dp]
     L.svsdf_forward_T.argtypes = [C.c_int, dp, dp]
@@ -122,6 +124,7 @@ def lib():
     L.svsdf_shape_sdf.argtypes = [vp, C.c_int64, dp, dp]
     L.svsdf_shape_grad1.argtypes = [vp, C.c_int64, dp, dp]
     L.svsdf_cost_grad_device.argtypes = [vp, C.c_int, dp, dp, C.c_int, C.POINTER(C.c_float), dp]
+    L.svsdf_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.svsdf_kernel_launches.argtypes = [vp, C.POINTER(C.c_int64)]
     L.svsdf_executed_evals.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64)]
     L.svsdf_fp64_peak.argtypes = [vp, dp]
@@ -175,6 +178,24 @@ def minco_propagate(init_s, final_s, q, T, gdC, gdT):
     if rc:
         raise SvsdfError(f"svsdf_minco_propagate: {rc}")
     return gq.reshape(N - 1, 3).T.copy(), gT
+
+
+def lbfgs_minimize(fun, x0, params: "LbfgsParams | None" = None):
+    """Host L-BFGS of the product on a Python callable fun(x) -> (f, g).  Returns (status, x, stats)."""
+    x = _f64(x0).copy()
+    n = x.shape[0]
+
+    def _cb(_inst, xp, gp, nn):
+        xv = np.ctypeslib.as_array(xp, shape=(nn,))
+        f, g = fun(xv.copy())
+        np.ctypeslib.as_array(gp, shape=(nn,))[:] = g
+        return float(f)
+
+    cb = EVAL_T(_cb)
+    st = OptStats()
+    rc = lib().svsdf_lbfgs_minimize(cb, None, _p(x), n, C.byref(params) if params is not None else None, None, None,
+                                    C.byref(st))
+    return rc, x, dict(final_cost=st.final_cost, iterations=st.iterations, evaluations=st.evaluations, status=st.status)
 
 
 def forward_T(tau):
@@ -331,6 +352,12 @@ class Context:
         out = np.empty((rel.shape[0], 3))
         self._ck(lib().svsdf_shape_grad1(self.h, rel.shape[0], _p(rel), _p(out)), "svsdf_shape_grad1")
         return out
+
+    def last_kernel_ms(self):
+        """Device ms of (k_pose_table, k_outer, k_compact + k_gsip, k_finalize) in the last cost_grad_device call."""
+        out = (C.c_float * 4)()
+        self._ck(lib().svsdf_last_kernel_ms(self.h, out), "svsdf_last_kernel_ms")
+        return [float(v) for v in out]
 
     def kernel_launches(self) -> int:
         n = C.c_int64()

@@ -1,0 +1,205 @@
+"""Batch-of-problems mode (BASELINE config 5): independent start/goal problems sharded over the GPUs of one box.
+
+One process per GPU (torch.distributed; NCCL on GPUs, gloo in the CPU tests).  Problems are independent — own
+decision vector, own query set, own optimiser state — so the shard is a contiguous block of problem indices per rank
+and there is NO collective on the data path.  The only shared datum is the map, broadcast once from rank 0 as the
+reference's bit-packed 2-D "map kernel" (src/map_manager/include/map_manager/PCSmap_manager.h:32, 81-108:
+(X + 2h) x ceil((Y + 2h) / 8) bytes, h = (kernel_size - 1) / 2, MSB-first); results are gathered at the end.
+
+Query points of a problem are the occupied cell centres inside the AABBs (half-size kernel_size * res / 3) around its
+waypoints, visiting for each waypoint only the cells outside the previous waypoint's box and de-duplicating by cell
+id — the 2-D (z = 0 layer) restatement of plan_manager.cpp:156-175 / PCSmap_manager.h:118-125, 184-219.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Callable, Optional
+
+import numpy as np
+
+from . import scenes
+
+OR_MASK = np.array([0x80, 0x40, 0x20, 0x10, 0x08, 0x04, 0x02, 0x01], dtype=np.uint8)  # PCSmap_manager.h:32
+
+
+@dataclasses.dataclass
+class GridMap:
+    occ: np.ndarray  # (X, Y) bool, z = 0 layer
+    origin: np.ndarray  # (2,) world coordinates of the corner of cell (0, 0)  (boundary_xyzmin)
+    res: float
+
+    @property
+    def shape(self):
+        return self.occ.shape
+
+    def cell_centers(self, ij: np.ndarray) -> np.ndarray:
+        """GridMap3D::getGridCubeCenter: min + (idx + 0.5) * res."""
+        return self.origin[None, :] + (ij + 0.5) * self.res
+
+
+def pack_map_kernel(occ: np.ndarray, kernel_size: int = 17) -> np.ndarray:
+    """generateMapKernel2D (PCSmap_manager.h:81-108)."""
+    X, Y = occ.shape
+    h = (kernel_size - 1) // 2
+    xs, ys = X + 2 * h, Y + 2 * h
+    row = (ys + 7) // 8
+    out = np.zeros((xs, row), dtype=np.uint8)
+    ii, jj = np.nonzero(occ)
+    fx, fy = ii + h, jj + h
+    np.bitwise_or.at(out, (fx, fy // 8), OR_MASK[fy % 8])
+    return out
+
+
+def unpack_map_kernel(kernel: np.ndarray, X: int, Y: int, kernel_size: int = 17) -> np.ndarray:
+    h = (kernel_size - 1) // 2
+    bits = np.unpackbits(kernel, axis=1, bitorder="big")  # MSB first
+    return bits[h : h + X, h : h + Y].astype(bool)
+
+
+def pack_map_kernel_from_points(points: np.ndarray, res: float, kernel_size: int = 17) -> np.ndarray:
+    """Occupancy grid from a point set (bounding box of the points, PCSmap_manager.cpp:116-150), then packed."""
+    gm = gridmap_from_points(points, res)
+    return pack_map_kernel(gm.occ, kernel_size)
+
+
+def gridmap_from_points(points: np.ndarray, res: float) -> GridMap:
+    xy = np.asarray(points, dtype=np.float64)[:, :2]
+    lo = xy.min(axis=0) - 0.5 * res
+    hi = xy.max(axis=0) + 0.5 * res
+    size = np.maximum(np.ceil((hi - lo) / res).astype(int), 1)  # Gridmap3D.cpp:25-41
+    ij = np.clip(np.floor((xy - lo) / res).astype(int), 0, size - 1)
+    occ = np.zeros(tuple(size), dtype=bool)
+    occ[ij[:, 0], ij[:, 1]] = True
+    return GridMap(occ=occ, origin=lo, res=res)
+
+
+def make_random_map(extent: float = 60.0, res: float = 0.025, density: float = 0.3, seed: int = scenes.SEED_MAP) -> GridMap:
+    rng = np.random.Generator(np.random.MT19937(seed))
+    n = int(np.ceil(extent / res))
+    occ = rng.random((n, n), dtype=np.float32) < density
+    return GridMap(occ=occ, origin=np.zeros(2), res=res)
+
+
+def extract_query_points(gm: GridMap, waypoints: np.ndarray, half: float) -> np.ndarray:
+    """getPointsInAABBOutOfLastOne over the waypoint sequence (plan_manager.cpp:156-167): occupied cells in each
+    waypoint's box that are outside the previous waypoint's box, de-duplicated by unified id (i + j * X), returned in
+    ascending id order (the reference iterates an unordered_map, i.e. in unspecified order)."""
+    X, Y = gm.shape
+    lo_w, hi_w = gm.origin, gm.origin + np.array([X, Y]) * gm.res
+
+    def box_idx(c):
+        c1 = np.clip(c - half, lo_w, hi_w)  # projInMap
+        c2 = np.clip(c + half, lo_w, hi_w)
+        i1 = np.floor((c1 - gm.origin) / gm.res).astype(int)
+        i2 = np.floor((c2 - gm.origin) / gm.res).astype(int)
+        return i1, i2
+
+    ids = []
+    prev = None
+    for w in np.asarray(waypoints, dtype=np.float64)[:, :2]:
+        i1, i2 = box_idx(w)
+        a1, a2 = np.clip(i1, 0, [X - 1, Y - 1]), np.clip(i2, 0, [X - 1, Y - 1])
+        sub = gm.occ[a1[0] : a2[0] + 1, a1[1] : a2[1] + 1]
+        ii, jj = np.nonzero(sub)
+        ii, jj = ii + a1[0], jj + a1[1]
+        if prev is not None:
+            p1, p2 = prev
+            outside = (ii > p2[0]) | (ii < p1[0]) | (jj > p2[1]) | (jj < p1[1])
+            ii, jj = ii[outside], jj[outside]
+        ids.append(jj.astype(np.int64) * X + ii)
+        prev = (i1, i2)
+    if not ids:
+        return np.zeros((0, 3))
+    uid = np.unique(np.concatenate(ids))
+    ij = np.stack([uid % X, uid // X], axis=1)
+    pts = np.zeros((uid.size, 3))
+    pts[:, :2] = gm.cell_centers(ij)
+    return pts
+
+
+def partition(n_problems: int, world: int, rank: int) -> range:
+    """Contiguous block partition (remainder spread over the first ranks)."""
+    base, rem = divmod(n_problems, world)
+    lo = rank * base + min(rank, rem)
+    return range(lo, lo + base + (1 if rank < rem else 0))
+
+
+def broadcast_map(kernel: Optional[np.ndarray], device=None, src: int = 0):
+    """Broadcast the packed map kernel from `src` to every rank (the only collective of the batch mode).
+    Returns the kernel as a uint8 torch tensor on `device` (CPU for gloo)."""
+    import torch
+    import torch.distributed as dist
+
+    device = device if device is not None else torch.device("cpu")
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return torch.from_numpy(np.ascontiguousarray(kernel)).to(device)
+    shape = torch.zeros(2, dtype=torch.int64, device=device)
+    if dist.get_rank() == src:
+        shape = torch.tensor(list(kernel.shape), dtype=torch.int64, device=device)
+    dist.broadcast(shape, src=src)
+    if dist.get_rank() == src:
+        buf = torch.from_numpy(np.ascontiguousarray(kernel)).to(device)
+    else:
+        buf = torch.empty(tuple(int(v) for v in shape.tolist()), dtype=torch.uint8, device=device)
+    dist.broadcast(buf, src=src)
+    return buf
+
+
+def problem_scene(gm: GridMap, start, goal, N: int = 8, P: Optional[int] = None, seed: int = 0, clearance: float = 2.75) -> scenes.Scene:
+    """One start/goal problem on the shared map: seeded nominal spline, query points extracted from the map around its
+    waypoints, a corridor around the nominal path kept free (stand-in for the A* feasibility of the reference's front
+    end), optionally sub-sampled to exactly P points."""
+    init_s, final_s, q, T = scenes.make_trajectory("star", N, seed, start, goal)
+    b = scenes.minco_dense(init_s, final_s, q, T)
+    half = scenes.YAML["kernel_size"] * scenes.YAML["occupancy_resolution"] / 3.0
+    wps = np.concatenate([init_s[:2, :1], q[:2], final_s[:2, :1]], axis=1).T
+    pts = extract_query_points(gm, wps, half)
+    path = scenes.eval_traj_xy(b, T, np.linspace(0.0, float(T.sum()), 1001))[:, :2]
+    keep = np.ones(pts.shape[0], dtype=bool)
+    for s in range(0, pts.shape[0], 200_000):
+        blk = pts[s : s + 200_000, :2]
+        d2 = ((blk[:, None, :] - path[None, ::2, :]) ** 2).sum(axis=2).min(axis=1)
+        keep[s : s + 200_000] = d2 > clearance * clearance
+    pts = pts[keep]
+    if P is not None and pts.shape[0] > P:
+        rng = np.random.Generator(np.random.MT19937(seed + 1))
+        pts = pts[np.sort(rng.choice(pts.shape[0], size=P, replace=False))]
+    return scenes.Scene(shape="star", N=N, init_s=init_s, final_s=final_s, q=q, T=T, coeffs=b, points=pts, resolution=gm.res)
+
+
+class BatchRunner:
+    """Runs the problems of this rank and gathers the per-problem results.
+
+    solve(scene, index) -> 1-D float array (fixed length) is injected: on a GPU box it wraps
+    ``api.Context.optimize``; the gloo tests inject a CPU stand-in so the sharding / broadcast / gather logic is
+    exercised without CUDA."""
+
+    def __init__(self, solve: Callable[[scenes.Scene, int], np.ndarray], result_len: int):
+        self.solve = solve
+        self.result_len = result_len
+
+    def run(self, gm: GridMap, problems: np.ndarray, N: int = 8, P: Optional[int] = None, device=None):
+        import torch
+        import torch.distributed as dist
+
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        rank = dist.get_rank() if dist.is_initialized() else 0
+        n = problems.shape[0]
+        mine = partition(n, world, rank)
+        local = np.full((n, self.result_len), np.nan)
+        for k in mine:
+            sg = problems[k]
+            sc = problem_scene(gm, sg[:2], sg[2:4], N=N, P=P, seed=scenes.SEED_BATCH + k)
+            local[k] = self.solve(sc, k)
+        if world == 1:
+            return local
+        # gather: every rank contributes its rows; nan elsewhere -> nan-aware merge
+        dev = device if device is not None else torch.device("cpu")
+        t = torch.from_numpy(np.nan_to_num(local, nan=0.0)).to(dev)
+        m = torch.from_numpy((~np.isnan(local)).astype(np.float64)).to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dist.all_reduce(m, op=dist.ReduceOp.SUM)
+        out = t.cpu().numpy()
+        cnt = m.cpu().numpy()
+        assert np.all(cnt == 1.0), "every problem must be solved by exactly one rank"
+        return out

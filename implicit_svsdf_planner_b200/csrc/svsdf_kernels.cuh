@@ -773,6 +773,7 @@ struct LaunchCfg {
     int grid_outer, grid_gsip;
     size_t smem_outer, smem_gsip;
     cudaStream_t stream;
+    cudaEvent_t after_outer;  // optional timing mark recorded right after k_outer
 };
 
 template <int SHAPE, bool XFORM>
@@ -789,6 +790,7 @@ static cudaError_t launch_shape(const KernelArgs &A, const ShapeParams &S, const
     k_outer<SHAPE, XFORM><<<cfg.grid_outer, kWarpsPerBlock * 32, cfg.smem_outer, cfg.stream>>>(A, S);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    if (cfg.after_outer) cudaEventRecord(cfg.after_outer, cfg.stream);
     if (A.want_gsip) {
         k_compact<<<1, 1024, 0, cfg.stream>>>(A.inside_flag, A.P, A.inside_list, A.n_inside);
         k_gsip<SHAPE, XFORM><<<cfg.grid_gsip, kWarpsPerBlock * 32, cfg.smem_gsip, cfg.stream>>>(A, S);
@@ -833,8 +835,9 @@ cudaError_t launch_pose_table(double *blob, int K1, cudaStream_t stream) {
 }
 
 cudaError_t launch_cost_kernels(const KernelArgs &A, const ShapeParams &S, int N, int grid_outer, int grid_gsip,
-                                cudaStream_t stream) {
+                                cudaStream_t stream, cudaEvent_t after_outer) {
     LaunchCfg cfg;
+    cfg.after_outer = after_outer;
     cfg.grid_outer = grid_outer;
     cfg.grid_gsip = grid_gsip;
     cfg.smem_outer = (size_t)(A.blob_doubles + kWarpsPerBlock * (19 * N + 1)) * sizeof(double);

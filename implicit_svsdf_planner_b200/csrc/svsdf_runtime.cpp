@@ -32,6 +32,9 @@ struct svsdf_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t evk[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // per-kernel timing marks
+    bool mark_kernels = false;
+    float last_kernel_ms[4] = {0, 0, 0, 0};  // pose table, k_outer, k_compact + k_gsip, k_finalize
     std::string err;
     int64_t launches = 0;
 
@@ -206,7 +209,15 @@ int ensure_stage(svsdf_ctx *ctx, size_t bytes) {
 
 // updateTraj (sw_manager.hpp:376-385) + the layer-1 lattice of choiceTInit (:538-581): builds the blob in
 // pinned memory, uploads it and launches the pose-table kernel.
-int upload_traj(svsdf_ctx *ctx, int N, const double *T, const double *coeffs) {
+int pose_table(svsdf_ctx *ctx) {
+    cudaError_t e = ctx->strict ? strict::launch_pose_table(ctx->d_blob, ctx->layout.K1, ctx->stream)
+                                : fast::launch_pose_table(ctx->d_blob, ctx->layout.K1, ctx->stream);
+    CK(e);
+    ctx->launches += 1;
+    return SVSDF_OK;
+}
+
+int upload_traj(svsdf_ctx *ctx, int N, const double *T, const double *coeffs, bool launch_pose = true) {
     if (N < 1 || N > kMaxPieces || !T || !coeffs) {
         ctx->err = "svsdf: N out of range (1..64) or null trajectory";
         return SVSDF_ERR_INVALID;
@@ -258,13 +269,10 @@ int upload_traj(svsdf_ctx *ctx, int N, const double *T, const double *coeffs) {
         for (double t = 0.0; t <= D; t += 0.15) h[L.off_lat + k++] = t;
     }
     CK(cudaMemcpyAsync(ctx->d_blob, h, (size_t)L.off_pose * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    cudaError_t e = ctx->strict ? strict::launch_pose_table(ctx->d_blob, K1, ctx->stream)
-                                : fast::launch_pose_table(ctx->d_blob, K1, ctx->stream);
-    CK(e);
-    ctx->launches += 1;
     ctx->layout = L;
     ctx->traj_N = N;
     ctx->traj_D = D;
+    if (launch_pose) return pose_table(ctx);
     return SVSDF_OK;
 }
 
@@ -328,10 +336,13 @@ int run_kernels(svsdf_ctx *ctx, const double *d_points, int64_t P, bool reduce, 
         ctx->err = "svsdf: trajectory blob does not fit in shared memory";
         return SVSDF_ERR_INVALID;
     }
-    cudaError_t e = ctx->strict ? strict::launch_cost_kernels(A, ctx->shape, N, grid, grid_gsip, ctx->stream)
-                                : fast::launch_cost_kernels(A, ctx->shape, N, grid, grid_gsip, ctx->stream);
+    cudaError_t e = ctx->strict ? strict::launch_cost_kernels(A, ctx->shape, N, grid, grid_gsip, ctx->stream,
+                                                              ctx->mark_kernels ? ctx->evk[2] : nullptr)
+                                : fast::launch_cost_kernels(A, ctx->shape, N, grid, grid_gsip, ctx->stream,
+                                                            ctx->mark_kernels ? ctx->evk[2] : nullptr);
     CK(e);
     ctx->launches += gsip ? 3 : 1;
+    if (ctx->mark_kernels) CK(cudaEventRecord(ctx->evk[3], ctx->stream));
     if (reduce) {
         e = ctx->strict ? strict::launch_finalize(ctx->d_partials, grid, N, ctx->d_n_inside, ctx->d_gsip_contrib,
                                                   ctx->d_gsip_piece, ctx->d_out, ctx->stream)
@@ -457,6 +468,8 @@ int svsdf_create(const svsdf_config *cfg, svsdf_ctx **out) {
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(e);
     if ((e = cudaEventCreate(&ctx->ev0)) != cudaSuccess) return fail(e);
     if ((e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) return fail(e);
+    for (int k = 0; k < 5; ++k)
+        if ((e = cudaEventCreate(&ctx->evk[k])) != cudaSuccess) return fail(e);
     if ((e = cudaMalloc(&ctx->d_n_inside, sizeof(int))) != cudaSuccess) return fail(e);
     if ((e = cudaMalloc(&ctx->d_eval_counter, sizeof(unsigned long long))) != cudaSuccess) return fail(e);
     cudaMemset(ctx->d_n_inside, 0, sizeof(int));
@@ -480,6 +493,8 @@ void svsdf_destroy(svsdf_ctx *ctx) {
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for (int k = 0; k < 5; ++k)
+        if (ctx->evk[k]) cudaEventDestroy(ctx->evk[k]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -603,18 +618,26 @@ int svsdf_cost_grad_device(svsdf_ctx *ctx, int N, const double *T, const double 
     if (!ctx || repeats < 1) return SVSDF_ERR_INVALID;
     if (!ctx->d_points) { ctx->err = "svsdf: query points not set"; return SVSDF_ERR_NOT_READY; }
     CK(cudaSetDevice(ctx->device));
-    int rc = upload_traj(ctx, N, T, coeffs);
+    int rc = upload_traj(ctx, N, T, coeffs, false);
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     for (int r = 0; r < repeats; ++r) {
+        ctx->mark_kernels = (r == repeats - 1);
+        if (ctx->mark_kernels) CK(cudaEventRecord(ctx->evk[0], ctx->stream));
+        rc = pose_table(ctx);
+        if (rc) return rc;
+        if (ctx->mark_kernels) CK(cudaEventRecord(ctx->evk[1], ctx->stream));
         rc = run_kernels(ctx, ctx->d_points, ctx->P, true, true, nullptr, nullptr, nullptr, nullptr);
+        if (ctx->mark_kernels) cudaEventRecord(ctx->evk[4], ctx->stream);
+        ctx->mark_kernels = false;
         if (rc) return rc;
     }
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    for (int k = 0; k < 4; ++k) CK(cudaEventElapsedTime(&ctx->last_kernel_ms[k], ctx->evk[k], ctx->evk[k + 1]));
     if (ms_per_eval) *ms_per_eval = ms / repeats;
     if (out_host) {
         const int nout = 1 + 19 * N + 1;
@@ -664,12 +687,7 @@ void svsdf_default_lbfgs_params(svsdf_lbfgs_params *p) {
     p->cautious_factor = d.cautious_factor; p->machine_prec = d.machine_prec;
 }
 
-int svsdf_optimize(svsdf_ctx *ctx, const double *initS, const double *finalS, double *opt_x, int N,
-                   const svsdf_lbfgs_params *params, svsdf_progress_t progress, void *user, double *T_out,
-                   double *coeffs_out, svsdf_opt_stats *stats) {
-    if (!ctx || !opt_x) return SVSDF_ERR_INVALID;
-    int rc = svsdf_set_boundary(ctx, initS, finalS, N);
-    if (rc) return rc;
+static host::LbfgsParams to_host_params(const svsdf_lbfgs_params *params) {
     svsdf_lbfgs_params dp;
     svsdf_default_lbfgs_params(&dp);
     if (!params) params = &dp;
@@ -679,6 +697,31 @@ int svsdf_optimize(svsdf_ctx *ctx, const double *initS, const double *finalS, do
     hp.min_step = params->min_step; hp.max_step = params->max_step; hp.f_dec_coeff = params->f_dec_coeff;
     hp.s_curv_coeff = params->s_curv_coeff; hp.cautious_factor = params->cautious_factor;
     hp.machine_prec = params->machine_prec;
+    return hp;
+}
+
+int svsdf_lbfgs_minimize(svsdf_eval_t eval, void *instance, double *x, int n, const svsdf_lbfgs_params *params,
+                         svsdf_progress_t progress, void *user, svsdf_opt_stats *stats) {
+    if (!eval || !x || n <= 0) return host::LBFGSERR_INVALID_N;
+    host::Lbfgs solver(to_host_params(params));
+    auto t0 = std::chrono::steady_clock::now();
+    host::LbfgsResult R = solver.minimize(x, n, eval, instance, progress, user);
+    auto t1 = std::chrono::steady_clock::now();
+    if (stats) {
+        stats->final_cost = R.f; stats->iterations = R.iterations; stats->evaluations = R.evaluations;
+        stats->status = R.status; stats->seconds = std::chrono::duration<double>(t1 - t0).count();
+        stats->gpu_seconds = 0.0;
+    }
+    return R.status;
+}
+
+int svsdf_optimize(svsdf_ctx *ctx, const double *initS, const double *finalS, double *opt_x, int N,
+                   const svsdf_lbfgs_params *params, svsdf_progress_t progress, void *user, double *T_out,
+                   double *coeffs_out, svsdf_opt_stats *stats) {
+    if (!ctx || !opt_x) return SVSDF_ERR_INVALID;
+    int rc = svsdf_set_boundary(ctx, initS, finalS, N);
+    if (rc) return rc;
+    host::LbfgsParams hp = to_host_params(params);
     const int n = N + 3 * (N - 1);
     ctx->gpu_ms_total = 0.0;
     ctx->time_kernels = true;
@@ -760,6 +803,12 @@ static int shape_eval(svsdf_ctx *ctx, int64_t n, const double *rel, double *out,
 }
 int svsdf_shape_sdf(svsdf_ctx *ctx, int64_t n, const double *rel, double *sdf_out) { return shape_eval(ctx, n, rel, sdf_out, 0); }
 int svsdf_shape_grad1(svsdf_ctx *ctx, int64_t n, const double *rel, double *grad3_out) { return shape_eval(ctx, n, rel, grad3_out, 1); }
+
+int svsdf_last_kernel_ms(const svsdf_ctx *ctx, float *out4) {
+    if (!ctx || !out4) return SVSDF_ERR_INVALID;
+    for (int k = 0; k < 4; ++k) out4[k] = ctx->last_kernel_ms[k];
+    return SVSDF_OK;
+}
 
 int svsdf_kernel_launches(const svsdf_ctx *ctx, int64_t *count) {
     if (!ctx || !count) return SVSDF_ERR_INVALID;

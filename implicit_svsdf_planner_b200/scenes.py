@@ -179,45 +179,40 @@ def make_scene(
     path = eval_traj_xy(b, T, ts)[:, :2]
 
     rng = _rng(seed_map)
-    # choose the resolution so that the candidate set (in boxes, outside the corridor) is ~3.5x P
-    area = 0.0
-    res = 0.25
-    for _ in range(40):
+    # choose the resolution so that the candidate set (in boxes, outside the corridor) is ~3.3x P: count candidates
+    # on a coarse 0.25 m grid, then scale (cells ~ 1 / res^2)
+    def grid(res):
         nx = int(math.ceil((hi[0] - lo[0]) / res))
         ny = int(math.ceil((hi[1] - lo[1]) / res))
-        if nx * ny > 60_000_000:
-            break
         xs = lo[0] + (np.arange(nx) + 0.5) * res
         ys = lo[1] + (np.arange(ny) + 0.5) * res
-        cand = _candidates(xs, ys, wps, half, path, clearance, rng_jitter=None)
-        if cand.shape[0] >= 3.0 * P:
-            break
-        res *= 0.8
+        return _candidates(xs, ys, wps, half, path, clearance)
+
+    res = 0.25
+    cand = grid(res)
+    if cand.shape[0] < 3.0 * P:
+        res = 0.25 * math.sqrt(cand.shape[0] / (3.3 * P))
+        cand = grid(res)
     if cand.shape[0] < P:
         raise ValueError(f"scene too small for P={P} (candidates={cand.shape[0]})")
     sel = np.sort(rng.choice(cand.shape[0], size=P, replace=False))  # keep grid (row-major) order
     pts = np.zeros((P, 3))
     pts[:, :2] = cand[sel]
     pts[:, 2] = rng.integers(0, 3, size=P) * YAML["occupancy_resolution"]  # stacked voxels; z is ignored by the cost
-    del area
     return Scene(shape=shape, N=N, init_s=init_s, final_s=final_s, q=q, T=T, coeffs=b, points=pts, resolution=res)
 
 
-def _candidates(xs, ys, wps, half, path, clearance, rng_jitter=None):
+def _candidates(xs, ys, wps, half, path, clearance):
+    from scipy.spatial import cKDTree
+
     gx, gy = np.meshgrid(xs, ys, indexing="xy")  # row-major: y rows, x fastest
     pts = np.stack([gx.ravel(), gy.ravel()], axis=1)
     inbox = np.zeros(pts.shape[0], dtype=bool)
     for w in wps:
         inbox |= (np.abs(pts[:, 0] - w[0]) <= half) & (np.abs(pts[:, 1] - w[1]) <= half)
     pts = pts[inbox]
-    # distance to the sampled path (chunked)
-    keep = np.ones(pts.shape[0], dtype=bool)
-    sub = path[::8]
-    for s in range(0, pts.shape[0], 200_000):
-        blk = pts[s : s + 200_000]
-        d2 = ((blk[:, None, :] - sub[None, :, :]) ** 2).sum(axis=2).min(axis=1)
-        keep[s : s + 200_000] = d2 > clearance * clearance
-    return pts[keep]
+    d, _ = cKDTree(path).query(pts, k=1)  # distance to the densely sampled nominal path
+    return pts[d > clearance]
 
 
 def make_batch_problems(n_problems: int, seed: int = SEED_BATCH, extent=(2.0, 58.0)):

@@ -134,6 +134,12 @@ int svsdf_optimize(svsdf_ctx *ctx, const double *initS, const double *finalS, do
                    const svsdf_lbfgs_params *params, svsdf_progress_t progress, void *user, double *T_out,
                    double *coeffs_out, svsdf_opt_stats *stats);
 
+/* Host L-BFGS on an arbitrary callback (same role as lbfgs::lbfgs_optimize, utils/include/utils/lbfgs_ref.hpp:434):
+ * minimises eval(instance, x, g, n) from x (in/out).  Re-entrant.  Returns the lbfgs_ref.hpp status code. */
+typedef double (*svsdf_eval_t)(void *instance, const double *x, double *g, const int n);
+int svsdf_lbfgs_minimize(svsdf_eval_t eval, void *instance, double *x, int n, const svsdf_lbfgs_params *params,
+                         svsdf_progress_t progress, void *user, svsdf_opt_stats *stats);
+
 /* R7: host MINCO_S3NU. q: 3 x (N-1) column-major. Outputs may be NULL. */
 int svsdf_minco_forward(const double *initS, const double *finalS, int N, const double *q, const double *T,
                         double *coeffs_out, double *energy, double *gradC_out, double *gradT_out);
@@ -155,6 +161,9 @@ int svsdf_cost_grad_device(svsdf_ctx *ctx, int N, const double *T, const double 
                            float *ms_per_eval, double *out_host);
 
 /* Measurement helpers */
+/* Device time (ms, CUDA events on the context's stream) of the kernels of the last svsdf_cost_grad_device
+ * evaluation: out4 = { k_pose_table, k_outer, k_compact + k_gsip, k_finalize }. */
+int svsdf_last_kernel_ms(const svsdf_ctx *ctx, float *out4);
 int svsdf_kernel_launches(const svsdf_ctx *ctx, int64_t *count);       /* kernels launched by this ctx so far */
 int svsdf_executed_evals(svsdf_ctx *ctx, int enable, uint64_t *count); /* lane-level SDF evaluations counter */
 int svsdf_fp64_peak(svsdf_ctx *ctx, double *tflops);                   /* measured DFMA peak (2 flop/FMA) */

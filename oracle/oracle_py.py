@@ -13,24 +13,26 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libsvsdf_oracle.so")
-_lib = None
+_SO_FMA = os.path.join(_HERE, "_build", "libsvsdf_oracle_fma.so")
+_libs = {}
 
 dp = C.POINTER(C.c_double)
 
 
 def build(force: bool = False) -> str:
     srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "svsdf_oracle.hpp", "minco_oracle.hpp", "shapes.hpp")]
-    stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
+    stale = any((not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+                for so in (_SO, _SO_FMA))
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
 
 
-def lib():
-    global _lib
-    if _lib is None:
+def lib(variant: str = "default"):
+    """variant "default": no FMA contraction (the reference's x86-64 build); "fma": -ffp-contract=fast -mfma."""
+    if variant not in _libs:
         build()
-        L = C.CDLL(_SO)
+        L = C.CDLL(_SO if variant == "default" else _SO_FMA)
         L.orc_create.restype = C.c_void_p
         L.orc_create.argtypes = [C.c_char_p, dp, dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]
         L.orc_destroy.argtypes = [C.c_void_p]
@@ -70,8 +72,8 @@ def lib():
         L.orc_lbfgs.argtypes = [C.c_void_p, dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, dp]
         L.orc_max_threads.restype = C.c_int
         L.orc_num_procs.restype = C.c_int
-        _lib = L
-    return _lib
+        _libs[variant] = L
+    return _libs[variant]
 
 
 def _p(a):
@@ -132,73 +134,75 @@ def minco_propagate(init_s, final_s, q, T, gdC, gdT):
 class Oracle:
     """Handle on the CPU restatement of TrajOptimizer + SweptVolumeManager for one shape."""
 
-    def __init__(self, shape="star", poly_params=(0.0, 0.0, 0.0), weight_p=60.0, safety_hor=0.7, rho=3.8, threads=1, polygon=None):
+    def __init__(self, shape="star", poly_params=(0.0, 0.0, 0.0), weight_p=60.0, safety_hor=0.7, rho=3.8, threads=1, polygon=None,
+                 variant="default"):
         pp = _f64(poly_params)
         poly = _f64(polygon).reshape(-1) if polygon is not None else None
-        self.h = lib().orc_create(shape.encode(), _p(pp), _p(poly), 0 if poly is None else poly.size // 2, weight_p, safety_hor, rho, threads)
+        self.L = lib(variant)
+        self.h = self.L.orc_create(shape.encode(), _p(pp), _p(poly), 0 if poly is None else poly.size // 2, weight_p, safety_hor, rho, threads)
         self.N = 0
 
     def __del__(self):
         try:
             if self.h:
-                lib().orc_destroy(self.h)
+                self.L.orc_destroy(self.h)
                 self.h = None
         except Exception:
             pass
 
     def set_threads(self, n):
-        lib().orc_set_threads(self.h, int(n))
+        self.L.orc_set_threads(self.h, int(n))
 
     def set_points(self, pts):
         pts = _f64(pts)
-        lib().orc_set_points(self.h, _p(pts), pts.shape[0], pts.shape[1])
+        self.L.orc_set_points(self.h, _p(pts), pts.shape[0], pts.shape[1])
         self.P = pts.shape[0]
 
     def set_traj(self, T, coeffs_colmajor):
         T = _f64(T)
         c = _f64(coeffs_colmajor).reshape(-1)
         self.N = T.shape[0]
-        lib().orc_set_traj(self.h, self.N, _p(T), _p(c))
+        self.L.orc_set_traj(self.h, self.N, _p(T), _p(c))
 
     def duration(self):
-        return lib().orc_traj_duration(self.h)
+        return self.L.orc_traj_duration(self.h)
 
     def traj_pos(self, t):
         out = np.empty(3)
-        lib().orc_traj_pos(self.h, float(t), _p(out))
+        self.L.orc_traj_pos(self.h, float(t), _p(out))
         return out
 
     def traj_vel(self, t):
         out = np.empty(3)
-        lib().orc_traj_vel(self.h, float(t), _p(out))
+        self.L.orc_traj_vel(self.h, float(t), _p(out))
         return out
 
     def sdf_at(self, p, t):
         p = _f64(p)
-        return lib().orc_sdf_at(self.h, _p(p), float(t))
+        return self.L.orc_sdf_at(self.h, _p(p), float(t))
 
     def choice_t_init(self, p, dt=0.15):
         p = _f64(p)
-        return lib().orc_choice_t_init(self.h, _p(p), dt)
+        return self.L.orc_choice_t_init(self.h, _p(p), dt)
 
     def gradient_descent(self, p, tmin, tmax, x0):
         p = _f64(p)
         fx = C.c_double()
         x = C.c_double()
-        lib().orc_gradient_descent(self.h, _p(p), tmin, tmax, x0, C.cast(C.byref(fx), dp), C.cast(C.byref(x), dp))
+        self.L.orc_gradient_descent(self.h, _p(p), tmin, tmax, x0, C.cast(C.byref(fx), dp), C.cast(C.byref(x), dp))
         return fx.value, x.value
 
     def count_evals(self, on=True):
-        lib().orc_count_evals(self.h, 1 if on else 0)
+        self.L.orc_count_evals(self.h, 1 if on else 0)
 
     def eval_count(self):
-        return int(lib().orc_eval_count(self.h))
+        return int(self.L.orc_eval_count(self.h))
 
     def query_outer(self, pts):
         pts = _f64(pts).reshape(-1, 3)
         n = pts.shape[0]
         sdf, ts, g = np.empty(n), np.empty(n), np.empty((n, 3))
-        lib().orc_query_outer(self.h, n, _p(pts), _p(sdf), _p(ts), _p(g))
+        self.L.orc_query_outer(self.h, n, _p(pts), _p(sdf), _p(ts), _p(g))
         return sdf, ts, g
 
     def query(self, pts):
@@ -206,7 +210,7 @@ class Oracle:
         n = pts.shape[0]
         sdf, ts, g = np.empty(n), np.empty(n), np.empty((n, 3))
         rounds = np.zeros(n, dtype=np.int32)
-        lib().orc_query(self.h, n, _p(pts), _p(sdf), _p(ts), _p(g), rounds.ctypes.data_as(C.POINTER(C.c_int)))
+        self.L.orc_query(self.h, n, _p(pts), _p(sdf), _p(ts), _p(g), rounds.ctypes.data_as(C.POINTER(C.c_int)))
         return sdf, ts, g, rounds
 
     def cost_grad(self, T, coeffs_colmajor, cost0=0.0, gradT0=None, gradC0=None, per_point=False):
@@ -217,43 +221,43 @@ class Oracle:
         gT = np.zeros(N) if gradT0 is None else _f64(gradT0).copy()
         gC = np.zeros(18 * N) if gradC0 is None else _f64(gradC0).reshape(-1).copy()
         pp = np.empty((self.P, 7)) if per_point else None
-        inside = lib().orc_cost_grad(self.h, N, _p(T), _p(c), C.cast(C.byref(cost), dp), _p(gT), _p(gC), _p(pp))
+        inside = self.L.orc_cost_grad(self.h, N, _p(T), _p(c), C.cast(C.byref(cost), dp), _p(gT), _p(gC), _p(pp))
         return cost.value, gT, gC, pp, int(inside)
 
     def time_cost_grad(self, T, coeffs_colmajor, warm=1, reps=3):
         T = _f64(T)
         c = _f64(coeffs_colmajor).reshape(-1)
         cost = C.c_double()
-        sec = lib().orc_time_cost_grad(self.h, T.shape[0], _p(T), _p(c), warm, reps, C.cast(C.byref(cost), dp))
+        sec = self.L.orc_time_cost_grad(self.h, T.shape[0], _p(T), _p(c), warm, reps, C.cast(C.byref(cost), dp))
         return sec, cost.value
 
     def set_conditions(self, init_s, final_s, N):
         i_s = _f64(np.asarray(init_s).T).reshape(-1)
         f_s = _f64(np.asarray(final_s).T).reshape(-1)
         self.N = N
-        lib().orc_set_conditions(self.h, _p(i_s), _p(f_s), N)
+        self.L.orc_set_conditions(self.h, _p(i_s), _p(f_s), N)
 
     def evaluate(self, x):
         x = _f64(x)
         g = np.empty_like(x)
-        f = lib().orc_evaluate(self.h, _p(x), _p(g), x.shape[0])
+        f = self.L.orc_evaluate(self.h, _p(x), _p(g), x.shape[0])
         return f, g
 
     def last_costs(self):
         out = np.empty(3)
-        lib().orc_last_costs(self.h, _p(out))
+        self.L.orc_last_costs(self.h, _p(out))
         return out
 
     def get_coeffs(self):
         T = np.empty(self.N)
         b = np.empty(18 * self.N)
-        lib().orc_get_coeffs(self.h, _p(T), _p(b))
+        self.L.orc_get_coeffs(self.h, _p(T), _p(b))
         return T, b
 
     def lbfgs(self, x0, mem_size=16, past=3, delta=1e-6, g_epsilon=0.0, max_iterations=0, min_step=1e-32):
         x = _f64(x0).copy()
         stats = np.zeros(4)
-        ret = lib().orc_lbfgs(self.h, _p(x), x.shape[0], mem_size, past, delta, g_epsilon, max_iterations, min_step, _p(stats))
+        ret = self.L.orc_lbfgs(self.h, _p(x), x.shape[0], mem_size, past, delta, g_epsilon, max_iterations, min_step, _p(stats))
         return ret, x, dict(f=stats[0], iters=int(stats[1]), evals=int(stats[2]), seconds=stats[3])
 
 

@@ -1,0 +1,105 @@
+"""CPU, world_size = 2 over gloo: the host-side logic of the batch-of-problems mode (map packing + broadcast,
+contiguous sharding with no data-path collective, result gather).  The per-problem solver is a CPU stand-in injected
+into BatchRunner (the real one wraps the CUDA context and is exercised by the GPU bench)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from implicit_svsdf_planner_b200 import batch, scenes  # noqa: E402
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _fake_solve(scene, k):
+    # deterministic function of the problem's inputs only (what a real solver's result would depend on)
+    return np.array([k, scene.P, float(scene.points[:, :2].sum()), float(scene.q.sum())])
+
+
+def _worker(rank, world, port, tmpdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        gm = batch.make_random_map(extent=60.0, res=0.5, density=0.3, seed=123) if rank == 0 else None
+        kern = batch.pack_map_kernel(gm.occ, 17) if rank == 0 else None
+        t = batch.broadcast_map(kern)  # the only collective before the run
+        X = Y = 120
+        occ = batch.unpack_map_kernel(t.numpy(), X, Y, 17)
+        gm_local = batch.GridMap(occ=occ, origin=np.zeros(2), res=0.5)
+        problems = scenes.make_batch_problems(7, seed=99)
+        runner = batch.BatchRunner(_fake_solve, 4)
+        out = runner.run(gm_local, problems, N=8, P=None)
+        np.save(os.path.join(tmpdir, f"out_{rank}.npy"), out)
+        np.save(os.path.join(tmpdir, f"occ_{rank}.npy"), occ)
+        mine = list(batch.partition(7, world, rank))
+        np.save(os.path.join(tmpdir, f"mine_{rank}.npy"), np.array(mine))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partition_is_a_contiguous_cover():
+    for n in (0, 1, 7, 8, 4096):
+        for w in (1, 2, 3, 8):
+            parts = [list(batch.partition(n, w, r)) for r in range(w)]
+            flat = [i for p in parts for i in p]
+            assert flat == list(range(n))
+            sizes = [len(p) for p in parts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_map_kernel_packing_matches_reference_layout():
+    rng = np.random.default_rng(0)
+    occ = rng.random((13, 21)) < 0.4
+    k = batch.pack_map_kernel(occ, 17)
+    h = 8
+    assert k.shape == (13 + 2 * h, (21 + 2 * h + 7) // 8) and k.dtype == np.uint8
+    # bit (x, y) lives in byte [(x+h), (y+h)//8] under mask 0x80 >> ((y+h) % 8)   (PCSmap_manager.h:32, 96-103)
+    for x, y in ((0, 0), (5, 7), (12, 20), (3, 15)):
+        bit = (k[x + h, (y + h) // 8] >> (7 - (y + h) % 8)) & 1
+        assert bool(bit) == bool(occ[x, y])
+    assert np.array_equal(batch.unpack_map_kernel(k, 13, 21, 17), occ)
+    assert int(np.unpackbits(k).sum()) == int(occ.sum())  # the padding ring stays empty
+
+
+def test_query_point_extraction_dedups_and_skips_previous_box():
+    occ = np.ones((40, 40), dtype=bool)
+    gm = batch.GridMap(occ=occ, origin=np.zeros(2), res=1.0)
+    half = 3.0
+    one = batch.extract_query_points(gm, np.array([[10.5, 10.5]]), half)
+    assert one.shape[0] == 7 * 7 and np.all(one[:, 2] == 0)
+    two = batch.extract_query_points(gm, np.array([[10.5, 10.5], [12.5, 10.5]]), half)
+    assert two.shape[0] == 7 * 7 + 2 * 7  # only the two new columns of the second box
+    assert np.unique(two[:, :2], axis=0).shape[0] == two.shape[0]
+    # cell centres: min + (idx + 0.5) * res
+    assert np.allclose(np.modf(one[:, :2])[0], 0.5)
+
+
+def test_world_size_2_gloo_broadcast_shard_gather(tmp_path):
+    world = 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    o0, o1 = np.load(tmp_path / "out_0.npy"), np.load(tmp_path / "out_1.npy")
+    assert np.array_equal(o0, o1) and not np.isnan(o0).any()  # every rank ends with all results
+    assert np.array_equal(np.load(tmp_path / "occ_0.npy"), np.load(tmp_path / "occ_1.npy"))  # map arrived intact
+    m0, m1 = np.load(tmp_path / "mine_0.npy"), np.load(tmp_path / "mine_1.npy")
+    assert list(m0) == [0, 1, 2, 3] and list(m1) == [4, 5, 6]
+    # multi-rank result == single-process result (problems are independent)
+    gm = batch.make_random_map(extent=60.0, res=0.5, density=0.3, seed=123)
+    problems = scenes.make_batch_problems(7, seed=99)
+    ref = batch.BatchRunner(_fake_solve, 4).run(gm, problems, N=8, P=None)
+    assert np.array_equal(ref, o0)
+    assert np.array_equal(o0[:, 0], np.arange(7))

@@ -1,0 +1,383 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI (include/svsdf.h via
+implicit_svsdf_planner_b200.api), against the CPU oracle on the same seeded inputs and against the committed golden
+vectors.
+
+Tolerances (north_star: cost and gradient within 1e-6 relative of the reference):
+  * cost                         rel <= 1e-9   (observed ~1e-15)
+  * per-point sdf                abs <= 1e-9   (observed ~1e-13)
+  * gradients, strict_fp build   normwise rel <= 1e-6 vs the oracle (the reference's x86-64, un-fused arithmetic)
+  * gradients, default build     normwise rel <= 1e-6 vs the oracle compiled with FMA contraction, and <= 1e-4 vs
+                                 the un-fused oracle: the reference algorithm itself moves by ~1e-5 in gradC when
+                                 its own source is compiled with contraction (flat minima of t -> sdf at the
+                                 trajectory ends, where the robot is at rest), see
+                                 test_reference_algorithm_is_sensitive_to_fma_contraction and DESIGN.md §Parity.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from implicit_svsdf_planner_b200 import api, scenes
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+ALL_SHAPES = ["star", "sdHorseshoe", "sdPie", "sdPie2", "sdArc", "sdTunnel", "sdCutDisk", "sdTrapezoid", "sdRhombus",
+              "sdHeart", "sdRoundedX", "bigX", "sdRoundedCross", "sdOrientedVesica", "sdMoon", "sdUnevenCapsule",
+              "Circle", "unknown_mesh_shape"]
+
+
+def nrel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def pts0(sc):
+    return np.c_[sc.points[:, :2], np.zeros(sc.P)]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# R5: shape functors
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("strict", [False, True])
+def test_shape_functors_match_oracle(oracle_mod, strict):
+    rng = np.random.default_rng(42)
+    rel = np.c_[rng.uniform(-7, 7, size=(5000, 2)), np.zeros(5000)]
+    for pp in ((0.0, 0.0, 0.0), (0.6, -0.3, 25.0)):
+        for name in ALL_SHAPES:
+            ctx = api.Context(name, poly_params=pp, strict_fp=strict)
+            s_gpu = ctx.shape_sdf(rel)
+            s_cpu = oracle_mod.shape_sdf(name, rel, poly_params=pp)
+            assert np.abs(s_gpu - s_cpu).max() <= 1e-12, (name, pp, np.abs(s_gpu - s_cpu).max())
+            g_gpu = ctx.shape_grad1(rel)
+            g_cpu = oracle_mod.shape_grad1(name, rel, poly_params=pp)
+            # FD with dx = 1e-6 amplifies 1-ulp differences by 1e6/2; compare away from SDF creases
+            ok = np.abs(g_gpu - g_cpu).max(axis=1) < 1e-6
+            assert ok.mean() > 0.995, (name, pp, ok.mean())
+            ctx.close()
+
+
+def test_custom_polygon_fallback(oracle_mod):
+    poly = [3.0, -1.0, 3.0, 1.0, 0.0, 2.5, -3.0, 1.0, -3.0, -1.0]
+    rng = np.random.default_rng(1)
+    rel = np.c_[rng.uniform(-6, 6, size=(2000, 2)), np.zeros(2000)]
+    ctx = api.Context("custom_poly", polygon=poly)
+    assert np.abs(ctx.shape_sdf(rel) - oracle_mod.shape_sdf("custom_poly", rel, polygon=poly)).max() < 1e-12
+    g_gpu, g_cpu = ctx.shape_grad1(rel), oracle_mod.shape_grad1("custom_poly", rel, polygon=poly)
+    assert (np.abs(g_gpu - g_cpu).max(axis=1) < 1e-9).mean() > 0.995
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# R2: per-point swept-volume SDF queries
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("strict", [False, True])
+def test_query_outer_and_true_sdf_match_oracle(oracle_mod, scene2k, scene_small_inside, strict):
+    for sc in (scene2k, scene_small_inside):
+        co = sc.coeffs_colmajor()
+        opt = api.TrajOptimizer("star", strict_fp=strict)
+        sv = opt.sv_manager
+        sv.updateTraj(sc.T, co)
+        orc = oracle_mod.Oracle("star", threads=oracle_mod.num_procs(), variant="default" if strict else "fma")
+        orc.set_traj(sc.T, co)
+        p = pts0(sc)
+        s_c, t_c, g_c = orc.query_outer(p)
+        s_g, t_g, g_g = sv.getSDFofSweptVolume(p)
+        assert np.abs(s_g - s_c).max() <= 1e-9
+        # t* is only defined up to the flatness of t -> sdf(t) (see module docstring); sdf is what must agree
+        assert np.median(np.abs(t_g - t_c)) <= 1e-7
+        assert (np.abs(g_g - g_c).max(axis=1) < 1e-5).mean() > 0.99
+        s_c, t_c, g_c, r_c = orc.query(p)
+        s_g, t_g, g_g, r_g = sv.getTrueSDFofSweptVolume(p)
+        assert np.array_equal(r_c, r_g)  # same GSIP round count for every point
+        assert np.abs(s_g - s_c).max() <= 1e-9
+        inside = s_c <= 0
+        if inside.any():
+            assert np.abs(g_g[inside] - g_c[inside]).max() <= 1e-9  # world-frame unit direction
+            assert np.abs(np.linalg.norm(g_g[inside], axis=1) - 1.0).max() < 1e-12
+
+
+def test_query_matches_committed_golden():
+    for name in ("config1_star_2k.npz", "config_inside_400.npz"):
+        G = np.load(os.path.join(HERE, "golden", name))
+        ctx = api.Context(str(G["shape"]), weight_p=float(G["weight_p"]), safety_hor=float(G["safety_hor"]),
+                          rho=float(G["rho"]), strict_fp=True)
+        p = np.c_[G["points"][:, :2], np.zeros(G["points"].shape[0])]
+        s, t, g, r = ctx.query(G["T"], G["coeffs_colmajor"], p)
+        assert np.array_equal(r, G["query_rounds"])
+        assert np.abs(s - G["query_sdf"]).max() <= 1e-9
+        assert np.median(np.abs(t - G["query_tstar"])) <= 1e-7
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# R1: cost + gradient accumulation
+# ----------------------------------------------------------------------------------------------------------------
+def test_cost_grad_strict_matches_oracle_within_1e6(oracle_mod, scene2k, scene_small_inside):
+    for sc in (scene2k, scene_small_inside):
+        co = sc.coeffs_colmajor()
+        opt = api.TrajOptimizer("star", weight_p=sc.weight_p, safety_hor=sc.safety_hor, rho=sc.rho, strict_fp=True)
+        opt.parallel_points = sc.points
+        orc = oracle_mod.Oracle("star", threads=oracle_mod.num_procs())
+        orc.set_points(sc.points)
+        c0, gT0, gC0, _, inside = orc.cost_grad(sc.T, co)
+        c1, gT1, gC1 = opt.addSaftyPenaOnSweptVolumeParallelTrueSDF(sc.T, co)
+        assert abs(c1 - c0) <= 1e-9 * abs(c0)
+        assert nrel(gC1, gC0) <= 1e-6 and nrel(gT1, gT0) <= 1e-6, (nrel(gC1, gC0), nrel(gT1, gT0))
+
+
+def test_cost_grad_default_build_matches_fma_oracle(oracle_mod, scene2k, scene_small_inside):
+    for sc in (scene2k, scene_small_inside):
+        co = sc.coeffs_colmajor()
+        opt = api.TrajOptimizer("star", strict_fp=False)
+        opt.parallel_points = sc.points
+        c1, gT1, gC1 = opt.addSaftyPenaOnSweptVolumeParallelTrueSDF(sc.T, co)
+        o_fma = oracle_mod.Oracle("star", threads=oracle_mod.num_procs(), variant="fma")
+        o_fma.set_points(sc.points)
+        c0, gT0, gC0, _, _ = o_fma.cost_grad(sc.T, co)
+        assert abs(c1 - c0) <= 1e-9 * abs(c0)
+        assert nrel(gC1, gC0) <= 1e-6 and nrel(gT1, gT0) <= 1e-6, (nrel(gC1, gC0), nrel(gT1, gT0))
+        o_ref = oracle_mod.Oracle("star", threads=oracle_mod.num_procs())
+        o_ref.set_points(sc.points)
+        c2, gT2, gC2, _, _ = o_ref.cost_grad(sc.T, co)
+        assert abs(c1 - c2) <= 1e-9 * abs(c2)
+        assert nrel(gC1, gC2) <= 1e-4 and nrel(gT1, gT2) <= 1e-4
+
+
+def test_reference_algorithm_is_sensitive_to_fma_contraction(oracle_mod, scene2k):
+    """Documents the noise floor: the reference's own algorithm, compiled from the same source with and without FMA
+    contraction, disagrees with itself in gradC by ~1e-5 on config 1 while the cost agrees to 1e-15."""
+    sc = scene2k
+    co = sc.coeffs_colmajor()
+    a = oracle_mod.Oracle("star", threads=oracle_mod.num_procs())
+    b = oracle_mod.Oracle("star", threads=oracle_mod.num_procs(), variant="fma")
+    a.set_points(sc.points)
+    b.set_points(sc.points)
+    ca, gTa, gCa, ppa, _ = a.cost_grad(sc.T, co, per_point=True)
+    cb, gTb, gCb, ppb, _ = b.cost_grad(sc.T, co, per_point=True)
+    assert abs(ca - cb) <= 1e-12 * abs(ca)
+    assert 1e-7 < nrel(gCb, gCa) < 1e-4
+    # the disagreement comes from a handful of points whose minimiser sits in the flat end of the trajectory
+    dt = np.abs(ppa[:, 1] - ppb[:, 1])
+    worst = np.argsort(-dt)[:5]
+    assert np.all(ppa[worst, 1] > sc.T.sum() - 0.01) or np.all(ppa[worst, 1] < 0.01)
+
+
+def test_cost_grad_accumulates_and_is_bitwise_deterministic(scene2k):
+    sc = scene2k
+    co = sc.coeffs_colmajor()
+    ctx = api.Context("star")
+    ctx.set_points(sc.points)
+    c1, gT1, gC1 = ctx.cost_grad(sc.T, co)
+    c2, gT2, gC2 = ctx.cost_grad(sc.T, co)
+    assert c1 == c2 and np.array_equal(gT1, gT2) and np.array_equal(gC1, gC2)
+    rng = np.random.default_rng(0)
+    aT, aC = rng.normal(size=sc.N), rng.normal(size=18 * sc.N)
+    c3, gT3, gC3 = ctx.cost_grad(sc.T, co, cost0=7.0, gradT0=aT, gradC0=aC)
+    assert c3 == c1 + 7.0 and np.array_equal(gT3, gT1 + aT) and np.array_equal(gC3, gC1 + aC)
+    # a second context (fresh buffers) gives the same bits
+    ctx2 = api.Context("star")
+    ctx2.set_points(sc.points)
+    c4, gT4, gC4 = ctx2.cost_grad(sc.T, co)
+    assert c4 == c1 and np.array_equal(gC4, gC1)
+
+
+def test_cost_grad_matches_committed_golden():
+    for name in ("config1_star_2k.npz", "config_inside_400.npz"):
+        G = np.load(os.path.join(HERE, "golden", name))
+        ctx = api.Context(str(G["shape"]), weight_p=float(G["weight_p"]), safety_hor=float(G["safety_hor"]),
+                          rho=float(G["rho"]), strict_fp=True)
+        ctx.set_points(G["points"])
+        c, gT, gC = ctx.cost_grad(G["T"], G["coeffs_colmajor"])
+        assert abs(c - float(G["cost"])) <= 1e-9 * abs(c)
+        assert nrel(gC, G["gradC"]) <= 1e-6 and nrel(gT, G["gradT"]) <= 1e-6
+        ctx.set_boundary(G["init_s"], G["final_s"], int(G["N"]))
+        f, g = ctx.evaluate(G["x0"])
+        assert abs(f - float(G["eval_f"])) <= 1e-9 * abs(f)
+        assert nrel(g, G["eval_g"]) <= 1e-6
+
+
+@pytest.mark.parametrize("shape,N", [("sdHorseshoe", 16), ("sdPie", 8), ("sdTunnel", 5), ("sdRoundedCross", 8),
+                                     ("sdMoon", 8), ("unknown_mesh_shape", 8)])
+def test_other_shapes_and_piece_counts(oracle_mod, shape, N):
+    sc = scenes.make_scene(shape if shape in scenes.START_GOAL else "star", N, 600, clearance=2.0)
+    co = sc.coeffs_colmajor()
+    ctx = api.Context(shape, strict_fp=True)
+    ctx.set_points(sc.points)
+    orc = oracle_mod.Oracle(shape, threads=oracle_mod.num_procs())
+    orc.set_points(sc.points)
+    c0, gT0, gC0, pp, inside = orc.cost_grad(sc.T, co, per_point=True)
+    c1, gT1, gC1 = ctx.cost_grad(sc.T, co)
+    assert c0 > 0
+    assert abs(c1 - c0) <= 1e-9 * abs(c0), (shape, c1, c0)
+    assert nrel(gC1, gC0) <= 2e-6 and nrel(gT1, gT0) <= 2e-6, (shape, nrel(gC1, gC0), nrel(gT1, gT0))
+
+
+def test_body_frame_offset_of_the_shape(oracle_mod):
+    sc = scenes.make_scene("star", 8, 500, clearance=2.6)
+    co = sc.coeffs_colmajor()
+    pp = (0.4, -0.2, 20.0)
+    ctx = api.Context("star", poly_params=pp, strict_fp=True)
+    ctx.set_points(sc.points)
+    orc = oracle_mod.Oracle("star", poly_params=pp, threads=oracle_mod.num_procs())
+    orc.set_points(sc.points)
+    c0, gT0, gC0, _, _ = orc.cost_grad(sc.T, co)
+    c1, gT1, gC1 = ctx.cost_grad(sc.T, co)
+    assert abs(c1 - c0) <= 1e-9 * abs(c0) and nrel(gC1, gC0) <= 2e-6
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# R3 / R4: full cost callback and host optimiser
+# ----------------------------------------------------------------------------------------------------------------
+def test_evaluate_callback_matches_oracle(oracle_mod, scene2k):
+    sc = scene2k
+    opt = api.TrajOptimizer("star", weight_p=sc.weight_p, safety_hor=sc.safety_hor, rho=sc.rho, strict_fp=True)
+    opt.parallel_points = sc.points
+    opt.setConditions(sc.init_s, sc.final_s, sc.N)
+    orc = oracle_mod.Oracle("star", threads=oracle_mod.num_procs())
+    orc.set_points(sc.points)
+    orc.set_conditions(sc.init_s, sc.final_s, sc.N)
+    rng = np.random.default_rng(4)
+    for k in range(3):
+        x = sc.x0 + (0.05 * k) * rng.normal(size=sc.x0.size)
+        f0, g0 = orc.evaluate(x)
+        f1, g1 = opt.costFunction(x)
+        assert abs(f1 - f0) <= 1e-9 * abs(f0)
+        assert nrel(g1, g0) <= 1e-6, nrel(g1, g0)
+        assert np.abs(opt.ctx.last_costs() - orc.last_costs()).max() <= 1e-8 * abs(f0)
+
+
+def test_optimize_reduces_cost_and_final_point_agrees_with_oracle(oracle_mod):
+    sc = scenes.make_scene("star", 8, 1500, clearance=2.9)
+    opt = api.TrajOptimizer("star", weight_p=sc.weight_p, safety_hor=sc.safety_hor, rho=sc.rho, strict_fp=True)
+    opt.parallel_points = sc.points
+    opt.setConditions(sc.init_s, sc.final_s, sc.N)
+    f_start, _ = opt.costFunction(sc.x0)
+    params = api.default_lbfgs_params(mem_size=16, past=3, delta=1e-5, g_epsilon=0.0, max_iterations=40, min_step=1e-32)
+    rc, x, T, b, st = opt.optimize_traj(sc.init_s, sc.final_s, sc.x0, sc.N, params)
+    assert st["final_cost"] < f_start and st["iterations"] >= 3 and st["evaluations"] >= st["iterations"]
+    assert np.all(T > 0) and np.all(np.isfinite(b))
+    # final cost and gradient on identical inputs (the optimiser's final x) within 1e-6 of the oracle
+    orc = oracle_mod.Oracle("star", threads=oracle_mod.num_procs())
+    orc.set_points(sc.points)
+    orc.set_conditions(sc.init_s, sc.final_s, sc.N)
+    f0, g0 = orc.evaluate(x)
+    f1, g1 = opt.costFunction(x)
+    assert abs(f1 - f0) <= 1e-9 * abs(f0) and nrel(g1, g0) <= 1e-6
+    assert abs(st["final_cost"] - f1) <= 1e-9 * abs(f1)
+
+
+def test_progress_callback_can_cancel(scene2k):
+    sc = scene2k
+    opt = api.TrajOptimizer("star")
+    opt.parallel_points = sc.points[:500]
+    calls = []
+
+    def progress(_user, _x, k):
+        calls.append(k)
+        return 1 if k >= 2 else 0
+
+    rc, x, T, b, st = opt.optimize_traj(sc.init_s, sc.final_s, sc.x0, sc.N, api.default_lbfgs_params(max_iterations=50), progress)
+    assert calls == [1, 2] and st["status"] == 2 and rc == 2  # LBFGS_CANCELED
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Edge cases and error behaviour
+# ----------------------------------------------------------------------------------------------------------------
+def test_edge_cases(oracle_mod, scene2k):
+    sc = scene2k
+    co = sc.coeffs_colmajor()
+    ctx = api.Context("star", strict_fp=True)
+    # empty query set
+    ctx.set_points(np.zeros((0, 3)))
+    c, gT, gC = ctx.cost_grad(sc.T, co)
+    assert c == 0.0 and not gT.any() and not gC.any()
+    s, t, g, r = ctx.query(sc.T, co, np.zeros((0, 3)))
+    assert s.size == 0
+    # one point; duplicated points act as integer weights
+    one = sc.points[[np.argmin(np.abs(sc.points[:, 0] - 12.0))]]
+    ctx.set_points(one)
+    c1, gT1, gC1 = ctx.cost_grad(sc.T, co)
+    ctx.set_points(np.repeat(one, 3, axis=0))
+    c3, gT3, gC3 = ctx.cost_grad(sc.T, co)
+    assert abs(c3 - 3 * c1) <= 1e-12 * max(1.0, abs(c3)) and np.allclose(gC3, 3 * gC1, rtol=1e-12, atol=1e-12)
+    # far away points: no penalty at all
+    far = sc.points.copy()
+    far[:, 1] += 1000.0
+    ctx.set_points(far)
+    c, gT, gC = ctx.cost_grad(sc.T, co)
+    assert c == 0.0 and not gT.any() and not gC.any()
+    # stride-2 input equals stride-3 input; z is ignored
+    ctx.set_points(sc.points[:100, :2])
+    a = ctx.cost_grad(sc.T, co)
+    zz = sc.points[:100].copy()
+    zz[:, 2] = 123.0
+    ctx.set_points(zz)
+    b = ctx.cost_grad(sc.T, co)
+    assert a[0] == b[0] and np.array_equal(a[2], b[2])
+    # minimal and larger piece counts
+    for N in (2, 3, 32):
+        scn = scenes.make_scene("star", N, 200, clearance=2.6)
+        ctx.set_points(scn.points)
+        orc = oracle_mod.Oracle("star", threads=oracle_mod.num_procs())
+        orc.set_points(scn.points)
+        c0, gT0, gC0, _, _ = orc.cost_grad(scn.T, scn.coeffs_colmajor())
+        c1, gT1, gC1 = ctx.cost_grad(scn.T, scn.coeffs_colmajor())
+        assert abs(c1 - c0) <= 1e-9 * max(1.0, abs(c0)) and nrel(gC1, gC0) <= 2e-6, (N, c1, c0)
+
+
+def test_errors_are_reported_not_thrown(scene2k):
+    sc = scene2k
+    co = sc.coeffs_colmajor()
+    ctx = api.Context("star")
+    with pytest.raises(api.SvsdfError):  # points not set
+        ctx.cost_grad(sc.T, co)
+    ctx.set_points(sc.points[:10])
+    with pytest.raises(api.SvsdfError):  # too many pieces
+        ctx.cost_grad(np.full(65, 1.0), np.zeros(18 * 65))
+    with pytest.raises(api.SvsdfError):  # total duration >= 300 s (sw_manager.hpp:380)
+        ctx.cost_grad(sc.T * 20.0, co)
+    bad = sc.T.copy()
+    bad[2] = -1.0
+    with pytest.raises(api.SvsdfError):
+        ctx.cost_grad(bad, co)
+    with pytest.raises(api.SvsdfError):  # evaluate without boundary conditions
+        ctx.evaluate(sc.x0)
+    # the context still works afterwards
+    c, _, _ = ctx.cost_grad(sc.T, co)
+    assert np.isfinite(c)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Full-size (BASELINE config 2: 200k points) size-independent properties
+# ----------------------------------------------------------------------------------------------------------------
+def test_full_size_properties_200k(oracle_mod):
+    sc = scenes.make_scene("star", 8, 200_000)
+    co = sc.coeffs_colmajor()
+    ctx = api.Context("star")
+    ctx.set_points(sc.points)
+    c, gT, gC = ctx.cost_grad(sc.T, co)
+    assert np.isfinite(c) and c > 0
+    # additivity over a partition of the query set
+    half = sc.P // 2
+    ctx.set_points(sc.points[:half])
+    ca, gTa, gCa = ctx.cost_grad(sc.T, co)
+    ctx.set_points(sc.points[half:])
+    cb, gTb, gCb = ctx.cost_grad(sc.T, co)
+    assert abs((ca + cb) - c) <= 1e-11 * c and nrel(gCa + gCb, gC) <= 1e-11 and nrel(gTa + gTb, gT) <= 1e-11
+    # permutation invariance
+    perm = np.random.default_rng(3).permutation(sc.P)
+    ctx.set_points(sc.points[perm])
+    cp, gTp, gCp = ctx.cost_grad(sc.T, co)
+    assert abs(cp - c) <= 1e-11 * c and nrel(gCp, gC) <= 1e-11
+    # spot check of a random subset against the oracle (per-point sdf) and its share of the cost
+    idx = np.sort(np.random.default_rng(5).choice(sc.P, size=1500, replace=False))
+    sub = sc.points[idx]
+    orc = oracle_mod.Oracle("star", threads=oracle_mod.num_procs())
+    orc.set_points(sub)
+    c0, gT0, gC0, _, _ = orc.cost_grad(sc.T, co)
+    ctx.set_points(sub)
+    c1, gT1, gC1 = ctx.cost_grad(sc.T, co)
+    assert abs(c1 - c0) <= 1e-9 * abs(c0) and nrel(gC1, gC0) <= 1e-4
+    s_g, t_g, g_g, r_g = ctx.query(sc.T, co, np.c_[sub[:, :2], np.zeros(len(sub))])
+    orc.set_traj(sc.T, co)
+    s_c, t_c, g_c, r_c = orc.query(np.c_[sub[:, :2], np.zeros(len(sub))])
+    assert np.abs(s_g - s_c).max() <= 1e-9 and np.array_equal(r_g, r_c)
