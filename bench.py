@@ -114,15 +114,28 @@ def cpu_baseline(sc, sample_points: int, threads: int | None = None, reps: int =
     from oracle import oracle_py as O
 
     nproc = O.num_procs()
-    threads = threads or int(round(1.5 * nproc))
     stride = max(1, sc.P // sample_points)
     pts = sc.points[::stride]
-    orc = O.Oracle(sc.shape, weight_p=sc.weight_p, safety_hor=sc.safety_hor, rho=sc.rho, threads=threads)
+    orc = O.Oracle(sc.shape, weight_p=sc.weight_p, safety_hor=sc.safety_hor, rho=sc.rho, threads=1)
     orc.set_points(pts)
-    sec, cost = orc.time_cost_grad(sc.T, sc.coeffs_colmajor(), warm=1, reps=reps)
-    return {"value": pts.shape[0] / sec, "unit": UNIT, "cores": nproc, "threads": threads, "kind": "port",
+    # the reference README recommends threads = 1.5 x logical cores; on many-core hosts (or cgroup-limited
+    # containers) that oversubscribes, so a few counts are tried and the best one is reported
+    tried = {}
+    for th in ([threads] if threads else thread_candidates(nproc)):
+        orc.set_threads(th)
+        sec, _ = orc.time_cost_grad(sc.T, sc.coeffs_colmajor(), warm=1, reps=reps)
+        tried[th] = sec
+    best = min(tried, key=tried.get)
+    return {"value": pts.shape[0] / tried[best], "unit": UNIT, "cores": nproc, "threads": best, "kind": "port",
             "sample": f"every {stride}th point of the {sc.P}-point config-2 workload ({pts.shape[0]} points), best of {reps} "
-                      f"after 1 warm-up, OpenMP schedule(dynamic)", "seconds_per_eval_of_sample": sec}
+                      f"after 1 warm-up, OpenMP schedule(dynamic); thread counts tried (s/eval): "
+                      + ", ".join(f"{k}: {v:.4f}" for k, v in tried.items()),
+            "seconds_per_eval_of_sample": tried[best]}
+
+
+def thread_candidates(nproc: int):
+    c = {int(round(1.5 * nproc)), nproc, max(1, nproc // 2), max(1, nproc // 4)}
+    return sorted(c, reverse=True)
 
 
 def run_reference(args):
@@ -133,12 +146,17 @@ def run_reference(args):
     from oracle import oracle_py as O
 
     nproc = O.num_procs()
-    threads = int(round(1.5 * nproc))
-    stride = 10
+    stride = 4
     pts = sc.points[::stride]
-    orc = O.Oracle(sc.shape, weight_p=sc.weight_p, safety_hor=sc.safety_hor, rho=sc.rho, threads=threads)
+    orc = O.Oracle(sc.shape, weight_p=sc.weight_p, safety_hor=sc.safety_hor, rho=sc.rho, threads=1)
     orc.set_points(pts)
     co = sc.coeffs_colmajor()
+    tried = {}
+    for th in thread_candidates(nproc):  # pick the best thread count (see cpu_baseline)
+        orc.set_threads(th)
+        tried[th], _ = orc.time_cost_grad(sc.T, co, warm=1, reps=1)
+    threads = min(tried, key=tried.get)
+    orc.set_threads(threads)
     for _ in range(args.warmup):
         orc.cost_grad(sc.T, co)
     t0 = time.perf_counter()
@@ -288,7 +306,7 @@ def main():
                               "iterations": st["iterations"], "evaluations": st["evaluations"], "status": st["status"],
                               "final_cost": st["final_cost"], "seconds": st["seconds"], "gpu_seconds": st["gpu_seconds"]}
         if not args.no_cpu_baseline and world == 1:
-            extra["cpu_baseline"] = cpu_baseline(sc, sample_points=20_000)
+            extra["cpu_baseline"] = cpu_baseline(sc, sample_points=50_000)
         elif not args.no_cpu_baseline:
             extra["cpu_baseline"] = cpu_baseline(sc, sample_points=5_000, reps=1)
 

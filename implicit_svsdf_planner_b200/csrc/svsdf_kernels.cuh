@@ -38,6 +38,8 @@ namespace svsdf {
 namespace SVSDF_NS {
 
 constexpr unsigned FULL = 0xffffffffu;
+using dev::smaxd;
+using dev::smind;
 
 // ------------------------------------------------------------------------------------------------
 // Trajectory view over the shared-memory copy of the blob
@@ -48,7 +50,8 @@ struct TrajView {
     const double *T;     // [N]
     const double *c;     // [N][3][6] ascending powers
     const double *lat;   // [K1]
-    const double *pose;  // [K1][4]  x, y, cos, sin
+    const double *pose;  // [4][K1pad] SoA: x, y, cos, sin
+    int K1pad;
 };
 
 __device__ __forceinline__ TrajView make_view(const double *blob) {
@@ -61,6 +64,7 @@ __device__ __forceinline__ TrajView make_view(const double *blob) {
     tv.c = blob + L.off_c;
     tv.lat = blob + L.off_lat;
     tv.pose = blob + L.off_pose;
+    tv.K1pad = L.K1pad;
     return tv;
 }
 
@@ -129,16 +133,20 @@ __device__ __forceinline__ double eval_sdf(const TrajView &tv, const ShapeParams
     return dev::shape_sdf<SHAPE, XFORM>(S, rx, ry);
 }
 
-// Warp arg-min with the sequential loop's semantics: the FIRST index holding the minimum value wins, NaN never
-// wins (the reference's test is `dis < min_dis`).
-__device__ __forceinline__ void warp_argmin(double &f, int &k) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        double fo = __shfl_xor_sync(FULL, f, off);
-        int ko = __shfl_xor_sync(FULL, k, off);
-        bool take = (fo < f) || (fo == f && ko < k);
-        if (take) { f = fo; k = ko; }
-    }
+// Warp arg-min with the sequential loop's semantics: the FIRST lane holding the minimum value wins; NaN never wins
+// (callers map NaN to +inf; the reference's test is `dis < min_dis`).  Two 32-bit REDUX.MIN over an order-preserving
+// integer image of the double, then a ballot for the first lane.  Returns the winning lane; f becomes the minimum.
+__device__ __forceinline__ int warp_argmin_lane(double &f) {
+    f = f + 0.0;  // -0.0 -> +0.0 so that equal values have equal keys
+    unsigned long long b = (unsigned long long)__double_as_longlong(f);
+    b ^= (b >> 63) ? 0xffffffffffffffffull : 0x8000000000000000ull;  // monotone map double -> uint64
+    const unsigned hi = (unsigned)(b >> 32), lo = (unsigned)b;
+    const unsigned mh = __reduce_min_sync(FULL, hi);
+    const unsigned ml = __reduce_min_sync(FULL, hi == mh ? lo : 0xffffffffu);
+    const unsigned win = __ballot_sync(FULL, hi == mh && lo == ml);
+    const int src = __ffs(win) - 1;
+    f = __shfl_sync(FULL, f, src);
+    return src;
 }
 
 struct OuterResult {
@@ -161,15 +169,14 @@ __device__ __forceinline__ OuterResult solve_outer(const TrajView &tv, const Sha
         int k = base + lane;
         double f = INF;
         if (k < tv.K1) {
-            const double *ps = tv.pose + 4 * k;
+            const double *ps = tv.pose + k;
             double rx, ry;
-            rel_from_pose(px, py, ps[0], ps[1], ps[2], ps[3], rx, ry);
+            rel_from_pose(px, py, ps[0], ps[tv.K1pad], ps[2 * tv.K1pad], ps[3 * tv.K1pad], rx, ry);
             f = dev::shape_sdf<SHAPE, XFORM>(S, rx, ry);
             if (!(f == f)) f = INF;
         }
         evals += min(32, tv.K1 - base);
-        int kb = k;
-        warp_argmin(f, kb);
+        const int kb = base + warp_argmin_lane(f);
         if (f < min_dis) {
             min_dis = f;
             seed = tv.lat[kb];
@@ -180,19 +187,17 @@ __device__ __forceinline__ OuterResult solve_outer(const TrajView &tv, const Sha
 #pragma unroll 1
     for (int layer = 2; layer <= 4; ++layer) {
         dt *= 0.1;
-        double t = fmax(0.0, seed - 10 * dt);
-        double term = fmin(D, seed + 10 * dt);
-#pragma unroll 1
-        for (int i = 0; i < 21; ++i)
-            if (i < lane) t += dt;  // lane k holds t0 + dt added k times (same rounding as the loop)
+        double t = smaxd(0.0, seed - 10 * dt);
+        const double term = smind(D, seed + 10 * dt);
+#pragma unroll
+        for (int i = 0; i < 20; ++i)
+            if (i < lane) t += dt;  // lane k (<= 20) holds t0 + dt added k times (same rounding as the loop)
         bool valid = (lane <= 20) && (t <= term);
         double f = eval_sdf<SHAPE, XFORM>(tv, S, px, py, t);
         if (!valid || !(f == f)) f = INF;
         evals += __popc(__ballot_sync(FULL, valid));
-        int kb = lane;
-        double tb = t;
-        warp_argmin(f, kb);
-        tb = __shfl_sync(FULL, t, kb);
+        const int kb = warp_argmin_lane(f);
+        const double tb = __shfl_sync(FULL, t, kb);
         if (f < min_dis) {
             min_dis = f;
             seed = tb;
@@ -200,8 +205,8 @@ __device__ __forceinline__ OuterResult solve_outer(const TrajView &tv, const Sha
     }
 
     // ---- gradientDescent: bounds [ts-3.4, ts+3.4] ∩ [0, D] (:856-857) ----
-    const double t_min = fmax(0.0, seed - 3.4);
-    const double t_max = fmin(seed + 3.4, D);
+    const double t_min = smaxd(0.0, seed - 3.4);
+    const double t_max = smind(seed + 3.4, D);
     double x = seed, prev_x = 10000000.0;
     // fx = f(x0): x0 is the scan's arg-min, so its value is min_dis (same function, same argument).
     double fx = min_dis;
@@ -211,58 +216,81 @@ __device__ __forceinline__ OuterResult solve_outer(const TrajView &tv, const Sha
     }
     int iter = 0;
     bool stop = false;
+    // pred: predicted sign of the FD slope at the next x (0 = unknown).  With a prediction, one round evaluates all
+    // 29 halvings in the predicted direction plus the two slope samples; a wrong prediction costs one extra round.
+    // Decisions are the sequential loop's: the slope's sign always comes from lanes 30/31, and the accepted halving
+    // is the first (largest step) whose candidate decreases f.
+    int pred = 0;
 #pragma unroll 1
     while (iter < 1000 && !stop && fabs(x - prev_x) > 1e-16) {
         prev_x = x;
-        // Round A: lanes 0-14: x - tau_j (sign +1), lanes 15-29: x + tau_j (sign -1), j = 0..14;
-        //          lane 30: t1 = max(0, x-1e-6), lane 31: t2 = min(D, x+1e-6)   (getSDF_DOTAtTimeStamp :798-806)
-        double tq;
-        {
-            int j = (lane < 15) ? lane : lane - 15;
-            double tau = scalbn(0.01, -j);  // alpha halved j times (exact)
-            double change = (lane < 15) ? -tau : tau;  // -tau * sign(g)
-            double xc = x + change;
-            xc = fmax(fmin(xc, t_max), t_min);
-            if (lane == 30) xc = fmax(0.0, x - 0.000001);
-            if (lane == 31) xc = fmin(D, x + 0.000001);
-            tq = xc;
-        }
-        double fq = eval_sdf<SHAPE, XFORM>(tv, S, px, py, tq);
-        evals += 32;
-        double f1 = __shfl_sync(FULL, fq, 30), f2 = __shfl_sync(FULL, fq, 31);
-        double g = (f2 - f1) * 500000;
-        int sgn = (int)(g > 0) - (int)(g < 0);
-        int jacc = -1;
+        int sgn, jacc = -1;
         double xacc = x, facc = fx;
-        if (sgn != 0) {
-            bool ok = (fq - fx) < 0;
-            unsigned m = __ballot_sync(FULL, ok);
-            unsigned grp = (sgn > 0) ? (m & 0x7fffu) : ((m >> 15) & 0x7fffu);
-            if (grp) {
-                jacc = __ffs(grp) - 1;
-                int src = (sgn > 0) ? jacc : jacc + 15;
-                xacc = __shfl_sync(FULL, tq, src);
-                facc = __shfl_sync(FULL, fq, src);
-            } else {
-                // Round B: halvings j = 15..28 in the known direction
-                int j = 15 + lane;
-                double tau = scalbn(0.01, -j);
-                double change = -tau * (double)sgn;
-                double xc = x + change;
-                xc = fmax(fmin(xc, t_max), t_min);
-                double fb = eval_sdf<SHAPE, XFORM>(tv, S, px, py, xc);
-                evals += 14;
-                bool okb = (lane < 14) && ((fb - fx) < 0);
-                unsigned mb = __ballot_sync(FULL, okb);
-                if (mb) {
-                    int src = __ffs(mb) - 1;
-                    jacc = 15 + src;
-                    xacc = __shfl_sync(FULL, xc, src);
-                    facc = __shfl_sync(FULL, fb, src);
+        const double xl = smaxd(0.0, x - 0.000001), xr = smind(D, x + 0.000001);  // getSDF_DOTAtTimeStamp :798-806
+        if (pred == 0) {
+            // Round A: lanes 0-14: x - tau_j (sign +1), lanes 15-29: x + tau_j (sign -1), j = 0..14; 30/31: slope
+            const int j = (lane < 15) ? lane : lane - 15;
+            const double tau = scalbn(0.01, -j);  // alpha halved j times (exact)
+            const double change = (lane < 15) ? -tau : tau;  // -tau * sign(g)
+            double tq = smaxd(smind(x + change, t_max), t_min);
+            tq = (lane == 30) ? xl : tq;
+            tq = (lane == 31) ? xr : tq;
+            const double fq = eval_sdf<SHAPE, XFORM>(tv, S, px, py, tq);
+            evals += 32;
+            const double g = (__shfl_sync(FULL, fq, 31) - __shfl_sync(FULL, fq, 30)) * 500000;
+            sgn = (int)(g > 0) - (int)(g < 0);
+            if (sgn != 0) {
+                const unsigned m = __ballot_sync(FULL, (fq - fx) < 0);
+                const unsigned grp = (sgn > 0) ? (m & 0x7fffu) : ((m >> 15) & 0x7fffu);
+                if (grp) {
+                    jacc = __ffs(grp) - 1;
+                    const int src = (sgn > 0) ? jacc : jacc + 15;
+                    xacc = __shfl_sync(FULL, tq, src);
+                    facc = __shfl_sync(FULL, fq, src);
+                } else {
+                    // Round B: halvings j = 15..28 in the known direction
+                    const double taub = scalbn(0.01, -(15 + lane));
+                    const double xc = smaxd(smind(x + (-taub * (double)sgn), t_max), t_min);
+                    const double fb = eval_sdf<SHAPE, XFORM>(tv, S, px, py, xc);
+                    evals += 14;
+                    const unsigned mb = __ballot_sync(FULL, (lane < 14) && ((fb - fx) < 0));
+                    if (mb) {
+                        const int src = __ffs(mb) - 1;
+                        jacc = 15 + src;
+                        xacc = __shfl_sync(FULL, xc, src);
+                        facc = __shfl_sync(FULL, fb, src);
+                    }
+                }
+            }
+        } else {
+            // Round P: lanes 0-28: x - tau_j * pred, j = 0..28; lanes 30/31: slope
+            const double tau = scalbn(0.01, -lane);
+            double tq = smaxd(smind(x + (-tau * (double)pred), t_max), t_min);
+            tq = (lane == 30) ? xl : tq;
+            tq = (lane == 31) ? xr : tq;
+            double fq = eval_sdf<SHAPE, XFORM>(tv, S, px, py, tq);
+            evals += 31;
+            const double g = (__shfl_sync(FULL, fq, 31) - __shfl_sync(FULL, fq, 30)) * 500000;
+            sgn = (int)(g > 0) - (int)(g < 0);
+            if (sgn != 0) {
+                if (sgn != pred) {  // mispredicted: evaluate the halvings in the actual direction
+                    tq = smaxd(smind(x + (-tau * (double)sgn), t_max), t_min);
+                    fq = eval_sdf<SHAPE, XFORM>(tv, S, px, py, tq);
+                    evals += 29;
+                }
+                const unsigned m = __ballot_sync(FULL, (lane < 29) && ((fq - fx) < 0));
+                if (m) {
+                    jacc = __ffs(m) - 1;
+                    xacc = __shfl_sync(FULL, tq, jacc);
+                    facc = __shfl_sync(FULL, fq, jacc);
                 }
             }
         }
         if (jacc >= 0) {
+            // a full, unclamped stride means we are still walking downhill: same sign next; otherwise the step
+            // overshot the minimiser (tau_j is the largest decreasing step) and the slope flips
+            const bool walking = (jacc == 0) && (xacc == x + (-0.01 * (double)sgn));
+            pred = walking ? sgn : -sgn;
             x = xacc;
             fx = facc;
             iter += jacc + 1;
@@ -442,8 +470,9 @@ __global__ void k_pose_table(double *blob) {
     double x, y, yaw, sy, cy;
     traj_pos(tv, tv.lat[k], x, y, yaw);
     sincos(yaw, &sy, &cy);
-    double *ps = blob + blob_layout(tv.N, tv.K1).off_pose + 4 * k;
-    ps[0] = x; ps[1] = y; ps[2] = cy; ps[3] = sy;
+    const BlobLayout L = blob_layout(tv.N, tv.K1);
+    double *ps = blob + L.off_pose + k;
+    ps[0] = x; ps[L.K1pad] = y; ps[2 * L.K1pad] = cy; ps[3 * L.K1pad] = sy;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -513,16 +542,27 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_compact: ordered compaction of the inside flags (single CTA, 1024 threads) -> inside_list, n_inside
+// k_compact: ordered compaction of the inside flags (single CTA, 1024 threads) -> inside_list, n_inside.
+// Flags are 0/1 bytes; every thread owns a contiguous run of 16-byte words (coalesced uint4 loads, popcount).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_compact(const unsigned char *flag, int64_t P, int *list, int *n_out) {
     __shared__ int wsum[32];
     __shared__ int total;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t chunk = (P + 1023) / 1024;
-    const int64_t beg = (int64_t)tid * chunk, end = (beg + chunk < P) ? beg + chunk : P;
+    const int64_t nwords = (P + 15) / 16;              // flag buffer is allocated with >= 16 bytes of slack
+    const int64_t per = (nwords + 1023) / 1024;        // words per thread
+    const int64_t w0 = (int64_t)tid * per, w1 = (w0 + per < nwords) ? w0 + per : nwords;
+    const uint4 *f4 = reinterpret_cast<const uint4 *>(flag);
     int cnt = 0;
-    for (int64_t i = beg; i < end; ++i) cnt += flag[i] ? 1 : 0;
+    for (int64_t w = w0; w < w1; ++w) {
+        uint4 v = f4[w];
+        if (16 * w + 16 > P) {  // mask the tail beyond P
+            unsigned char *b = reinterpret_cast<unsigned char *>(&v);
+            for (int q = 0; q < 16; ++q)
+                if (16 * w + q >= P) b[q] = 0;
+        }
+        cnt += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+    }
     int inc = cnt;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -544,8 +584,17 @@ __global__ void __launch_bounds__(1024) k_compact(const unsigned char *flag, int
     }
     __syncthreads();
     int pos = wsum[warp] + inc - cnt;
-    for (int64_t i = beg; i < end; ++i)
-        if (flag[i]) list[pos++] = (int)i;
+    if (cnt > 0) {
+        for (int64_t w = w0; w < w1; ++w) {
+            const uint4 v = f4[w];
+            if ((v.x | v.y | v.z | v.w) == 0u) continue;
+            const unsigned char *b = reinterpret_cast<const unsigned char *>(&v);
+            for (int q = 0; q < 16; ++q) {
+                const int64_t i = 16 * w + q;
+                if (i < P && b[q]) list[pos++] = (int)i;
+            }
+        }
+    }
     if (tid == 0) *n_out = total;
 }
 
@@ -631,7 +680,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
             if (iter > 8) break;
             if (fabs(max_g) < 0.1) break;
             theta_res /= (2 + 1);  // expandSet(2, theta*) (:105-123)
-            theta_res = fmax(0.3, theta_res);
+            theta_res = smaxd(0.3, theta_res);
             theta0 = star_theta;
             iter++;
         }
@@ -671,48 +720,70 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_finalize: fixed-order sum of the K1 CTA partials and the K2 per-point contributions.
+// k_finalize: fixed-order sum of the K1 CTA partials and the K2 per-point contributions.  One warp per accumulator
+// entry: lane l adds partials l, l+32, ... in order, the 32 lane sums are combined by a fixed shuffle tree, so the
+// result is bit-reproducible.  The last CTA to finish (ticket counter) writes the output record:
 // out: [0] cost, [1 .. 18N] gradC in Eigen column-major order (d*6N + 6i + q), [1+18N .. 1+19N) gradT with the
 // reference's rule gradT(j) += gdT for all j < piece (back_end_optimizer.hpp:859-862), [1+19N] n_inside.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum_fixed(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(FULL, v, off);
+    return __shfl_sync(FULL, v, 0);
+}
+
 __global__ void __launch_bounds__(256) k_finalize(const double *partials, int n_blocks, int N, const int *n_inside,
-                                                  const double *gsip_contrib, const int *gsip_piece, double *out) {
-    extern __shared__ double sred[];  // 19N + 1 totals in accumulator order
+                                                  const double *gsip_contrib, const int *gsip_piece, double *tot,
+                                                  unsigned int *ticket, double *out) {
     const int nacc = 19 * N + 1;
     const int n_in = n_inside ? *n_inside : 0;
-    for (int e = threadIdx.x; e < nacc; e += blockDim.x) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int e = blockIdx.x * 8 + warp;
+    if (e < nacc) {
         double s = 0.0;
-        for (int b = 0; b < n_blocks; ++b) s += partials[(int64_t)b * nacc + e];
-        // K2 contributions, in ascending point order (inside_list is sorted)
+        for (int b = lane; b < n_blocks; b += 32) s += partials[(int64_t)b * nacc + e];
+        s = warp_sum_fixed(s);
+        // K2 contributions, ascending point order (inside_list is sorted)
+        double s2 = 0.0;
         if (e < 18 * N) {
-            int piece = e / 18, within = e - 18 * piece;
-            for (int k = 0; k < n_in; ++k)
-                if (gsip_piece[k] == piece) s += gsip_contrib[20 * (int64_t)k + 1 + within];
+            const int piece = e / 18, within = e - 18 * piece;
+            for (int k = lane; k < n_in; k += 32)
+                if (gsip_piece[k] == piece) s2 += gsip_contrib[20 * (int64_t)k + 1 + within];
         } else if (e < 19 * N) {
-            int piece = e - 18 * N;
-            for (int k = 0; k < n_in; ++k)
-                if (gsip_piece[k] == piece) s += gsip_contrib[20 * (int64_t)k + 19];
+            const int piece = e - 18 * N;
+            for (int k = lane; k < n_in; k += 32)
+                if (gsip_piece[k] == piece) s2 += gsip_contrib[20 * (int64_t)k + 19];
         } else {
-            for (int k = 0; k < n_in; ++k) s += gsip_contrib[20 * (int64_t)k];
+            for (int k = lane; k < n_in; k += 32) s2 += gsip_contrib[20 * (int64_t)k];
         }
-        sred[e] = s;
+        s2 = warp_sum_fixed(s2);
+        if (lane == 0) tot[e] = s + s2;
     }
+    __shared__ bool last;
+    __threadfence();
     __syncthreads();
-    for (int e = threadIdx.x; e < nacc; e += blockDim.x) {
-        if (e < 18 * N) {
-            int piece = e / 18, within = e - 18 * piece;
-            int d = within / 6, q = within - 6 * d;
-            out[1 + d * 6 * N + 6 * piece + q] = sred[e];
-        } else if (e < 19 * N) {
-            int j = e - 18 * N;
-            double s = 0.0;
-            for (int i = j + 1; i < N; ++i) s += sred[18 * N + i];
-            out[1 + 18 * N + j] = s;
+    if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    for (int q = threadIdx.x; q < nacc; q += blockDim.x) {
+        if (q < 18 * N) {
+            const int piece = q / 18, within = q - 18 * piece;
+            const int d = within / 6, pw = within - 6 * d;
+            out[1 + d * 6 * N + 6 * piece + pw] = __ldcg(tot + q);
+        } else if (q < 19 * N) {
+            const int j = q - 18 * N;
+            double sfx = 0.0;
+            for (int i = j + 1; i < N; ++i) sfx += __ldcg(tot + 18 * N + i);
+            out[1 + 18 * N + j] = sfx;
         } else {
-            out[0] = sred[e];
+            out[0] = __ldcg(tot + q);
         }
     }
-    if (threadIdx.x == 0) out[1 + 19 * N] = (double)n_in;
+    if (threadIdx.x == 0) {
+        out[1 + 19 * N] = (double)n_in;
+        *ticket = 0u;  // re-arm for the next evaluation
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -847,9 +918,11 @@ cudaError_t launch_cost_kernels(const KernelArgs &A, const ShapeParams &S, int N
 }
 
 cudaError_t launch_finalize(const double *partials, int n_blocks, int N, const int *n_inside,
-                            const double *gsip_contrib, const int *gsip_piece, double *out, cudaStream_t stream) {
-    k_finalize<<<1, 256, (19 * N + 1) * sizeof(double), stream>>>(partials, n_blocks, N, n_inside, gsip_contrib,
-                                                                 gsip_piece, out);
+                            const double *gsip_contrib, const int *gsip_piece, double *tot, unsigned int *ticket,
+                            double *out, cudaStream_t stream) {
+    const int nacc = 19 * N + 1;
+    k_finalize<<<(nacc + 7) / 8, 256, 0, stream>>>(partials, n_blocks, N, n_inside, gsip_contrib, gsip_piece, tot,
+                                                   ticket, out);
     return cudaGetLastError();
 }
 

@@ -12,8 +12,8 @@ namespace svsdf {
     cudaError_t launch_cost_kernels(const KernelArgs &A, const ShapeParams &S, int N, int grid_outer,            \
                                     int grid_gsip, cudaStream_t stream, cudaEvent_t after_outer);                \
     cudaError_t launch_finalize(const double *partials, int n_blocks, int N, const int *n_inside,                \
-                                const double *gsip_contrib, const int *gsip_piece, double *out,                  \
-                                cudaStream_t stream);                                                            \
+                                const double *gsip_contrib, const int *gsip_piece, double *tot,                  \
+                                unsigned int *ticket, double *out, cudaStream_t stream);                         \
     cudaError_t launch_shape_eval(const ShapeParams &S, const double *rel_xy, int64_t n, double *out, int grad,  \
                                   cudaStream_t stream);                                                          \
     cudaError_t launch_fp64_peak(double *out, int grid, int iters, cudaStream_t stream);                         \

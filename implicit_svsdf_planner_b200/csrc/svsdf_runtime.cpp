@@ -65,6 +65,8 @@ struct svsdf_ctx {
     double *d_partials = nullptr;
     int64_t cap_partials = 0;
     double *d_out = nullptr;  // 1 + 19N + 1
+    double *d_tot = nullptr;  // 19N + 1 (finalize scratch)
+    unsigned int *d_ticket = nullptr;
     double *h_out = nullptr;  // pinned
     int cap_out = 0;
     // query scratch (per-point outputs)
@@ -307,6 +309,9 @@ int run_kernels(svsdf_ctx *ctx, const double *d_points, int64_t P, bool reduce, 
             if (ctx->h_out) cudaFreeHost(ctx->h_out);
             ctx->d_out = nullptr; ctx->h_out = nullptr; ctx->cap_out = 0;
             CK(cudaMalloc(&ctx->d_out, (size_t)(nacc + 64) * sizeof(double)));
+            cudaFree(ctx->d_tot);
+            ctx->d_tot = nullptr;
+            CK(cudaMalloc(&ctx->d_tot, (size_t)(nacc + 64) * sizeof(double)));
             CK(cudaMallocHost(&ctx->h_out, (size_t)(nacc + 64) * sizeof(double)));
             ctx->cap_out = nacc + 64;
         }
@@ -345,9 +350,9 @@ int run_kernels(svsdf_ctx *ctx, const double *d_points, int64_t P, bool reduce, 
     if (ctx->mark_kernels) CK(cudaEventRecord(ctx->evk[3], ctx->stream));
     if (reduce) {
         e = ctx->strict ? strict::launch_finalize(ctx->d_partials, grid, N, ctx->d_n_inside, ctx->d_gsip_contrib,
-                                                  ctx->d_gsip_piece, ctx->d_out, ctx->stream)
+                                                  ctx->d_gsip_piece, ctx->d_tot, ctx->d_ticket, ctx->d_out, ctx->stream)
                         : fast::launch_finalize(ctx->d_partials, grid, N, ctx->d_n_inside, ctx->d_gsip_contrib,
-                                                ctx->d_gsip_piece, ctx->d_out, ctx->stream);
+                                                ctx->d_gsip_piece, ctx->d_tot, ctx->d_ticket, ctx->d_out, ctx->stream);
         CK(e);
         ctx->launches += 1;
     }
@@ -472,6 +477,8 @@ int svsdf_create(const svsdf_config *cfg, svsdf_ctx **out) {
         if ((e = cudaEventCreate(&ctx->evk[k])) != cudaSuccess) return fail(e);
     if ((e = cudaMalloc(&ctx->d_n_inside, sizeof(int))) != cudaSuccess) return fail(e);
     if ((e = cudaMalloc(&ctx->d_eval_counter, sizeof(unsigned long long))) != cudaSuccess) return fail(e);
+    if ((e = cudaMalloc(&ctx->d_ticket, sizeof(unsigned int))) != cudaSuccess) return fail(e);
+    cudaMemset(ctx->d_ticket, 0, sizeof(unsigned int));
     cudaMemset(ctx->d_n_inside, 0, sizeof(int));
     cudaMemset(ctx->d_eval_counter, 0, sizeof(unsigned long long));
     *out = ctx;
@@ -485,7 +492,7 @@ void svsdf_destroy(svsdf_ctx *ctx) {
     if (ctx->own_points) cudaFree(ctx->d_points);
     cudaFree(ctx->d_flag); cudaFree(ctx->d_inside_tstar); cudaFree(ctx->d_inside_list);
     cudaFree(ctx->d_gsip_contrib); cudaFree(ctx->d_gsip_piece); cudaFree(ctx->d_n_inside);
-    cudaFree(ctx->d_eval_counter); cudaFree(ctx->d_blob); cudaFree(ctx->d_partials); cudaFree(ctx->d_out);
+    cudaFree(ctx->d_eval_counter); cudaFree(ctx->d_tot); cudaFree(ctx->d_ticket); cudaFree(ctx->d_blob); cudaFree(ctx->d_partials); cudaFree(ctx->d_out);
     cudaFree(ctx->d_q_points); cudaFree(ctx->d_q_sdf); cudaFree(ctx->d_q_ts); cudaFree(ctx->d_q_grad);
     cudaFree(ctx->d_q_rounds);
     if (ctx->h_blob) cudaFreeHost(ctx->h_blob);

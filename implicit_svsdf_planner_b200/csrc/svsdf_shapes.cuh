@@ -8,8 +8,42 @@
 namespace svsdf {
 namespace dev {
 
-__device__ __forceinline__ double clipd(double v, double lo, double hi) { return fmax(fmin(v, hi), lo); }
+// std::max / std::min exactly as libstdc++ defines them (the reference calls these, not fmax/fmin): 1 compare + select
+__device__ __forceinline__ double smaxd(double a, double b) { return (a < b) ? b : a; }
+__device__ __forceinline__ double smind(double a, double b) { return (b < a) ? b : a; }
+__device__ __forceinline__ double clipd(double v, double lo, double hi) { return smaxd(smind(v, hi), lo); }
 __device__ __forceinline__ double len2(double x, double y) { return sqrt(x * x + y * y); }
+
+// a / b for a divisor b known at compile time, given rb = RN(1/b): q = RN(a*rb), r = a - b*q (exact, FMA),
+// result RN(q + r*rb).  Markstein's correction step: returns the correctly rounded quotient (bit-identical to the
+// IEEE division the reference performs; tests/test_gpu_parity.py::test_strict_shape_functors_are_bitwise checks it)
+// in 3 FP64 instructions instead of the ~20-instruction generic division sequence.
+__device__ __forceinline__ double div_const(double a, double b, double rb) {
+    const double q = a * rb;
+    const double r = fma(-b, q, a);
+    return fma(r, rb, q);
+}
+
+// Literal constants of the shape functors live in __constant__ memory so that FP64 instructions read them as
+// constant-bank operands (a double immediate otherwise costs two UMOV per use).  Values are the reference's literals;
+// derived entries are folded by the host compiler in IEEE double, one rounding per operation, exactly as the
+// reference computes them at run time.
+namespace kc {
+constexpr double star_k1x = 0.809016994375, star_k1y = -0.587785252292, star_r = 2.8, star_rf = 0.6;
+constexpr double star_bax = star_rf * (-star_k1y) - 0.0, star_bay = star_rf * star_k1x - 1.0;
+constexpr double star_bb = star_bax * star_bax + star_bay * star_bay;
+constexpr double trap_k2x = 3.0 - 1.0, trap_k2y = 2.0 * 2.0;
+constexpr double trap_kk = trap_k2x * trap_k2x + trap_k2y * trap_k2y;
+constexpr double rhom_bb = 1.0 * 1.0 + 4.5 * 4.5;
+}  // namespace kc
+__constant__ double KSTAR[8] = {kc::star_k1x, kc::star_k1y, kc::star_r, kc::star_bax, kc::star_bay, kc::star_bb,
+                                1.0 / kc::star_bb, 2.0};
+__constant__ double KHORSE[4] = {1.5, 1.55, 0.20, 0.0};
+__constant__ double KMISC[16] = {
+    /*0 pie r*/ 3.0, /*1 arc ra*/ 2.3333, /*2 arc rb*/ 0.5, /*3 tunnel whx*/ 2.5, /*4 tunnel why*/ 1.5,
+    /*5 cutdisk r*/ 5.0, /*6 cutdisk h*/ 2.0, /*7 trap kk*/ kc::trap_kk, /*8 1/trap kk*/ 1.0 / kc::trap_kk,
+    /*9 rhombus by*/ 4.5, /*10 rhombus bb*/ kc::rhom_bb, /*11 1/bb*/ 1.0 / kc::rhom_bb, /*12*/ 0.25, /*13*/ 0.75,
+    /*14*/ 0.5, /*15*/ 2.4};
 
 template <int SHAPE>
 struct ShapeFn;
@@ -18,20 +52,19 @@ struct ShapeFn;
 template <>
 struct ShapeFn<SH_STAR> {
     static __device__ __forceinline__ double sdf(const ShapeParams &, double px, double py) {
-        const double r = 2.8, rf = 0.6;
-        const double k1x = 0.809016994375, k1y = -0.587785252292;
+        const double k1x = KSTAR[0], k1y = KSTAR[1], r = KSTAR[2];
         const double k2x = -k1x, k2y = k1y;
         px = fabs(px);
-        double m = 2.0 * fmax(k1x * px + k1y * py, 0.0);
+        double m = KSTAR[7] * smaxd(k1x * px + k1y * py, 0.0);
         px -= m * k1x;
         py -= m * k1y;
-        m = 2.0 * fmax(k2x * px + k2y * py, 0.0);
+        m = KSTAR[7] * smaxd(k2x * px + k2y * py, 0.0);
         px -= m * k2x;
         py -= m * k2y;
         px = fabs(px);
         py -= r;
-        const double bax = rf * (-k1y) - 0.0, bay = rf * k1x - 1.0;
-        double h = clipd((px * bax + py * bay) / (bax * bax + bay * bay), 0.0, r);
+        const double bax = KSTAR[3], bay = KSTAR[4];  // rf * (-k1.y, k1.x) - (0, 1)
+        double h = clipd(div_const(px * bax + py * bay, KSTAR[5], KSTAR[6]), 0.0, r);
         double dx = px - bax * h, dy = py - bay * h;
         return len2(dx, dy) * copysign(1.0, py * bax - px * bay);
     }
@@ -41,7 +74,7 @@ struct ShapeFn<SH_STAR> {
 template <>
 struct ShapeFn<SH_HORSESHOE> {
     static __device__ __forceinline__ double sdf(const ShapeParams &S, double px, double py) {
-        const double r = 1.5, wx = 1.55, wy = 0.20;
+        const double r = KHORSE[0], wx = KHORSE[1], wy = KHORSE[2];
         const double cx = S.cst[0], cy = S.cst[1];
         px = fabs(px);
         double l = len2(px, py);
@@ -52,8 +85,8 @@ struct ShapeFn<SH_HORSESHOE> {
         if (px0 <= 0) qy = l;
         qx = qx - wx;
         qy = fabs(qy - r) - wy;
-        double tx = fmax(qx, 0.0), ty = fmax(qy, 0.0);
-        return len2(tx, ty) + fmin(0.0, fmax(qx, qy));
+        double tx = smaxd(qx, 0.0), ty = smaxd(qy, 0.0);
+        return len2(tx, ty) + smind(0.0, smaxd(qx, qy));
     }
 };
 
@@ -65,7 +98,7 @@ __device__ __forceinline__ double sd_pie_c(double px, double py, double cx, doub
     double k = clipd(px * cx + py * cy, 0.0, r);
     double dx = px - cx * k, dy = py - cy * k;
     double m = len2(dx, dy);
-    return fmax(l, m * copysign(1.0, cy * px - cx * py));
+    return smaxd(l, m * copysign(1.0, cy * px - cx * py));
 }
 template <>
 struct ShapeFn<SH_PIE> {
@@ -103,13 +136,13 @@ struct ShapeFn<SH_TUNNEL> {
         px = fabs(px);
         py = -py;
         double qx = px - whx, qy = py - why;
-        double mq = fmax(qx, 0.0);
+        double mq = smaxd(qx, 0.0);
         double d1 = mq * mq + qy * qy;
         qx = (py > 0.0) ? qx : len2(px, py) - whx;
-        double mqy = fmax(qy, 0.0);
+        double mqy = smaxd(qy, 0.0);
         double d2 = qx * qx + mqy * mqy;
-        double d = sqrt(fmin(d1, d2));
-        return (fmax(qx, qy) < 0.0) ? -d : d;
+        double d = sqrt(smind(d1, d2));
+        return (smaxd(qx, qy) < 0.0) ? -d : d;
     }
 };
 
@@ -120,7 +153,7 @@ struct ShapeFn<SH_CUTDISK> {
         const double r = 5.0, h = 2.0;
         const double w = S.cst[0];
         px = fabs(px);
-        double s = fmax((h - r) * px * px + w * w * (h + r - 2.0 * py), h * px - w * py);
+        double s = smaxd((h - r) * px * px + w * w * (h + r - 2.0 * py), h * px - w * py);
         if (s < 0.0) return len2(px, py) - r;
         if (px < w) return h - py;
         return len2(px - w, py - h);
@@ -135,13 +168,13 @@ struct ShapeFn<SH_TRAPEZOID> {
         const double k1x = r2, k1y = he;
         const double k2x = r2 - r1, k2y = 2.0 * he;
         px = fabs(px);
-        double cax = fmax(0.0, px - ((py < 0.0) ? r1 : r2));
+        double cax = smaxd(0.0, px - ((py < 0.0) ? r1 : r2));
         double cay = fabs(py) - he;
-        double t = clipd(((k1x - px) * k2x + (k1y - py) * k2y) / (k2x * k2x + k2y * k2y), 0.0, 1.0);
+        double t = clipd(div_const((k1x - px) * k2x + (k1y - py) * k2y, KMISC[7], KMISC[8]), 0.0, 1.0);
         double cbx = px - k1x + k2x * t;
         double cby = py - k1y + k2y * t;
         double s = (cbx < 0.0 && cay < 0.0) ? -1.0 : 1.0;
-        return s * sqrt(fmin(cax * cax + cay * cay, cbx * cbx + cby * cby));
+        return s * sqrt(smind(cax * cax + cay * cay, cbx * cbx + cby * cby));
     }
 };
 
@@ -153,8 +186,7 @@ struct ShapeFn<SH_RHOMBUS> {
         px = fabs(px);
         py = fabs(py);
         double mx = bx - 2.0 * px, my = by - 2.0 * py;
-        double dotp = bx * bx + by * by;
-        double h = clipd((mx * bx - my * by) / dotp, -1.0, 1.0);
+        double h = clipd(div_const(mx * bx - my * by, KMISC[10], KMISC[11]), -1.0, 1.0);
         double hx = 0.5 * bx, hy = 0.5 * by;
         double dx = px - hx * (1.0 - h), dy = py - hy * (1.0 + h);
         double d = len2(dx, dy);
@@ -173,10 +205,10 @@ struct ShapeFn<SH_HEART> {
         if (py + px > 1.0) return 4 * (len2(px - 0.25, py - 0.75) - S.cst[0]);
         double ax = px - 0.0, ay = py - 1.0;
         double v1 = ax * ax + ay * ay;
-        double t = fmax(px + py, 0.0);
+        double t = smaxd(px + py, 0.0);
         double bx = px - 0.5 * t, by = py - 0.5 * t;
         double v2 = bx * bx + by * by;
-        return 4 * (sqrt(fmin(v1, v2)) * copysign(1.0, px - py));
+        return 4 * (sqrt(smind(v1, v2)) * copysign(1.0, px - py));
     }
 };
 
@@ -211,7 +243,7 @@ struct ShapeFn<SH_ROUNDEDCROSS> {
         if (ax < 1.0 && ay < ax * (k - h) + h) return 2 * (k - len2(ax - 1.0, ay - k));
         double d1x = ax - 0.0, d1y = ay - h;
         double d2x = ax - 1.0, d2y = ay - 0.0;
-        return 2 * sqrt(fmin(d1x * d1x + d1y * d1y, d2x * d2x + d2y * d2y));
+        return 2 * sqrt(smind(d1x * d1x + d1y * d1y, d2x * d2x + d2y * d2y));
     }
 };
 
@@ -245,9 +277,9 @@ struct ShapeFn<SH_MOON> {
         const double d = 0.8, ra = 3.0, rb = 2.4;
         const double a = S.cst[0], b = S.cst[1];
         qy = fabs(qy);
-        bool cond = d * (qx * b - qy * a) > d * d * fmax(b - qy, 0.0);
+        bool cond = d * (qx * b - qy * a) > d * d * smaxd(b - qy, 0.0);
         double dist1 = len2(qx - a, qy - b);
-        double dist2 = fmax(len2(qx, qy) - ra, -len2(qx - d, qy - 0.0) + rb);
+        double dist2 = smaxd(len2(qx, qy) - ra, -len2(qx - d, qy - 0.0) + rb);
         return cond ? dist1 : dist2;
     }
 };

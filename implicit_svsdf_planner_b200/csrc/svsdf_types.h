@@ -61,10 +61,11 @@ struct ShapeParams {
 //   [4]  T[Npad]              piece durations (Npad = N rounded up to even)
 //   [..] c[N][3][6]           per piece, per dim (x,y,yaw), ascending powers (== MINCO b rows 6i..6i+5)
 //   [..] lat[K1pad]           layer-1 lattice times t_k = 0.15 accumulated k times (host, IEEE adds)
-//   [..] pose[K1][4]          (x, y, cos yaw, sin yaw) at lat[k]  — filled on device by k_pose_table
+//   [..] pose[4][K1pad]       SoA rows x, y, cos yaw, sin yaw at lat[k] (conflict-free lane-strided reads) —
+//                             filled on device by k_pose_table
 struct BlobLayout {
     int N, K1;
-    int off_T, off_c, off_lat, off_pose, total;  // in doubles; total is even (16-byte multiple)
+    int off_T, off_c, off_lat, off_pose, K1pad, total;  // in doubles; total is even (16-byte multiple)
 };
 
 SVSDF_HD inline BlobLayout blob_layout(int N, int K1) {
@@ -77,7 +78,8 @@ SVSDF_HD inline BlobLayout blob_layout(int N, int K1) {
     L.off_c = L.off_T + Npad;
     L.off_lat = L.off_c + 18 * N;
     L.off_pose = L.off_lat + K1pad;
-    L.total = L.off_pose + 4 * K1;
+    L.K1pad = K1pad;
+    L.total = L.off_pose + 4 * K1pad;
     L.total = (L.total + 1) & ~1;
     return L;
 }
