@@ -116,7 +116,7 @@ def cpu_baseline(sc, sample_points: int, threads: int | None = None, reps: int =
     nproc = O.num_procs()
     stride = max(1, sc.P // sample_points)
     pts = sc.points[::stride]
-    orc = O.Oracle(sc.shape, weight_p=sc.weight_p, safety_hor=sc.safety_hor, rho=sc.rho, threads=1)
+    orc = O.Oracle(sc.shape, weight_p=sc.weight_p, safety_hor=sc.safety_hor, rho=sc.rho, threads=1, variant="glibc")
     orc.set_points(pts)
     # the reference README recommends threads = 1.5 x logical cores; on many-core hosts (or cgroup-limited
     # containers) that oversubscribes, so a few counts are tried and the best one is reported
@@ -126,7 +126,7 @@ def cpu_baseline(sc, sample_points: int, threads: int | None = None, reps: int =
         sec, _ = orc.time_cost_grad(sc.T, sc.coeffs_colmajor(), warm=1, reps=reps)
         tried[th] = sec
     best = min(tried, key=tried.get)
-    return {"value": pts.shape[0] / tried[best], "unit": UNIT, "cores": nproc, "threads": best, "kind": "port",
+    return {"value": pts.shape[0] / tried[best], "unit": UNIT, "cores": nproc, "threads": best, "kind": "port", "libm": "glibc sin/cos (the reference's own)",
             "sample": f"every {stride}th point of the {sc.P}-point config-2 workload ({pts.shape[0]} points), best of {reps} "
                       f"after 1 warm-up, OpenMP schedule(dynamic); thread counts tried (s/eval): "
                       + ", ".join(f"{k}: {v:.4f}" for k, v in tried.items()),
@@ -148,7 +148,7 @@ def run_reference(args):
     nproc = O.num_procs()
     stride = 4
     pts = sc.points[::stride]
-    orc = O.Oracle(sc.shape, weight_p=sc.weight_p, safety_hor=sc.safety_hor, rho=sc.rho, threads=1)
+    orc = O.Oracle(sc.shape, weight_p=sc.weight_p, safety_hor=sc.safety_hor, rho=sc.rho, threads=1, variant="glibc")
     orc.set_points(pts)
     co = sc.coeffs_colmajor()
     tried = {}

@@ -82,7 +82,7 @@ EXPORTED_SYMBOLS = [
     "svsdf_set_boundary", "svsdf_evaluate", "svsdf_last_costs", "svsdf_get_traj", "svsdf_default_lbfgs_params",
     "svsdf_optimize", "svsdf_minco_forward", "svsdf_minco_propagate", "svsdf_forward_T", "svsdf_backward_T",
     "svsdf_shape_sdf", "svsdf_shape_grad1", "svsdf_cost_grad_device", "svsdf_kernel_launches",
-    "svsdf_executed_evals", "svsdf_fp64_peak", "svsdf_device_ptr_points", "svsdf_lbfgs_minimize", "svsdf_last_kernel_ms",
+    "svsdf_executed_evals", "svsdf_fp64_peak", "svsdf_device_ptr_points", "svsdf_lbfgs_minimize", "svsdf_last_kernel_ms", "svsdf_sincos",
 ]
 
 
@@ -124,6 +124,7 @@ def lib():
     L.svsdf_shape_sdf.argtypes = [vp, C.c_int64, dp, dp]
     L.svsdf_shape_grad1.argtypes = [vp, C.c_int64, dp, dp]
     L.svsdf_cost_grad_device.argtypes = [vp, C.c_int, dp, dp, C.c_int, C.POINTER(C.c_float), dp]
+    L.svsdf_sincos.argtypes = [vp, C.c_int64, dp, dp, dp]
     L.svsdf_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.svsdf_kernel_launches.argtypes = [vp, C.POINTER(C.c_int64)]
     L.svsdf_executed_evals.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64)]
@@ -216,7 +217,7 @@ class Context:
     """Owns one svsdf_ctx (one GPU, one stream)."""
 
     def __init__(self, shape="star", poly_params=(0.0, 0.0, 0.0), weight_p=60.0, safety_hor=0.7, rho=3.8, device=0,
-                 strict_fp=False, polygon=None):
+                 strict_fp=True, polygon=None):
         L = lib()
         cfg = _Config()
         L.svsdf_default_config(C.byref(cfg))
@@ -353,6 +354,12 @@ class Context:
         self._ck(lib().svsdf_shape_grad1(self.h, rel.shape[0], _p(rel), _p(out)), "svsdf_shape_grad1")
         return out
 
+    def sincos(self, x):
+        x = _f64(x).reshape(-1)
+        s, c = np.empty_like(x), np.empty_like(x)
+        self._ck(lib().svsdf_sincos(self.h, x.size, _p(x), _p(s), _p(c)), "svsdf_sincos")
+        return s, c
+
     def last_kernel_ms(self):
         """Device ms of (k_pose_table, k_outer, k_compact + k_gsip, k_finalize) in the last cost_grad_device call."""
         out = (C.c_float * 4)()
@@ -406,7 +413,7 @@ class TrajOptimizer:
     """Mirror of the reference's TrajOptimizer for the back-end SVSDF cost (back_end_optimizer.hpp)."""
 
     def __init__(self, shape="star", poly_params=(0.0, 0.0, 0.0), weight_p=60.0, safety_hor=0.7, rho=3.8, device=0,
-                 strict_fp=False, polygon=None):
+                 strict_fp=True, polygon=None):
         self.ctx = Context(shape, poly_params, weight_p, safety_hor, rho, device, strict_fp, polygon)
         self.sv_manager = SweptVolumeManager(self.ctx)
         self._points = None

@@ -28,6 +28,7 @@
 #include <stdint.h>
 
 #include "svsdf_shapes.cuh"
+#include "svsdf_sincos.cuh"
 #include "svsdf_types.h"
 
 #ifndef SVSDF_NS
@@ -128,7 +129,7 @@ template <int SHAPE, bool XFORM>
 __device__ __forceinline__ double eval_sdf(const TrajView &tv, const ShapeParams &S, double px, double py, double t) {
     double x, y, yaw, sy, cy, rx, ry;
     traj_pos(tv, t, x, y, yaw);
-    sincos(yaw, &sy, &cy);
+    dev::sincos_fdlibm(yaw, sy, cy);
     rel_from_pose(px, py, x, y, cy, sy, rx, ry);
     return dev::shape_sdf<SHAPE, XFORM>(S, rx, ry);
 }
@@ -314,7 +315,7 @@ __device__ __forceinline__ void grad_prel(const TrajView &tv, const ShapeParams 
     const int lane = threadIdx.x & 31;
     double x, y, yaw, sy, cy, rx, ry;
     traj_pos(tv, t, x, y, yaw);
-    sincos(yaw, &sy, &cy);
+    dev::sincos_fdlibm(yaw, sy, cy);
     rel_from_pose(px, py, x, y, cy, sy, rx, ry);
     if (SHAPE == SH_POLYGON) {
         dev::PolyHit H = dev::polygon_scan(S, rx, ry);
@@ -391,7 +392,7 @@ __device__ __forceinline__ Contribution point_contribution(const TrajView &tv, c
         vel[d] = b;
     }
     double yaw = pos[2], sy, cy;
-    sincos(yaw, &sy, &cy);
+    dev::sincos_fdlibm(yaw, sy, cy);
     if (sdf < 0) {  // :832 world -> body
         double g0 = cy * gx + sy * gy;
         double g1 = -sy * gx + cy * gy;
@@ -469,7 +470,7 @@ __global__ void k_pose_table(double *blob) {
     if (k >= tv.K1) return;
     double x, y, yaw, sy, cy;
     traj_pos(tv, tv.lat[k], x, y, yaw);
-    sincos(yaw, &sy, &cy);
+    dev::sincos_fdlibm(yaw, sy, cy);
     const BlobLayout L = blob_layout(tv.N, tv.K1);
     double *ps = blob + L.off_pose + k;
     ps[0] = x; ps[L.K1pad] = y; ps[2 * L.K1pad] = cy; ps[3 * L.K1pad] = sy;
@@ -657,7 +658,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
             for (int k = warp; k < ns; k += kWarpsPerBlock) {
                 double th = s_theta[k];
                 double sn, cs;
-                sincos(th, &sn, &cs);
+                dev::sincos_fdlibm(th, sn, cs);
                 double yx = px + 1.0 * r * cs, yy = py + 1.0 * r * sn;  // CircleCoord2D::getPosition (:36-39)
                 OuterResult R = solve_outer<SHAPE, XFORM>(tv, S, yx, yy);
                 my_evals += (unsigned long long)R.evals;
@@ -685,7 +686,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
             iter++;
         }
         double sn, cs;
-        sincos(star_theta, &sn, &cs);
+        dev::sincos_fdlibm(star_theta, sn, cs);
         double corx = px + 1.0 * r_star * cs, cory = py + 1.0 * r_star * sn;
         double gx = corx - px, gy = cory - py;
         double z = gx * gx + gy * gy;
@@ -826,6 +827,15 @@ __global__ void k_shape_grad(const __grid_constant__ ShapeParams S, const double
     out3[3 * i] = gx; out3[3 * i + 1] = gy; out3[3 * i + 2] = 0.0;
 }
 
+__global__ void k_sincos(const double *x, int64_t n, double *s, double *c) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double sv, cv;
+    dev::sincos_fdlibm(x[i], sv, cv);
+    s[i] = sv;
+    c[i] = cv;
+}
+
 // FP64 FMA peak micro-benchmark (roofline denominator; MEASURED_PEAKS.json has no FP64 figure)
 __global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters) {
     double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -964,6 +974,12 @@ cudaError_t launch_shape_eval(const ShapeParams &S, const double *rel_xy, int64_
         case SH_POLYGON: return launch_shape_fn<SH_POLYGON, false>(S, rel_xy, n, out, grad, stream);
         default: return cudaErrorInvalidValue;
     }
+}
+
+cudaError_t launch_sincos(const double *x, int64_t n, double *s, double *c, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    k_sincos<<<(int)((n + 255) / 256), 256, 0, stream>>>(x, n, s, c);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_fp64_peak(double *out, int grid, int iters, cudaStream_t stream) {

@@ -17,6 +17,7 @@ namespace svsdf {
     cudaError_t launch_shape_eval(const ShapeParams &S, const double *rel_xy, int64_t n, double *out, int grad,  \
                                   cudaStream_t stream);                                                          \
     cudaError_t launch_fp64_peak(double *out, int grid, int iters, cudaStream_t stream);                         \
+    cudaError_t launch_sincos(const double *x, int64_t n, double *s, double *c, cudaStream_t stream);            \
     }
 SVSDF_DECLARE_LAUNCHERS(fast)
 SVSDF_DECLARE_LAUNCHERS(strict)

@@ -433,6 +433,7 @@ void svsdf_default_config(svsdf_config *cfg) {
     cfg->weight_p = 60.0;
     cfg->safety_hor = 0.7;
     cfg->rho = 3.8;
+    cfg->strict_fp = 1;  // reference-rounding build is the default
 }
 
 int svsdf_shape_id(const char *name) { return shape_id_from_name(name); }
@@ -810,6 +811,25 @@ static int shape_eval(svsdf_ctx *ctx, int64_t n, const double *rel, double *out,
 }
 int svsdf_shape_sdf(svsdf_ctx *ctx, int64_t n, const double *rel, double *sdf_out) { return shape_eval(ctx, n, rel, sdf_out, 0); }
 int svsdf_shape_grad1(svsdf_ctx *ctx, int64_t n, const double *rel, double *grad3_out) { return shape_eval(ctx, n, rel, grad3_out, 1); }
+
+int svsdf_sincos(svsdf_ctx *ctx, int64_t n, const double *x, double *sin_out, double *cos_out) {
+    if (!ctx || n < 0 || (n > 0 && (!x || !sin_out || !cos_out))) return SVSDF_ERR_INVALID;
+    if (n == 0) return SVSDF_OK;
+    CK(cudaSetDevice(ctx->device));
+    double *d = nullptr;
+    CK(cudaMalloc(&d, (size_t)n * 3 * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(d, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+        e = ctx->strict ? strict::launch_sincos(d, n, d + n, d + 2 * n, ctx->stream)
+                        : fast::launch_sincos(d, n, d + n, d + 2 * n, ctx->stream);
+    ctx->launches += 1;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sin_out, d + n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(cos_out, d + 2 * n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) { ctx->err = cudaGetErrorString(e); return SVSDF_ERR_CUDA; }
+    return SVSDF_OK;
+}
 
 int svsdf_last_kernel_ms(const svsdf_ctx *ctx, float *out4) {
     if (!ctx || !out4) return SVSDF_ERR_INVALID;

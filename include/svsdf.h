@@ -57,7 +57,9 @@ typedef struct {
     double safety_hor;        /* yaml safety_hor (star.yaml: 0.7)  */
     double rho;               /* yaml rho        (star.yaml: 3.8)  */
     int device;               /* CUDA device ordinal */
-    int strict_fp;            /* 1: kernels compiled with -fmad=false (CPU-like rounding; slower) */
+    int strict_fp;            /* 1 (default): kernels compiled with -fmad=false, bit-compatible with the un-fused
+                                 x86-64 arithmetic of the reference; 0: FMA-contracted build (~5-10 % faster, gradient
+                                 only within the reference's ~1e-5 contraction noise floor) */
     const double *polygon_xy; /* optional polygon vertices (x0,y0,x1,y1,...) for the fallback shape */
     int polygon_n;            /* number of vertices (<= 64) */
 } svsdf_config;
@@ -159,6 +161,9 @@ int svsdf_shape_grad1(svsdf_ctx *ctx, int64_t n, const double *rel, double *grad
  * n_inside) may be NULL. */
 int svsdf_cost_grad_device(svsdf_ctx *ctx, int N, const double *T, const double *coeffs, int repeats,
                            float *ms_per_eval, double *out_host);
+
+/* The device sin/cos used on the path (fdlibm restatement, csrc/svsdf_sincos.cuh), exposed for parity tests. */
+int svsdf_sincos(svsdf_ctx *ctx, int64_t n, const double *x, double *sin_out, double *cos_out);
 
 /* Measurement helpers */
 /* Device time (ms, CUDA events on the context's stream) of the kernels of the last svsdf_cost_grad_device

@@ -40,6 +40,11 @@ void orc_shape_grad1(const char *name, const double *poly_params, const double *
     for (int64_t i = 0; i < n; ++i) shape_grad1(S, rel[3 * i], rel[3 * i + 1], rel[3 * i + 2], out3 + 3 * i);
 }
 
+// the oracle's sin/cos (portable fdlibm restatement, or glibc in the "glibc"/"fma" variants)
+void orc_sincos(int64_t n, const double *x, double *s, double *c) {
+    for (int64_t i = 0; i < n; ++i) psc::sincos(x[i], s[i], c[i]);
+}
+
 void *orc_create(const char *name, const double *poly_params, const double *poly_xy, int poly_n, double weight_p,
                  double safety_hor, double rho, int threads) {
     TrajOptimizerOracle *o = new TrajOptimizerOracle();

@@ -14,25 +14,30 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libsvsdf_oracle.so")
 _SO_FMA = os.path.join(_HERE, "_build", "libsvsdf_oracle_fma.so")
+_SO_GLIBC = os.path.join(_HERE, "_build", "libsvsdf_oracle_glibc.so")
+_VARIANTS = {"default": _SO, "fma": _SO_FMA, "glibc": _SO_GLIBC}
 _libs = {}
 
 dp = C.POINTER(C.c_double)
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "svsdf_oracle.hpp", "minco_oracle.hpp", "shapes.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "svsdf_oracle.hpp", "minco_oracle.hpp", "shapes.hpp", "portable_sincos.hpp")]
     stale = any((not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
-                for so in (_SO, _SO_FMA))
+                for so in _VARIANTS.values())
     if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _SO
 
 
 def lib(variant: str = "default"):
-    """variant "default": no FMA contraction (the reference's x86-64 build); "fma": -ffp-contract=fast -mfma."""
+    """variant "default": portable (fdlibm) sin/cos, no FMA contraction — bit-compatible with the strict CUDA build;
+    "glibc": std::sin/std::cos, no contraction (the reference's x86-64 behaviour; timed as the CPU baseline);
+    "fma": glibc sin/cos with -ffp-contract=fast -mfma (what the same source does on FMA targets)."""
     if variant not in _libs:
         build()
-        L = C.CDLL(_SO if variant == "default" else _SO_FMA)
+        L = C.CDLL(_VARIANTS[variant])
+        L.orc_sincos.argtypes = [C.c_int64, dp, dp, dp]
         L.orc_create.restype = C.c_void_p
         L.orc_create.argtypes = [C.c_char_p, dp, dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]
         L.orc_destroy.argtypes = [C.c_void_p]
@@ -259,6 +264,13 @@ class Oracle:
         stats = np.zeros(4)
         ret = self.L.orc_lbfgs(self.h, _p(x), x.shape[0], mem_size, past, delta, g_epsilon, max_iterations, min_step, _p(stats))
         return ret, x, dict(f=stats[0], iters=int(stats[1]), evals=int(stats[2]), seconds=stats[3])
+
+
+def sincos(x, variant="default"):
+    x = _f64(x).reshape(-1)
+    s, c = np.empty_like(x), np.empty_like(x)
+    lib(variant).orc_sincos(x.size, _p(x), _p(s), _p(c))
+    return s, c
 
 
 def num_procs():

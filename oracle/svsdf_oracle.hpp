@@ -15,6 +15,7 @@
 #include <cstdint>
 #include <vector>
 
+#include "portable_sincos.hpp"
 #include "shapes.hpp"
 
 namespace oracle {
@@ -114,7 +115,8 @@ struct SweptVolume {
         double xt[3];
         traj.getPos(t, xt);
         double yaw = xt[2];
-        double s = std::sin(yaw), c = std::cos(yaw);
+        double s, c;
+        psc::sincos(yaw, s, c);
         double d0 = p[0] - xt[0], d1 = p[1] - xt[1], d2 = p[2] - xt[2];
         rel[0] = c * d0 + s * d1 + 0.0 * d2;
         rel[1] = -s * d0 + c * d1 + 0.0 * d2;
@@ -265,8 +267,10 @@ struct SweptVolume {
             for (double rk = rk0; rk > 0; rk -= rk_res) {
                 for (double theta = theta0; theta < theta0 + 2 * PI; theta += theta_res) {
                     // CircleCoord2D::getPosition :36-39
-                    yk3[0] = cx + rk * r * std::cos(theta);
-                    yk3[1] = cy + rk * r * std::sin(theta);
+                    double sth, cth;
+                    psc::sincos(theta, sth, cth);
+                    yk3[0] = cx + rk * r * cth;
+                    yk3[1] = cy + rk * r * sth;
                     yk3[2] = 0.0;
                     cur_g = getSDFofSweptVolume(yk3, time_seed_f, gtmp);
                     if (cur_g > max_g) {
@@ -288,8 +292,10 @@ struct SweptVolume {
             theta0 = star_theta;
             iter++;
         }
-        double corx = cx + star_rk * r_star * std::cos(star_theta);
-        double cory = cy + star_rk * r_star * std::sin(star_theta);
+        double sst, cst;
+        psc::sincos(star_theta, sst, cst);
+        double corx = cx + star_rk * r_star * cst;
+        double cory = cy + star_rk * r_star * sst;
         double gx = corx - p[0], gy = cory - p[1], gz = 0.0;
         double z = gx * gx + gy * gy + gz * gz;
         if (z > 0) {  // Eigen normalize()
@@ -363,7 +369,8 @@ inline void addSafetyPenaltyTrueSDF(const SweptVolume &sv, const CostParams &cp,
             pos[d] = a; vel[d] = b;
         }
         double yaw = pos[2];
-        double sy = std::sin(yaw), cy = std::cos(yaw);
+        double sy, cy;
+        psc::sincos(yaw, sy, cy);
         // rotate = [[cy,-sy,0],[sy,cy,0],[0,0,1]]
         pos[2] = 0.0;  // :829
         if (sdf_value < 0) {  // :832 gradp_rel = rotate^T * gradp_rel
