@@ -129,7 +129,7 @@ template <int SHAPE, bool XFORM>
 __device__ __forceinline__ double eval_sdf(const TrajView &tv, const ShapeParams &S, double px, double py, double t) {
     double x, y, yaw, sy, cy, rx, ry;
     traj_pos(tv, t, x, y, yaw);
-    dev::sincos_fdlibm(yaw, sy, cy);
+    dev::sincos_portable(yaw, sy, cy);
     rel_from_pose(px, py, x, y, cy, sy, rx, ry);
     return dev::shape_sdf<SHAPE, XFORM>(S, rx, ry);
 }
@@ -315,7 +315,7 @@ __device__ __forceinline__ void grad_prel(const TrajView &tv, const ShapeParams 
     const int lane = threadIdx.x & 31;
     double x, y, yaw, sy, cy, rx, ry;
     traj_pos(tv, t, x, y, yaw);
-    dev::sincos_fdlibm(yaw, sy, cy);
+    dev::sincos_portable(yaw, sy, cy);
     rel_from_pose(px, py, x, y, cy, sy, rx, ry);
     if (SHAPE == SH_POLYGON) {
         dev::PolyHit H = dev::polygon_scan(S, rx, ry);
@@ -392,7 +392,7 @@ __device__ __forceinline__ Contribution point_contribution(const TrajView &tv, c
         vel[d] = b;
     }
     double yaw = pos[2], sy, cy;
-    dev::sincos_fdlibm(yaw, sy, cy);
+    dev::sincos_portable(yaw, sy, cy);
     if (sdf < 0) {  // :832 world -> body
         double g0 = cy * gx + sy * gy;
         double g1 = -sy * gx + cy * gy;
@@ -470,7 +470,7 @@ __global__ void k_pose_table(double *blob) {
     if (k >= tv.K1) return;
     double x, y, yaw, sy, cy;
     traj_pos(tv, tv.lat[k], x, y, yaw);
-    dev::sincos_fdlibm(yaw, sy, cy);
+    dev::sincos_portable(yaw, sy, cy);
     const BlobLayout L = blob_layout(tv.N, tv.K1);
     double *ps = blob + L.off_pose + k;
     ps[0] = x; ps[L.K1pad] = y; ps[2 * L.K1pad] = cy; ps[3 * L.K1pad] = sy;
@@ -641,7 +641,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
         }
         // SampleSet2D::initSet (:74-103)
         double r = 10.0;
-        double theta0 = atan2(vx, -vy);
+        double theta0 = dev::atan2_portable(vx, -vy);
         if (theta0 < 0) theta0 += 2 * PI;
         double theta_res = PI + 0.1;
         double r_star = 0.0, real_t_star = 0.0, star_theta = 0.0;
@@ -658,7 +658,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
             for (int k = warp; k < ns; k += kWarpsPerBlock) {
                 double th = s_theta[k];
                 double sn, cs;
-                dev::sincos_fdlibm(th, sn, cs);
+                dev::sincos_portable(th, sn, cs);
                 double yx = px + 1.0 * r * cs, yy = py + 1.0 * r * sn;  // CircleCoord2D::getPosition (:36-39)
                 OuterResult R = solve_outer<SHAPE, XFORM>(tv, S, yx, yy);
                 my_evals += (unsigned long long)R.evals;
@@ -686,7 +686,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
             iter++;
         }
         double sn, cs;
-        dev::sincos_fdlibm(star_theta, sn, cs);
+        dev::sincos_portable(star_theta, sn, cs);
         double corx = px + 1.0 * r_star * cs, cory = py + 1.0 * r_star * sn;
         double gx = corx - px, gy = cory - py;
         double z = gx * gx + gy * gy;
@@ -831,7 +831,7 @@ __global__ void k_sincos(const double *x, int64_t n, double *s, double *c) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double sv, cv;
-    dev::sincos_fdlibm(x[i], sv, cv);
+    dev::sincos_portable(x[i], sv, cv);
     s[i] = sv;
     c[i] = cv;
 }

@@ -3,6 +3,7 @@
 // Operation order follows the reference so that a -fmad=false build differs from the CPU only through
 // libm (sin/cos); every function takes the body-frame point AFTER the shape pre-transform.
 #pragma once
+#include "svsdf_sincos.cuh"
 #include "svsdf_types.h"
 
 namespace svsdf {
@@ -328,7 +329,7 @@ __device__ __forceinline__ PolyHit polygon_scan(const ShapeParams &S, double qx,
         if (dis < H.dis) {
             H.dis = dis; H.cx = cx; H.cy = cy;
         }
-        double ths = atan2(sy - qy, sx - qx), the = atan2(ey - qy, ex - qx);
+        double ths = atan2_portable(sy - qy, sx - qx), the = atan2_portable(ey - qy, ex - qx);
         ths = (ths < 0.0) ? (ths + 2 * PI) : ths;
         the = (the < 0.0) ? (the + 2 * PI) : the;
         double d1 = fabs(ths - the);

@@ -45,6 +45,10 @@ void orc_sincos(int64_t n, const double *x, double *s, double *c) {
     for (int64_t i = 0; i < n; ++i) psc::sincos(x[i], s[i], c[i]);
 }
 
+void orc_atan2(int64_t n, const double *y, const double *x, double *out) {
+    for (int64_t i = 0; i < n; ++i) out[i] = psc::atan2(y[i], x[i]);
+}
+
 void *orc_create(const char *name, const double *poly_params, const double *poly_xy, int poly_n, double weight_p,
                  double safety_hor, double rho, int threads) {
     TrajOptimizerOracle *o = new TrajOptimizerOracle();

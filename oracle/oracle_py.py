@@ -38,6 +38,7 @@ def lib(variant: str = "default"):
         build()
         L = C.CDLL(_VARIANTS[variant])
         L.orc_sincos.argtypes = [C.c_int64, dp, dp, dp]
+        L.orc_atan2.argtypes = [C.c_int64, dp, dp, dp]
         L.orc_create.restype = C.c_void_p
         L.orc_create.argtypes = [C.c_char_p, dp, dp, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]
         L.orc_destroy.argtypes = [C.c_void_p]
@@ -271,6 +272,13 @@ def sincos(x, variant="default"):
     s, c = np.empty_like(x), np.empty_like(x)
     lib(variant).orc_sincos(x.size, _p(x), _p(s), _p(c))
     return s, c
+
+
+def atan2(y, x, variant="default"):
+    y, x = _f64(y).reshape(-1), _f64(x).reshape(-1)
+    out = np.empty_like(x)
+    lib(variant).orc_atan2(x.size, _p(y), _p(x), _p(out))
+    return out
 
 
 def num_procs():

@@ -14,6 +14,8 @@
 #include <string>
 #include <vector>
 
+#include "portable_sincos.hpp"
+
 namespace oracle {
 
 enum ShapeId {
@@ -338,7 +340,7 @@ inline PolyHit polygon_scan(const Shape &S, double qx, double qy) {
         if (dis < H.dis) { H.dis = dis; H.cx = cx; H.cy = cy; }
         // isCrossRayOnXDir :1370-1383
         double s2x = sx - qx, s2y = sy - qy, e2x = ex - qx, e2y = ey - qy;
-        double ths = std::atan2(s2y, s2x), the = std::atan2(e2y, e2x);
+        double ths = psc::atan2(s2y, s2x), the = psc::atan2(e2y, e2x);
         ths = (ths < 0.0) ? (ths + 2 * PI) : ths;
         the = (the < 0.0) ? (the + 2 * PI) : the;
         double d1 = std::abs(ths - the);

@@ -252,7 +252,7 @@ struct SweptVolume {
         // SampleSet2D::initSet :74-103
         double cx = p[0], cy = p[1];
         double r = r0;
-        double theta0 = std::atan2(vel[0], -vel[1]);
+        double theta0 = psc::atan2(vel[0], -vel[1]);
         if (theta0 < 0) theta0 += 2 * PI;
         double theta_res = PI + 0.1;
         const double rk_res = 1.5, rk0 = 1.0;
