@@ -102,9 +102,9 @@ def test_device_sincos_is_bitwise_the_oracles(oracle_mod):
     s_g, c_g = ctx.sincos(x)
     s_c, c_c = oracle_mod.sincos(x)
     assert np.array_equal(s_g, s_c) and np.array_equal(c_g, c_c)
-    # and it is a < 1 ulp sin/cos: at most 1 ulp away from glibc's
+    # and it is an accurate sin/cos: at most 2 ulp away from glibc's
     s_l, c_l = oracle_mod.sincos(x, "glibc")
-    assert (np.abs(s_g - s_l) <= np.spacing(np.abs(s_l))).all() and (np.abs(c_g - c_l) <= np.spacing(np.abs(c_l))).all()
+    assert (np.abs(s_g - s_l) <= 2 * np.spacing(np.abs(s_l))).all() and (np.abs(c_g - c_l) <= 2 * np.spacing(np.abs(c_l))).all()
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -123,8 +123,10 @@ def test_eval_count_matches_survey_estimate(oracle_mod, scene2k):
     assert 400 < per_point < 900, per_point
 
 
-def py_true_sdf(orc, p):
-    """SURVEY.md A.7 / sw_manager.hpp:916-1018 with the oracle's outer solve as the inner call."""
+def py_true_sdf(orc, p, O):
+    """SURVEY.md A.7 / sw_manager.hpp:916-1018 with the oracle's outer solve as the inner call (and the oracle's
+    portable sin/cos/atan2, so the comparison with the C++ control flow is exact)."""
+    _sc = lambda th: tuple(float(v[0]) for v in O.sincos([th]))  # (sin, cos)
     D = orc.duration()
     sdf, ts, g = orc.query_outer(np.array([[p[0], p[1], 0.0]]))
     if sdf[0] > 0:
@@ -147,7 +149,7 @@ def py_true_sdf(orc, p):
                     break
                 t -= 0.1
     r = 10.0
-    theta0 = math.atan2(vel[0], -vel[1])
+    theta0 = float(O.atan2([vel[0]], [-vel[1]])[0])
     if theta0 < 0:
         theta0 += 2 * PI
     theta_res = PI + 0.1
@@ -156,7 +158,8 @@ def py_true_sdf(orc, p):
         max_g, star_theta, real_t = -100000, 0.0, 0.0
         th = theta0
         while th < theta0 + 2 * PI:
-            y = np.array([[p[0] + 1.0 * r * math.cos(th), p[1] + 1.0 * r * math.sin(th), 0.0]])
+            sn, cs = _sc(th)
+            y = np.array([[p[0] + 1.0 * r * cs, p[1] + 1.0 * r * sn, 0.0]])
             s, t, _ = orc.query_outer(y)
             if s[0] > max_g:
                 max_g, real_t, star_theta = s[0], t[0], th
@@ -171,7 +174,8 @@ def py_true_sdf(orc, p):
         theta_res = max(0.3, theta_res / 3)
         theta0 = star_theta
         it += 1
-    cor = np.array([p[0] + r_star * math.cos(star_theta), p[1] + r_star * math.sin(star_theta)])
+    sn, cs = _sc(star_theta)
+    cor = np.array([p[0] + r_star * cs, p[1] + r_star * sn])
     gvec = np.array([cor[0] - p[0], cor[1] - p[1], 0.0])
     n = np.linalg.norm(gvec)
     if n > 0:
@@ -189,7 +193,7 @@ def test_interior_branch_matches_python_restatement(oracle_mod, scene_small_insi
     assert inside.size >= 10
     assert np.all(rounds[sdf > 0] == 0) and np.all(rounds[inside] >= 1) and rounds.max() <= 9
     for i in inside[:6]:
-        s_py, t_py, g_py, r_py = py_true_sdf(o, pts[i])
+        s_py, t_py, g_py, r_py = py_true_sdf(o, pts[i], oracle_mod)
         assert abs(s_py - sdf[i]) < 1e-12 and abs(t_py - ts[i]) < 1e-12 and r_py == rounds[i]
         assert np.abs(g_py - g[i]).max() < 1e-12
         assert abs(np.linalg.norm(g[i]) - 1.0) < 1e-12
