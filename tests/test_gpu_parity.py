@@ -326,7 +326,8 @@ def test_optimize_reduces_cost_and_final_point_agrees_with_oracle(oracle_mod):
     f0, g0 = orc.evaluate(x)
     f1, g1 = opt.costFunction(x)
     assert abs(f1 - f0) <= 1e-12 * abs(f0) and nrel(g1, g0) <= 1e-8
-    assert abs(st["final_cost"] - f1) <= 1e-9 * abs(f1)
+    if st["status"] >= 0:  # on a line-search failure lbfgs_ref.hpp:541-547 restores x but reports the last trial's f
+        assert abs(st["final_cost"] - f1) <= 1e-9 * abs(f1)
 
 
 def test_progress_callback_can_cancel(scene2k):
