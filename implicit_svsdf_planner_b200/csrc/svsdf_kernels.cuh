@@ -157,6 +157,18 @@ struct OuterResult {
 
 // getSDFofSweptVolume<false,*> (sw_manager.hpp:844-866) = choiceTInit (:538-581) + gradientDescent (:1249-1325),
 // executed cooperatively by one warp. All lanes return the same values.
+//
+// After the table-driven layer 1, everything is organised as ROUNDS of one SDF evaluation per lane, driven by a small
+// warp-uniform state machine with a single eval_sdf call site (the evaluation is ~250 instructions; inlining it once
+// keeps the kernel inside the 32 KB L1.5 instruction cache):
+//   M_LAT  choiceTInit layers 2..4: 21-sample window around the seed, dt *= 0.1 per layer
+//   M_F0   f(x0) when no sample was below the initial 1e9 (degenerate input; the reference evaluates it at iter == 0)
+//   M_A    first descent step: lanes 0-14 x - tau_j (slope sign +1), 15-29 x + tau_j (sign -1), j = 0..14; 30/31 slope
+//   M_B    halvings j = 15..28 in the known direction (only if M_A found no decreasing candidate)
+//   M_P    29 halvings in the PREDICTED direction + slope on lanes 30/31
+//   M_M    29 halvings in the actual direction after a misprediction
+// Decisions are the sequential loop's: the slope's sign always comes from the finite difference on lanes 30/31, and the
+// accepted halving is the first (largest step) whose candidate decreases f.
 template <int SHAPE, bool XFORM>
 __device__ __forceinline__ OuterResult solve_outer(const TrajView &tv, const ShapeParams &S, double px, double py) {
     const int lane = threadIdx.x & 31;
@@ -178,127 +190,127 @@ __device__ __forceinline__ OuterResult solve_outer(const TrajView &tv, const Sha
         }
         evals += min(32, tv.K1 - base);
         const int kb = base + warp_argmin_lane(f);
-        if (f < min_dis) {
+        if (__any_sync(FULL, f < min_dis)) {  // f is warp-uniform; the vote lets the compiler know the branch is too
             min_dis = f;
             seed = tv.lat[kb];
         }
     }
-    // ---- layers 2..4: 21-sample windows around the seed, dt *= 0.1 each ----
-    double dt = 0.15;
-#pragma unroll 1
-    for (int layer = 2; layer <= 4; ++layer) {
-        dt *= 0.1;
-        double t = smaxd(0.0, seed - 10 * dt);
-        const double term = smind(D, seed + 10 * dt);
-#pragma unroll
-        for (int i = 0; i < 20; ++i)
-            if (i < lane) t += dt;  // lane k (<= 20) holds t0 + dt added k times (same rounding as the loop)
-        bool valid = (lane <= 20) && (t <= term);
-        double f = eval_sdf<SHAPE, XFORM>(tv, S, px, py, t);
-        if (!valid || !(f == f)) f = INF;
-        evals += __popc(__ballot_sync(FULL, valid));
-        const int kb = warp_argmin_lane(f);
-        const double tb = __shfl_sync(FULL, t, kb);
-        if (f < min_dis) {
-            min_dis = f;
-            seed = tb;
-        }
-    }
 
-    // ---- gradientDescent: bounds [ts-3.4, ts+3.4] ∩ [0, D] (:856-857) ----
-    const double t_min = smaxd(0.0, seed - 3.4);
-    const double t_max = smind(seed + 3.4, D);
-    double x = seed, prev_x = 10000000.0;
-    // fx = f(x0): x0 is the scan's arg-min, so its value is min_dis (same function, same argument).
-    double fx = min_dis;
-    if (min_dis >= 1e9) {  // nothing was below the initial 1e9 (degenerate): evaluate like the reference does
-        fx = eval_sdf<SHAPE, XFORM>(tv, S, px, py, x);
-        evals += 1;
-    }
-    int iter = 0;
-    bool stop = false;
-    // pred: predicted sign of the FD slope at the next x (0 = unknown).  With a prediction, one round evaluates all
-    // 29 halvings in the predicted direction plus the two slope samples; a wrong prediction costs one extra round.
-    // Decisions are the sequential loop's: the slope's sign always comes from lanes 30/31, and the accepted halving
-    // is the first (largest step) whose candidate decreases f.
-    int pred = 0;
+    enum { M_LAT = 0, M_F0, M_A, M_B, M_P, M_M };
+    int mode = M_LAT, layer = 2;
+    double dt = 0.15, term = 0.0;
+    double x = 0.0, fx = 0.0, prev_x = 10000000.0, t_min = 0.0, t_max = 0.0;
+    int iter = 0, pred = 0, sgn = 0;
+    bool stop = false, running = true;
 #pragma unroll 1
-    while (iter < 1000 && !stop && fabs(x - prev_x) > 1e-16) {
-        prev_x = x;
-        int sgn, jacc = -1;
-        double xacc = x, facc = fx;
-        const double xl = smaxd(0.0, x - 0.000001), xr = smind(D, x + 0.000001);  // getSDF_DOTAtTimeStamp :798-806
-        if (pred == 0) {
-            // Round A: lanes 0-14: x - tau_j (sign +1), lanes 15-29: x + tau_j (sign -1), j = 0..14; 30/31: slope
-            const int j = (lane < 15) ? lane : lane - 15;
-            const double tau = scalbn(0.01, -j);  // alpha halved j times (exact)
-            const double change = (lane < 15) ? -tau : tau;  // -tau * sign(g)
-            double tq = smaxd(smind(x + change, t_max), t_min);
-            tq = (lane == 30) ? xl : tq;
-            tq = (lane == 31) ? xr : tq;
-            const double fq = eval_sdf<SHAPE, XFORM>(tv, S, px, py, tq);
-            evals += 32;
-            const double g = (__shfl_sync(FULL, fq, 31) - __shfl_sync(FULL, fq, 30)) * 500000;
-            sgn = (int)(g > 0) - (int)(g < 0);
-            if (sgn != 0) {
-                const unsigned m = __ballot_sync(FULL, (fq - fx) < 0);
-                const unsigned grp = (sgn > 0) ? (m & 0x7fffu) : ((m >> 15) & 0x7fffu);
-                if (grp) {
-                    jacc = __ffs(grp) - 1;
-                    const int src = (sgn > 0) ? jacc : jacc + 15;
-                    xacc = __shfl_sync(FULL, tq, src);
-                    facc = __shfl_sync(FULL, fq, src);
-                } else {
-                    // Round B: halvings j = 15..28 in the known direction
-                    const double taub = scalbn(0.01, -(15 + lane));
-                    const double xc = smaxd(smind(x + (-taub * (double)sgn), t_max), t_min);
-                    const double fb = eval_sdf<SHAPE, XFORM>(tv, S, px, py, xc);
-                    evals += 14;
-                    const unsigned mb = __ballot_sync(FULL, (lane < 14) && ((fb - fx) < 0));
-                    if (mb) {
-                        const int src = __ffs(mb) - 1;
-                        jacc = 15 + src;
-                        xacc = __shfl_sync(FULL, xc, src);
-                        facc = __shfl_sync(FULL, fb, src);
-                    }
-                }
-            }
+    while (running) {
+        // ---------------- sample time of this lane for the current round ----------------
+        double tq;
+        if (mode == M_LAT) {
+            dt *= 0.1;
+            double t = smaxd(0.0, seed - 10 * dt);
+            term = smind(D, seed + 10 * dt);
+#pragma unroll
+            for (int i = 0; i < 20; ++i)
+                if (i < lane) t += dt;  // lane k (<= 20) holds t0 + dt added k times (same rounding as the loop)
+            tq = t;
+        } else if (mode == M_F0) {
+            tq = x;
         } else {
-            // Round P: lanes 0-28: x - tau_j * pred, j = 0..28; lanes 30/31: slope
-            const double tau = scalbn(0.01, -lane);
-            double tq = smaxd(smind(x + (-tau * (double)pred), t_max), t_min);
-            tq = (lane == 30) ? xl : tq;
-            tq = (lane == 31) ? xr : tq;
-            double fq = eval_sdf<SHAPE, XFORM>(tv, S, px, py, tq);
-            evals += 31;
-            const double g = (__shfl_sync(FULL, fq, 31) - __shfl_sync(FULL, fq, 30)) * 500000;
-            sgn = (int)(g > 0) - (int)(g < 0);
-            if (sgn != 0) {
-                if (sgn != pred) {  // mispredicted: evaluate the halvings in the actual direction
-                    tq = smaxd(smind(x + (-tau * (double)sgn), t_max), t_min);
-                    fq = eval_sdf<SHAPE, XFORM>(tv, S, px, py, tq);
-                    evals += 29;
-                }
-                const unsigned m = __ballot_sync(FULL, (lane < 29) && ((fq - fx) < 0));
-                if (m) {
-                    jacc = __ffs(m) - 1;
-                    xacc = __shfl_sync(FULL, tq, jacc);
-                    facc = __shfl_sync(FULL, fq, jacc);
+            // descent candidates: x + (-tau_j * s), clamped (gradientDescent :1301-1304); slope samples on lanes 30/31
+            int j, sdir;
+            if (mode == M_A) { j = (lane < 15) ? lane : lane - 15; sdir = (lane < 15) ? 1 : -1; }
+            else if (mode == M_B) { j = 15 + lane; sdir = sgn; }
+            else { j = lane; sdir = (mode == M_P) ? pred : sgn; }
+            const double tau = scalbn(0.01, -j);  // alpha halved j times (exact)
+            tq = smaxd(smind(x + (-tau * (double)sdir), t_max), t_min);
+            if (mode != M_B) {
+                tq = (lane == 30) ? smaxd(0.0, x - 0.000001) : tq;  // getSDF_DOTAtTimeStamp :798-806
+                tq = (lane == 31) ? smind(D, x + 0.000001) : tq;
+            }
+        }
+        // ---------------- the one evaluation site ----------------
+        double fq = eval_sdf<SHAPE, XFORM>(tv, S, px, py, tq);
+
+        // ---------------- decisions (warp-uniform) ----------------
+        int next_mode = mode;
+        bool step_end = false;   // an outer step of gradientDescent ended (accepted or failed), or the descent starts
+        int src = -1;            // lane holding the accepted candidate
+        int jacc = -1;
+        bool failed = false;
+        if (mode == M_LAT) {
+            const bool lat_valid = (lane <= 20) && (tq <= term);
+            double fl = (lat_valid && (fq == fq)) ? fq : INF;
+            evals += __popc(__ballot_sync(FULL, lat_valid));
+            const int kb = warp_argmin_lane(fl);  // fl := warp minimum
+            const double tb = __shfl_sync(FULL, tq, kb);
+            if (__any_sync(FULL, fl < min_dis)) {
+                min_dis = fl;
+                seed = tb;
+            }
+            ++layer;
+            if (layer > 4) {
+                // gradientDescent set-up: bounds [ts-3.4, ts+3.4] ∩ [0, D] (:856-857), x0 = seed
+                t_min = smaxd(0.0, seed - 3.4);
+                t_max = smind(seed + 3.4, D);
+                x = seed;
+                fx = min_dis;  // f(x0): x0 is the scan's arg-min (same function, same argument)
+                if (__any_sync(FULL, min_dis >= 1e9)) next_mode = M_F0;  // nothing below 1e9: evaluate f(x0) explicitly
+                else step_end = true;
+            }
+        } else if (mode == M_F0) {
+            fx = __shfl_sync(FULL, fq, 0);
+            evals += 1;
+            step_end = true;
+        } else {
+            const unsigned m_dec = __ballot_sync(FULL, (fq - fx) < 0);  // candidates that decrease f
+            if (mode == M_A || mode == M_P) {
+                const double g = (__shfl_sync(FULL, fq, 31) - __shfl_sync(FULL, fq, 30)) * 500000;
+                sgn = (int)__any_sync(FULL, g > 0) - (int)__any_sync(FULL, g < 0);  // (int)(g > 0) - (g < 0)
+            }
+            if (mode == M_A) {
+                evals += 32;
+                const unsigned grp = (sgn > 0) ? (m_dec & 0x7fffu) : ((m_dec >> 15) & 0x7fffu);
+                if (sgn == 0) { failed = true; step_end = true; }
+                else if (grp) { jacc = __ffs(grp) - 1; src = (sgn > 0) ? jacc : jacc + 15; step_end = true; }
+                else next_mode = M_B;
+            } else if (mode == M_B) {
+                evals += 14;
+                const unsigned mb = m_dec & 0x3fffu;
+                if (mb) { src = __ffs(mb) - 1; jacc = 15 + src; }
+                else failed = true;
+                step_end = true;
+            } else {
+                evals += (mode == M_P) ? 31 : 29;
+                if (mode == M_P && sgn != 0 && sgn != pred) next_mode = M_M;  // mispredicted: redo in the actual direction
+                else {
+                    const unsigned m = m_dec & 0x1fffffffu;
+                    if (sgn != 0 && m) { jacc = __ffs(m) - 1; src = jacc; }
+                    else failed = true;
+                    step_end = true;
                 }
             }
         }
+        const double xacc = __shfl_sync(FULL, tq, src & 31), facc = __shfl_sync(FULL, fq, src & 31);
         if (jacc >= 0) {
-            // a full, unclamped stride means we are still walking downhill: same sign next; otherwise the step
+            // a full, unclamped stride means we are still walking downhill: same slope sign next; otherwise the step
             // overshot the minimiser (tau_j is the largest decreasing step) and the slope flips
-            const bool walking = (jacc == 0) && (xacc == x + (-0.01 * (double)sgn));
+            const bool walking = (jacc == 0) && __all_sync(FULL, xacc == x + (-0.01 * (double)sgn));
             pred = walking ? sgn : -sgn;
             x = xacc;
             fx = facc;
             iter += jacc + 1;
-        } else {
+        } else if (failed) {
             iter += 29;
             stop = true;
         }
+        if (step_end) {
+            // while (iter < max_iter && !stop && abs(x - prev_x) > tol)   (:1288)
+            running = (iter < 1000) && !stop && __all_sync(FULL, fabs(x - prev_x) > 1e-16);
+            prev_x = x;
+            next_mode = (pred == 0) ? M_A : M_P;
+        }
+        mode = next_mode;
     }
     OuterResult R;
     R.sdf = fx;
@@ -906,6 +918,49 @@ static cudaError_t dispatch(const KernelArgs &A, const ShapeParams &S, const Lau
         SVSDF_CASE(SH_CIRCLE)
 #undef SVSDF_CASE
         case SH_POLYGON: return launch_shape<SH_POLYGON, false>(A, S, cfg, N);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+template <int SHAPE, bool XFORM>
+static cudaError_t occ_shape(size_t smem_outer, size_t smem_gsip, int *occ_outer, int *occ_gsip) {
+    cudaError_t e = cudaFuncSetAttribute(k_outer<SHAPE, XFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_gsip<SHAPE, XFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_outer, k_outer<SHAPE, XFORM>, kWarpsPerBlock * 32, smem_outer);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_gsip, k_gsip<SHAPE, XFORM>, kWarpsPerBlock * 32, smem_gsip);
+}
+
+// Resident CTAs per SM of k_outer / k_gsip for this shape and trajectory size: the host sizes the grids as
+// SMs x occupancy so that the warp-stride loops run as exactly one full wave (no partial second wave).
+cudaError_t query_occupancy(const ShapeParams &S, int N, int blob_doubles, int *occ_outer, int *occ_gsip) {
+    const size_t so = (size_t)(blob_doubles + kWarpsPerBlock * (19 * N + 1)) * sizeof(double);
+    const size_t sg = (size_t)blob_doubles * sizeof(double);
+    const bool xf = S.has_xform != 0;
+    switch (S.id) {
+#define SVSDF_CASE(ID) \
+    case ID: return xf ? occ_shape<ID, true>(so, sg, occ_outer, occ_gsip) : occ_shape<ID, false>(so, sg, occ_outer, occ_gsip);
+        SVSDF_CASE(SH_STAR)
+        SVSDF_CASE(SH_HORSESHOE)
+        SVSDF_CASE(SH_PIE)
+        SVSDF_CASE(SH_PIE2)
+        SVSDF_CASE(SH_ARC)
+        SVSDF_CASE(SH_TUNNEL)
+        SVSDF_CASE(SH_CUTDISK)
+        SVSDF_CASE(SH_TRAPEZOID)
+        SVSDF_CASE(SH_RHOMBUS)
+        SVSDF_CASE(SH_HEART)
+        SVSDF_CASE(SH_ROUNDEDX)
+        SVSDF_CASE(SH_BIGX)
+        SVSDF_CASE(SH_ROUNDEDCROSS)
+        SVSDF_CASE(SH_VESICA)
+        SVSDF_CASE(SH_MOON)
+        SVSDF_CASE(SH_UNEVENCAPSULE)
+        SVSDF_CASE(SH_CIRCLE)
+#undef SVSDF_CASE
+        case SH_POLYGON: return occ_shape<SH_POLYGON, false>(so, sg, occ_outer, occ_gsip);
         default: return cudaErrorInvalidValue;
     }
 }

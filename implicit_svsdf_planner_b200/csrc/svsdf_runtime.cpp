@@ -61,6 +61,7 @@ struct svsdf_ctx {
     BlobLayout layout{};
     int traj_N = 0;
     double traj_D = 0.0;
+    int occ_N = -1, occ_blob = -1, occ_outer = 2, occ_gsip = 2;  // cached occupancy query
     // reduction
     double *d_partials = nullptr;
     int64_t cap_partials = 0;
@@ -278,11 +279,24 @@ int upload_traj(svsdf_ctx *ctx, int N, const double *T, const double *coeffs, bo
     return SVSDF_OK;
 }
 
+int refresh_occupancy(svsdf_ctx *ctx) {
+    if (ctx->occ_N == ctx->traj_N && ctx->occ_blob == ctx->layout.total) return SVSDF_OK;
+    int oo = 0, og = 0;
+    cudaError_t e = ctx->strict ? strict::query_occupancy(ctx->shape, ctx->traj_N, ctx->layout.total, &oo, &og)
+                                : fast::query_occupancy(ctx->shape, ctx->traj_N, ctx->layout.total, &oo, &og);
+    CK(e);
+    ctx->occ_outer = oo > 0 ? oo : 1;
+    ctx->occ_gsip = og > 0 ? og : 1;
+    ctx->occ_N = ctx->traj_N;
+    ctx->occ_blob = ctx->layout.total;
+    return SVSDF_OK;
+}
+
 int grid_for(const svsdf_ctx *ctx, int64_t P) {
-    // one warp per point, 8 warps per CTA; cap the grid at 4 CTAs per SM worth of resident work so each warp
-    // strides over many points (load balance) and the number of partials stays small.
+    // one warp per point, 8 warps per CTA, warp-stride loop.  The grid is exactly one full wave (SMs x resident CTAs
+    // per SM, from the occupancy query): a larger grid would run a partially filled second wave.
     int64_t need = (P + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    int64_t cap = (int64_t)ctx->sm_count * 4;
+    int64_t cap = (int64_t)ctx->sm_count * ctx->occ_outer;
     if (need < 1) need = 1;
     return (int)(need < cap ? need : cap);
 }
@@ -292,6 +306,8 @@ int run_kernels(svsdf_ctx *ctx, const double *d_points, int64_t P, bool reduce, 
                 double *o_ts, double *o_grad, int *o_rounds) {
     const int N = ctx->traj_N;
     int rc = ensure_scratch(ctx, P);
+    if (rc) return rc;
+    rc = refresh_occupancy(ctx);
     if (rc) return rc;
     const int grid = grid_for(ctx, P);
     const int nacc = 19 * N + 1;
@@ -334,7 +350,7 @@ int run_kernels(svsdf_ctx *ctx, const double *d_points, int64_t P, bool reduce, 
     A.gsip_contrib = ctx->d_gsip_contrib;
     A.gsip_piece = ctx->d_gsip_piece;
     A.eval_counter = ctx->count_evals ? ctx->d_eval_counter : nullptr;
-    const int grid_gsip = ctx->sm_count * 2;
+    const int grid_gsip = ctx->sm_count * ctx->occ_gsip;
     if (!gsip) CK(cudaMemsetAsync(ctx->d_n_inside, 0, sizeof(int), ctx->stream));
     size_t smem = (size_t)(A.blob_doubles + kWarpsPerBlock * nacc) * sizeof(double);
     if (smem > 200 * 1024) {

@@ -7,7 +7,7 @@ from implicit_svsdf_planner_b200 import api, scenes
 P = int(os.environ.get("SVSDF_P", "200000"))
 N = int(os.environ.get("SVSDF_N", "8"))
 shape = os.environ.get("SVSDF_SHAPE", "star")
-strict = os.environ.get("SVSDF_STRICT", "0") == "1"
+strict = os.environ.get("SVSDF_STRICT", "1") == "1"
 reps = int(os.environ.get("SVSDF_REPS", "3"))
 sc = scenes.make_scene(shape, N, P)
 ctx = api.Context(shape, strict_fp=strict)
