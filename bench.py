@@ -213,7 +213,8 @@ def main():
         kern = batch.pack_map_kernel_from_points(sc.points, sc.resolution) if rank == 0 else None
         map_bytes = int(batch.broadcast_map(kern, device=torch.device("cuda", local)).numel())
 
-    ctx = api.Context(SHAPE, weight_p=sc.weight_p, safety_hor=sc.safety_hor, rho=sc.rho, device=local, strict_fp=True)
+    strict = os.environ.get("SVSDF_BENCH_FMA", "0") != "1"  # default: the bit-exact strict build
+    ctx = api.Context(SHAPE, weight_p=sc.weight_p, safety_hor=sc.safety_hor, rho=sc.rho, device=local, strict_fp=strict)
     ctx.set_points(sc.points)
     flush = torch.empty(160 * 1024 * 1024, dtype=torch.float16, device=f"cuda:{local}")  # 320 MB > 126 MB L2
 
@@ -319,7 +320,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "config2: star, 8-piece MINCO, 200k query points, one cost+gradient evaluation per step"
                                    + ("" if world == 1 else f"; {world} independent problems of that size, one per GPU"),
-                       "shape": SHAPE, "pieces": N_PIECES, "points_per_gpu": sc.P, "fp_mode": "strict (-fmad=false)",
+                       "shape": SHAPE, "pieces": N_PIECES, "points_per_gpu": sc.P, "fp_mode": "strict (-fmad=false)" if strict else "fma-contracted (opt-in, not bit-exact)",
                        "l2": "flushed between timed iterations (320 MB memset, untimed); inputs are 3.2 MB",
                        "parallelism": "one problem per GPU, no data-path collective" if world > 1 else "single GPU",
                        "map_broadcast_bytes": map_bytes},

@@ -21,6 +21,7 @@ SO = os.path.join(LIBDIR, "libsvsdf_b200.so")
 NVCC = os.environ.get("SVSDF_NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++"]
+COMMON += os.environ.get("SVSDF_EXTRA_NVCC_FLAGS", "").split()  # experiments, e.g. -DSVSDF_OUTER_MIN_CTAS=4
 
 UNITS = [
     # (source, object, extra flags)

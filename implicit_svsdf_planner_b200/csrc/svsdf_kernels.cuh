@@ -492,8 +492,11 @@ __global__ void k_pose_table(double *blob) {
 // K1: outer solve for every point (+ penalty, chain rule and CTA reduction for outside points)
 // dynamic smem: [ blob | 8 warps x (19N + 1) accumulators ]
 // ------------------------------------------------------------------------------------------------
+#ifndef SVSDF_OUTER_MIN_CTAS
+#define SVSDF_OUTER_MIN_CTAS 3
+#endif
 template <int SHAPE, bool XFORM>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, SVSDF_OUTER_MIN_CTAS)
     k_outer(const __grid_constant__ KernelArgs A, const __grid_constant__ ShapeParams S) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t bar;
