@@ -620,8 +620,8 @@ __global__ void __launch_bounds__(1024) k_compact(const unsigned char *flag, int
 // running a full outer solve on its sample.
 // dynamic smem: [ blob ]
 // ------------------------------------------------------------------------------------------------
-template <int SHAPE, bool XFORM>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+template <int SHAPE, bool XFORM, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
     k_gsip(const __grid_constant__ KernelArgs A, const __grid_constant__ ShapeParams S) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -670,7 +670,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
             }
             if (ns > 24) ns = 24;  // cannot happen: theta_res >= 0.3 -> at most 21 samples
             __syncthreads();
-            for (int k = warp; k < ns; k += kWarpsPerBlock) {
+            for (int k = warp; k < ns; k += WARPS) {
                 double th = s_theta[k];
                 double sn, cs;
                 dev::sincos_portable(th, sn, cs);
@@ -870,6 +870,7 @@ struct LaunchCfg {
     size_t smem_outer, smem_gsip;
     cudaStream_t stream;
     cudaEvent_t after_outer;  // optional timing mark recorded right after k_outer
+    bool gsip_wide;           // use the 22-warp k_gsip variant
 };
 
 template <int SHAPE, bool XFORM>
@@ -879,7 +880,9 @@ static cudaError_t launch_shape(const KernelArgs &A, const ShapeParams &S, const
     if (!attr_set) {
         e = cudaFuncSetAttribute(k_outer<SHAPE, XFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_gsip<SHAPE, XFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        e = cudaFuncSetAttribute(k_gsip<SHAPE, XFORM, kWarpsPerBlock>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_gsip<SHAPE, XFORM, kGsipWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -889,7 +892,9 @@ static cudaError_t launch_shape(const KernelArgs &A, const ShapeParams &S, const
     if (cfg.after_outer) cudaEventRecord(cfg.after_outer, cfg.stream);
     if (A.want_gsip) {
         k_compact<<<1, 1024, 0, cfg.stream>>>(A.inside_flag, A.P, A.inside_list, A.n_inside);
-        k_gsip<SHAPE, XFORM><<<cfg.grid_gsip, kWarpsPerBlock * 32, cfg.smem_gsip, cfg.stream>>>(A, S);
+        // few inside points: one warp per ring sample (latency); many: 8-warp CTAs, two per SM (throughput)
+        if (cfg.gsip_wide) k_gsip<SHAPE, XFORM, kGsipWarps><<<cfg.grid_gsip, kGsipWarps * 32, cfg.smem_gsip, cfg.stream>>>(A, S);
+        else k_gsip<SHAPE, XFORM, kWarpsPerBlock><<<cfg.grid_gsip, kWarpsPerBlock * 32, cfg.smem_gsip, cfg.stream>>>(A, S);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
@@ -929,11 +934,11 @@ template <int SHAPE, bool XFORM>
 static cudaError_t occ_shape(size_t smem_outer, size_t smem_gsip, int *occ_outer, int *occ_gsip) {
     cudaError_t e = cudaFuncSetAttribute(k_outer<SHAPE, XFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_gsip<SHAPE, XFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    e = cudaFuncSetAttribute(k_gsip<SHAPE, XFORM, kWarpsPerBlock>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_outer, k_outer<SHAPE, XFORM>, kWarpsPerBlock * 32, smem_outer);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_gsip, k_gsip<SHAPE, XFORM>, kWarpsPerBlock * 32, smem_gsip);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_gsip, k_gsip<SHAPE, XFORM, kWarpsPerBlock>, kWarpsPerBlock * 32, smem_gsip);
 }
 
 // Resident CTAs per SM of k_outer / k_gsip for this shape and trajectory size: the host sizes the grids as
@@ -974,9 +979,10 @@ cudaError_t launch_pose_table(double *blob, int K1, cudaStream_t stream) {
 }
 
 cudaError_t launch_cost_kernels(const KernelArgs &A, const ShapeParams &S, int N, int grid_outer, int grid_gsip,
-                                cudaStream_t stream, cudaEvent_t after_outer) {
+                                cudaStream_t stream, cudaEvent_t after_outer, int gsip_wide) {
     LaunchCfg cfg;
     cfg.after_outer = after_outer;
+    cfg.gsip_wide = gsip_wide != 0;
     cfg.grid_outer = grid_outer;
     cfg.grid_gsip = grid_gsip;
     cfg.smem_outer = (size_t)(A.blob_doubles + kWarpsPerBlock * (19 * N + 1)) * sizeof(double);

@@ -62,6 +62,7 @@ struct svsdf_ctx {
     int traj_N = 0;
     double traj_D = 0.0;
     int occ_N = -1, occ_blob = -1, occ_outer = 2, occ_gsip = 2;  // cached occupancy query
+    int64_t last_n_inside = -1;  // interior points seen by the previous cost evaluation (picks the k_gsip variant)
     // reduction
     double *d_partials = nullptr;
     int64_t cap_partials = 0;
@@ -350,7 +351,9 @@ int run_kernels(svsdf_ctx *ctx, const double *d_points, int64_t P, bool reduce, 
     A.gsip_contrib = ctx->d_gsip_contrib;
     A.gsip_piece = ctx->d_gsip_piece;
     A.eval_counter = ctx->count_evals ? ctx->d_eval_counter : nullptr;
-    const int grid_gsip = ctx->sm_count * ctx->occ_gsip;
+    // previous evaluation had few interior points -> 22-warp CTAs (one warp per ring sample, lower latency)
+    const int gsip_wide = (reduce && ctx->last_n_inside >= 0 && ctx->last_n_inside <= ctx->sm_count) ? 1 : 0;
+    const int grid_gsip = gsip_wide ? ctx->sm_count : ctx->sm_count * ctx->occ_gsip;
     if (!gsip) CK(cudaMemsetAsync(ctx->d_n_inside, 0, sizeof(int), ctx->stream));
     size_t smem = (size_t)(A.blob_doubles + kWarpsPerBlock * nacc) * sizeof(double);
     if (smem > 200 * 1024) {
@@ -358,9 +361,9 @@ int run_kernels(svsdf_ctx *ctx, const double *d_points, int64_t P, bool reduce, 
         return SVSDF_ERR_INVALID;
     }
     cudaError_t e = ctx->strict ? strict::launch_cost_kernels(A, ctx->shape, N, grid, grid_gsip, ctx->stream,
-                                                              ctx->mark_kernels ? ctx->evk[2] : nullptr)
+                                                              ctx->mark_kernels ? ctx->evk[2] : nullptr, gsip_wide)
                                 : fast::launch_cost_kernels(A, ctx->shape, N, grid, grid_gsip, ctx->stream,
-                                                            ctx->mark_kernels ? ctx->evk[2] : nullptr);
+                                                            ctx->mark_kernels ? ctx->evk[2] : nullptr, gsip_wide);
     CK(e);
     ctx->launches += gsip ? 3 : 1;
     if (ctx->mark_kernels) CK(cudaEventRecord(ctx->evk[3], ctx->stream));
@@ -395,6 +398,7 @@ int cost_grad_raw(svsdf_ctx *ctx, int N, const double *T, const double *coeffs) 
         CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         ctx->gpu_ms_total += ms;
     }
+    ctx->last_n_inside = (int64_t)ctx->h_out[1 + 19 * N];
     return SVSDF_OK;
 }
 
@@ -551,6 +555,7 @@ int svsdf_set_points(svsdf_ctx *ctx, const double *pts, int64_t P, int stride) {
     CK(cudaMemcpyAsync(ctx->d_points, h, (size_t)P * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->P = P;
+    ctx->last_n_inside = -1;
     return ensure_scratch(ctx, P);
 }
 
@@ -663,9 +668,11 @@ int svsdf_cost_grad_device(svsdf_ctx *ctx, int N, const double *T, const double 
     CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     for (int k = 0; k < 4; ++k) CK(cudaEventElapsedTime(&ctx->last_kernel_ms[k], ctx->evk[k], ctx->evk[k + 1]));
     if (ms_per_eval) *ms_per_eval = ms / repeats;
-    if (out_host) {
+    {
         const int nout = 1 + 19 * N + 1;
-        CK(cudaMemcpy(out_host, ctx->d_out, (size_t)nout * sizeof(double), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(ctx->h_out, ctx->d_out, (size_t)nout * sizeof(double), cudaMemcpyDeviceToHost));
+        ctx->last_n_inside = (int64_t)ctx->h_out[1 + 19 * N];
+        if (out_host) std::memcpy(out_host, ctx->h_out, (size_t)nout * sizeof(double));
     }
     return SVSDF_OK;
 }

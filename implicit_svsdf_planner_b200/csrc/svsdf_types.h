@@ -37,7 +37,8 @@ enum ShapeId : int {
 
 constexpr int kMaxPolyEdges = 64;
 constexpr int kMaxPieces = 64;       // pieces per trajectory supported by the per-warp accumulators
-constexpr int kWarpsPerBlock = 8;    // K1/K2 block = 256 threads
+constexpr int kWarpsPerBlock = 8;    // k_outer block = 256 threads
+constexpr int kGsipWarps = 22;       // k_gsip block = 704 threads: one warp per ring sample (<= 21 per round)
 constexpr double kMaxDuration = 300.0;  // sw_manager.hpp:380: durations >= 300 s are not accepted by updateTraj
 
 // Parameters of the robot-shape SDF functor. Trigonometric constants the reference evaluates on the host
