@@ -82,7 +82,8 @@ EXPORTED_SYMBOLS = [
     "svsdf_set_boundary", "svsdf_evaluate", "svsdf_last_costs", "svsdf_get_traj", "svsdf_default_lbfgs_params",
     "svsdf_optimize", "svsdf_minco_forward", "svsdf_minco_propagate", "svsdf_forward_T", "svsdf_backward_T",
     "svsdf_shape_sdf", "svsdf_shape_grad1", "svsdf_cost_grad_device", "svsdf_kernel_launches",
-    "svsdf_executed_evals", "svsdf_fp64_peak", "svsdf_device_ptr_points", "svsdf_lbfgs_minimize", "svsdf_last_kernel_ms", "svsdf_sincos",
+    "svsdf_executed_evals", "svsdf_fp64_peak", "svsdf_device_ptr_points", "svsdf_lbfgs_minimize", "svsdf_last_kernel_ms", "svsdf_sincos", "svsdf_set_map", "svsdf_set_map_device",
+    "svsdf_extract_points", "svsdf_get_points",
 ]
 
 
@@ -125,6 +126,10 @@ def lib():
     L.svsdf_shape_grad1.argtypes = [vp, C.c_int64, dp, dp]
     L.svsdf_cost_grad_device.argtypes = [vp, C.c_int, dp, dp, C.c_int, C.POINTER(C.c_float), dp]
     L.svsdf_sincos.argtypes = [vp, C.c_int64, dp, dp, dp]
+    L.svsdf_set_map.argtypes = [vp, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
+    L.svsdf_set_map_device.argtypes = [vp, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
+    L.svsdf_extract_points.argtypes = [vp, dp, C.c_int, C.c_double, dp, C.c_int, C.c_double, C.POINTER(C.c_int64)]
+    L.svsdf_get_points.argtypes = [vp, dp, C.c_int64, C.POINTER(C.c_int64)]
     L.svsdf_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.svsdf_kernel_launches.argtypes = [vp, C.POINTER(C.c_int64)]
     L.svsdf_executed_evals.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64)]
@@ -352,6 +357,33 @@ class Context:
         rel = _f64(rel).reshape(-1, 3)
         out = np.empty((rel.shape[0], 3))
         self._ck(lib().svsdf_shape_grad1(self.h, rel.shape[0], _p(rel), _p(out)), "svsdf_shape_grad1")
+        return out
+
+    # ---- K3: query points from the packed map (next row) ----
+    def set_map(self, kernel_u8, X, Y, kernel_size, origin, res):
+        k = np.ascontiguousarray(kernel_u8, dtype=np.uint8)
+        self._ck(lib().svsdf_set_map(self.h, k.ctypes.data_as(C.c_void_p), X, Y, kernel_size, float(origin[0]), float(origin[1]),
+                                     float(res)), "svsdf_set_map")
+
+    def set_map_device(self, dev_ptr, X, Y, kernel_size, origin, res):
+        self._ck(lib().svsdf_set_map_device(self.h, C.c_void_p(dev_ptr), X, Y, kernel_size, float(origin[0]), float(origin[1]),
+                                            float(res)), "svsdf_set_map_device")
+
+    def extract_points(self, waypoints_xy, half, keepout_xy=None, clearance=0.0):
+        w = _f64(waypoints_xy).reshape(-1, 2)
+        ko = _f64(keepout_xy).reshape(-1, 2) if keepout_xy is not None else None
+        n = C.c_int64()
+        self._ck(lib().svsdf_extract_points(self.h, _p(w), w.shape[0], float(half), _p(ko), 0 if ko is None else ko.shape[0],
+                                            float(clearance), C.byref(n)), "svsdf_extract_points")
+        self.P = n.value
+        return n.value
+
+    def get_points(self):
+        n = C.c_int64()
+        lib().svsdf_get_points(self.h, None, 0, C.byref(n))
+        out = np.empty((n.value, 2))
+        if n.value:
+            self._ck(lib().svsdf_get_points(self.h, _p(out), n.value, C.byref(n)), "svsdf_get_points")
         return out
 
     def sincos(self, x):

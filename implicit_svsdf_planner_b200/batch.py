@@ -33,8 +33,8 @@ class GridMap:
         return self.occ.shape
 
     def cell_centers(self, ij: np.ndarray) -> np.ndarray:
-        """GridMap3D::getGridCubeCenter: min + (idx + 0.5) * res."""
-        return self.origin[None, :] + (ij + 0.5) * self.res
+        """GridMap3D::getGridCubeCenter: (idx + 0.5) * res + min."""
+        return (ij + 0.5) * self.res + self.origin[None, :]
 
 
 def pack_map_kernel(occ: np.ndarray, kernel_size: int = 17) -> np.ndarray:
@@ -80,10 +80,13 @@ def make_random_map(extent: float = 60.0, res: float = 0.025, density: float = 0
     return GridMap(occ=occ, origin=np.zeros(2), res=res)
 
 
-def extract_query_points(gm: GridMap, waypoints: np.ndarray, half: float) -> np.ndarray:
+def extract_query_points(gm: GridMap, waypoints: np.ndarray, half: float, keepout: Optional[np.ndarray] = None,
+                         clearance: float = 0.0) -> np.ndarray:
     """getPointsInAABBOutOfLastOne over the waypoint sequence (plan_manager.cpp:156-167): occupied cells in each
-    waypoint's box that are outside the previous waypoint's box, de-duplicated by unified id (i + j * X), returned in
-    ascending id order (the reference iterates an unordered_map, i.e. in unspecified order)."""
+    waypoint's box that are outside the previous waypoint's box, de-duplicated by cell id, returned in ascending
+    (i * Y + j) order — the memory order of the packed map, which is what the device kernel (csrc/svsdf_extract.cu)
+    produces; the reference iterates an unordered_map, i.e. in unspecified order.  This numpy version is the host
+    restatement the device kernel is tested against.  keepout/clearance: synthetic-scene option, see problem_scene."""
     X, Y = gm.shape
     lo_w, hi_w = gm.origin, gm.origin + np.array([X, Y]) * gm.res
 
@@ -106,14 +109,23 @@ def extract_query_points(gm: GridMap, waypoints: np.ndarray, half: float) -> np.
             p1, p2 = prev
             outside = (ii > p2[0]) | (ii < p1[0]) | (jj > p2[1]) | (jj < p1[1])
             ii, jj = ii[outside], jj[outside]
-        ids.append(jj.astype(np.int64) * X + ii)
-        prev = (i1, i2)
+        ids.append(ii.astype(np.int64) * Y + jj)
+        prev = (a1, a2)  # idcorner*_l are clamped indices too (Gridmap3D.cpp:150-172)
     if not ids:
         return np.zeros((0, 3))
     uid = np.unique(np.concatenate(ids))
-    ij = np.stack([uid % X, uid // X], axis=1)
+    ij = np.stack([uid // Y, uid % Y], axis=1)
     pts = np.zeros((uid.size, 3))
     pts[:, :2] = gm.cell_centers(ij)
+    if keepout is not None and len(keepout):
+        ko = np.asarray(keepout, dtype=np.float64).reshape(-1, 2)
+        keep = np.ones(pts.shape[0], dtype=bool)
+        for s in range(0, pts.shape[0], 100_000):
+            blk = pts[s : s + 100_000, :2]
+            dx = blk[:, None, 0] - ko[None, :, 0]
+            dy = blk[:, None, 1] - ko[None, :, 1]
+            keep[s : s + 100_000] = (dx * dx + dy * dy > clearance * clearance).all(axis=1)
+        pts = pts[keep]
     return pts
 
 
@@ -153,18 +165,17 @@ def problem_scene(gm: GridMap, start, goal, N: int = 8, P: Optional[int] = None,
     b = scenes.minco_dense(init_s, final_s, q, T)
     half = scenes.YAML["kernel_size"] * scenes.YAML["occupancy_resolution"] / 3.0
     wps = np.concatenate([init_s[:2, :1], q[:2], final_s[:2, :1]], axis=1).T
-    pts = extract_query_points(gm, wps, half)
-    path = scenes.eval_traj_xy(b, T, np.linspace(0.0, float(T.sum()), 1001))[:, :2]
-    keep = np.ones(pts.shape[0], dtype=bool)
-    for s in range(0, pts.shape[0], 200_000):
-        blk = pts[s : s + 200_000, :2]
-        d2 = ((blk[:, None, :] - path[None, ::2, :]) ** 2).sum(axis=2).min(axis=1)
-        keep[s : s + 200_000] = d2 > clearance * clearance
-    pts = pts[keep]
+    pts = extract_query_points(gm, wps, half, keepout=keepout_samples(b, T), clearance=clearance)
     if P is not None and pts.shape[0] > P:
         rng = np.random.Generator(np.random.MT19937(seed + 1))
         pts = pts[np.sort(rng.choice(pts.shape[0], size=P, replace=False))]
     return scenes.Scene(shape="star", N=N, init_s=init_s, final_s=final_s, q=q, T=T, coeffs=b, points=pts, resolution=gm.res)
+
+
+def keepout_samples(b: np.ndarray, T: np.ndarray, n: int = 150) -> np.ndarray:
+    """Samples of the nominal path used as keep-out centres (synthetic stand-in for the A* front end's guarantee that the
+    initial path is collision free; <= 160 samples, the device kernel's limit)."""
+    return scenes.eval_traj_xy(b, T, np.linspace(0.0, float(T.sum()), n))[:, :2]
 
 
 class BatchRunner:

@@ -27,11 +27,13 @@ UNITS = [
     # (source, object, extra flags)
     ("svsdf_kernels_fast.cu", "svsdf_kernels_fast.o", []),
     ("svsdf_kernels_strict.cu", "svsdf_kernels_strict.o", ["-fmad=false"]),
+    ("svsdf_extract.cu", "svsdf_extract.o", ["-fmad=false"]),  # cell centres must round like the host formula
     ("svsdf_runtime.cpp", "svsdf_runtime.o", []),
 ]
 HEADERS = [
     "svsdf_kernels.cuh",
     "svsdf_shapes.cuh",
+    "svsdf_sincos.cuh",
     "svsdf_types.h",
     "svsdf_launch.h",
     "host/minco.hpp",
@@ -44,9 +46,14 @@ def _mtime(p):
     return os.path.getmtime(p) if os.path.exists(p) else 0.0
 
 
+def _cmd(unit):
+    src, obj, extra = unit
+    return [NVCC, *ARCH, *COMMON, *extra, "-c", os.path.join(CSRC, src), "-o", os.path.join(OBJDIR, obj)]
+
+
 def _compile(unit, verbose):
     src, obj, extra = unit
-    cmd = [NVCC, *ARCH, *COMMON, *extra, "-c", os.path.join(CSRC, src), "-o", os.path.join(OBJDIR, obj)]
+    cmd = _cmd(unit)
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -54,6 +61,8 @@ def _compile(unit, verbose):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+    with open(os.path.join(OBJDIR, obj + ".cmd"), "w") as fh:  # rebuild when the flags change, not only the sources
+        fh.write(" ".join(_cmd(unit)))
     return r.stderr if verbose else ""
 
 
@@ -63,7 +72,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     todo = []
     for u in UNITS:
         src_t = max(_mtime(os.path.join(CSRC, u[0])), newest_hdr)
-        if force or _mtime(os.path.join(OBJDIR, u[1])) < src_t:
+        stamp = os.path.join(OBJDIR, u[1] + ".cmd")
+        same_cmd = os.path.exists(stamp) and open(stamp).read() == " ".join(_cmd(u))
+        if force or not same_cmd or _mtime(os.path.join(OBJDIR, u[1])) < src_t:
             todo.append(u)
     if todo:
         with cf.ThreadPoolExecutor(max_workers=len(todo)) as ex:

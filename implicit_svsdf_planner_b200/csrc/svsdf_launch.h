@@ -24,4 +24,8 @@ namespace svsdf {
 SVSDF_DECLARE_LAUNCHERS(fast)
 SVSDF_DECLARE_LAUNCHERS(strict)
 #undef SVSDF_DECLARE_LAUNCHERS
+cudaError_t launch_extract_count(const ExtractArgs &E, int *block_counts, int n_blocks, int64_t *n_total,
+                                 cudaStream_t stream);
+cudaError_t launch_extract_write(const ExtractArgs &E, const int *block_offsets, int n_blocks, double *out_xy,
+                                 int64_t cap, cudaStream_t stream);
 }  // namespace svsdf

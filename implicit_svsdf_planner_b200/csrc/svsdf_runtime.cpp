@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <chrono>
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -77,6 +78,16 @@ struct svsdf_ctx {
     int64_t cap_q = 0;
     double *h_stage = nullptr;  // pinned staging for points upload / results download
     size_t cap_stage = 0;
+
+    // packed map kernel (K3)
+    unsigned char *d_map = nullptr;
+    bool own_map = true;
+    size_t cap_map = 0;
+    int map_X = 0, map_Y = 0, map_h = 0, map_row_bytes = 0;
+    double map_ox = 0, map_oy = 0, map_res = 0;
+    int *d_block_counts = nullptr;
+    int cap_block_counts = 0;
+    int64_t *d_n_total = nullptr;
 
     // optimiser state (R3/R4)
     host::MincoS3NU minco;
@@ -516,6 +527,8 @@ void svsdf_destroy(svsdf_ctx *ctx) {
     cudaFree(ctx->d_eval_counter); cudaFree(ctx->d_tot); cudaFree(ctx->d_ticket); cudaFree(ctx->d_blob); cudaFree(ctx->d_partials); cudaFree(ctx->d_out);
     cudaFree(ctx->d_q_points); cudaFree(ctx->d_q_sdf); cudaFree(ctx->d_q_ts); cudaFree(ctx->d_q_grad);
     cudaFree(ctx->d_q_rounds);
+    if (ctx->own_map) cudaFree(ctx->d_map);
+    cudaFree(ctx->d_block_counts); cudaFree(ctx->d_n_total);
     if (ctx->h_blob) cudaFreeHost(ctx->h_blob);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -595,6 +608,8 @@ int svsdf_query(svsdf_ctx *ctx, int N, const double *T, const double *coeffs, in
     if (P > ctx->cap_q) {
         cudaFree(ctx->d_q_points); cudaFree(ctx->d_q_sdf); cudaFree(ctx->d_q_ts); cudaFree(ctx->d_q_grad);
         cudaFree(ctx->d_q_rounds);
+    if (ctx->own_map) cudaFree(ctx->d_map);
+    cudaFree(ctx->d_block_counts); cudaFree(ctx->d_n_total);
         ctx->d_q_points = ctx->d_q_sdf = ctx->d_q_ts = ctx->d_q_grad = nullptr;
         ctx->d_q_rounds = nullptr;
         ctx->cap_q = 0;
@@ -834,6 +849,134 @@ static int shape_eval(svsdf_ctx *ctx, int64_t n, const double *rel, double *out,
 }
 int svsdf_shape_sdf(svsdf_ctx *ctx, int64_t n, const double *rel, double *sdf_out) { return shape_eval(ctx, n, rel, sdf_out, 0); }
 int svsdf_shape_grad1(svsdf_ctx *ctx, int64_t n, const double *rel, double *grad3_out) { return shape_eval(ctx, n, rel, grad3_out, 1); }
+
+static int set_map_meta(svsdf_ctx *ctx, int X, int Y, int kernel_size, double ox, double oy, double res) {
+    if (X <= 0 || Y <= 0 || kernel_size < 1 || (kernel_size & 1) == 0 || !(res > 0.0)) {
+        ctx->err = "svsdf_set_map: bad map geometry (kernel_size must be odd, res > 0)";
+        return SVSDF_ERR_INVALID;
+    }
+    ctx->map_X = X; ctx->map_Y = Y; ctx->map_h = (kernel_size - 1) / 2;
+    ctx->map_row_bytes = (Y + 2 * ctx->map_h + 7) / 8;
+    ctx->map_ox = ox; ctx->map_oy = oy; ctx->map_res = res;
+    return SVSDF_OK;
+}
+
+int svsdf_set_map(svsdf_ctx *ctx, const unsigned char *kernel_bytes, int X, int Y, int kernel_size, double origin_x,
+                  double origin_y, double res) {
+    if (!ctx || !kernel_bytes) return SVSDF_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int rc = set_map_meta(ctx, X, Y, kernel_size, origin_x, origin_y, res);
+    if (rc) return rc;
+    const size_t bytes = (size_t)(X + 2 * ctx->map_h) * ctx->map_row_bytes;
+    if (!ctx->own_map) { ctx->d_map = nullptr; ctx->own_map = true; ctx->cap_map = 0; }
+    if (bytes > ctx->cap_map) {
+        cudaFree(ctx->d_map);
+        ctx->d_map = nullptr;
+        ctx->cap_map = 0;
+        CK(cudaMalloc(&ctx->d_map, bytes + 64));
+        ctx->cap_map = bytes + 64;
+    }
+    CK(cudaMemcpyAsync(ctx->d_map, kernel_bytes, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SVSDF_OK;
+}
+
+int svsdf_set_map_device(svsdf_ctx *ctx, const unsigned char *dev_kernel_bytes, int X, int Y, int kernel_size,
+                         double origin_x, double origin_y, double res) {
+    if (!ctx || !dev_kernel_bytes) return SVSDF_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int rc = set_map_meta(ctx, X, Y, kernel_size, origin_x, origin_y, res);
+    if (rc) return rc;
+    if (ctx->own_map) cudaFree(ctx->d_map);
+    ctx->d_map = const_cast<unsigned char *>(dev_kernel_bytes);
+    ctx->own_map = false;
+    ctx->cap_map = 0;
+    return SVSDF_OK;
+}
+
+int svsdf_extract_points(svsdf_ctx *ctx, const double *waypoints_xy, int W, double half, const double *keepout_xy,
+                         int n_keepout, double clearance, int64_t *n_points) {
+    if (!ctx || !waypoints_xy || W < 1 || W > kMaxWaypoints || n_keepout < 0 || n_keepout > kMaxKeepout ||
+        (n_keepout > 0 && !keepout_xy) || !(half >= 0.0))
+        return SVSDF_ERR_INVALID;
+    if (!ctx->d_map) { ctx->err = "svsdf_extract_points: map not set"; return SVSDF_ERR_NOT_READY; }
+    CK(cudaSetDevice(ctx->device));
+    ExtractArgs E;
+    std::memset(&E, 0, sizeof(E));
+    E.map = ctx->d_map;
+    E.X = ctx->map_X; E.Y = ctx->map_Y; E.h = ctx->map_h; E.row_bytes = ctx->map_row_bytes;
+    E.ox = ctx->map_ox; E.oy = ctx->map_oy; E.res = ctx->map_res;
+    E.W = W;
+    const double lo[2] = {E.ox, E.oy};
+    const double hi[2] = {E.ox + (double)E.X * E.res, E.oy + (double)E.Y * E.res};  // boundary_xyzmax
+    const int size[2] = {E.X, E.Y};
+    int rxmin = E.X, rxmax = -1, rymin = E.Y, rymax = -1;
+    for (int w = 0; w < W; ++w) {
+        int idx[2][2];
+        for (int a = 0; a < 2; ++a) {
+            for (int side = 0; side < 2; ++side) {
+                double c = waypoints_xy[2 * w + a] + (side ? half : -half);  // corner1 = center - half, corner2 = center + half
+                c = c < lo[a] ? lo[a] : c;                                  // projInMap (PCSmap_manager.h:128-135)
+                c = c > hi[a] ? hi[a] : c;
+                int i = (int)std::floor((c - lo[a]) / E.res);               // getGridIndex (Gridmap3D.cpp:144-148)
+                i = i < 0 ? 0 : i;
+                i = i >= size[a] ? size[a] - 1 : i;
+                idx[a][side] = i;
+            }
+        }
+        E.bx1[w] = idx[0][0]; E.bx2[w] = idx[0][1]; E.by1[w] = idx[1][0]; E.by2[w] = idx[1][1];
+        rxmin = std::min(rxmin, E.bx1[w]); rxmax = std::max(rxmax, E.bx2[w]);
+        rymin = std::min(rymin, E.by1[w]); rymax = std::max(rymax, E.by2[w]);
+    }
+    E.rx1 = rxmin;
+    E.wy1 = (rymin + E.h) / 32;
+    const int wy2 = (rymax + E.h) / 32;
+    E.nW = wy2 - E.wy1 + 1;
+    E.n_items = (long long)(rxmax - rxmin + 1) * E.nW;
+    E.n_keepout = n_keepout;
+    E.clearance = clearance;
+    for (int q = 0; q < 2 * n_keepout; ++q) E.keepout[q] = keepout_xy[q];
+    const int n_blocks = (int)((E.n_items + 255) / 256);
+    if (n_blocks + 1 > ctx->cap_block_counts) {
+        cudaFree(ctx->d_block_counts);
+        ctx->d_block_counts = nullptr;
+        ctx->cap_block_counts = 0;
+        CK(cudaMalloc(&ctx->d_block_counts, (size_t)(n_blocks + 1024) * sizeof(int)));
+        ctx->cap_block_counts = n_blocks + 1024;
+    }
+    if (!ctx->d_n_total) CK(cudaMalloc(&ctx->d_n_total, sizeof(int64_t)));
+    CK(launch_extract_count(E, ctx->d_block_counts, n_blocks, ctx->d_n_total, ctx->stream));
+    ctx->launches += 2;
+    int64_t total = 0;
+    CK(cudaMemcpyAsync(&total, ctx->d_n_total, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (total > 2000000000LL) { ctx->err = "svsdf_extract_points: too many points"; return SVSDF_ERR_INVALID; }
+    if (!ctx->own_points) { ctx->d_points = nullptr; ctx->own_points = true; ctx->cap_points = 0; }
+    if (total > ctx->cap_points || !ctx->d_points) {
+        cudaFree(ctx->d_points);
+        ctx->d_points = nullptr;
+        ctx->cap_points = 0;
+        CK(cudaMalloc(&ctx->d_points, (size_t)(total + 1024) * 2 * sizeof(double)));
+        ctx->cap_points = total + 1024;
+    }
+    CK(launch_extract_write(E, ctx->d_block_counts, n_blocks, ctx->d_points, total, ctx->stream));
+    ctx->launches += 1;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->P = total;
+    ctx->last_n_inside = -1;
+    if (n_points) *n_points = total;
+    return ensure_scratch(ctx, total);
+}
+
+int svsdf_get_points(svsdf_ctx *ctx, double *xy_out, int64_t capacity, int64_t *n_points) {
+    if (!ctx) return SVSDF_ERR_INVALID;
+    if (n_points) *n_points = ctx->P;
+    if (!xy_out || capacity <= 0 || ctx->P == 0) return SVSDF_OK;
+    CK(cudaSetDevice(ctx->device));
+    const int64_t n = ctx->P < capacity ? ctx->P : capacity;
+    CK(cudaMemcpy(xy_out, ctx->d_points, (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost));
+    return SVSDF_OK;
+}
 
 int svsdf_sincos(svsdf_ctx *ctx, int64_t n, const double *x, double *sin_out, double *cos_out) {
     if (!ctx || n < 0 || (n > 0 && (!x || !sin_out || !cos_out))) return SVSDF_ERR_INVALID;

@@ -116,4 +116,20 @@ struct KernelArgs {
     unsigned long long *eval_counter;  // optional: executed lane-evaluations (profiling builds)
 };
 
+// K3 (svsdf_extract.cu): query-point extraction from the packed map kernel
+constexpr int kMaxWaypoints = 66;   // interior waypoints of <= 64 pieces (+ optional end points)
+constexpr int kMaxKeepout = 160;    // keep-out polyline samples (synthetic scenes only)
+struct ExtractArgs {
+    const unsigned char *map;  // (X + 2h) x row_bytes, MSB-first bits along y (PCSmap_manager.h:81-108)
+    int X, Y, h, row_bytes;
+    double ox, oy, res;        // boundary_xyzmin (x, y) and grid resolution
+    int W;                     // number of waypoint boxes
+    int bx1[kMaxWaypoints], bx2[kMaxWaypoints], by1[kMaxWaypoints], by2[kMaxWaypoints];  // clamped index boxes
+    int rx1, wy1, nW;          // bounding rectangle: first row, first 32-cell word, words per row
+    long long n_items;         // rows * nW
+    int n_keepout;
+    double clearance;
+    double keepout[2 * kMaxKeepout];
+};
+
 }  // namespace svsdf

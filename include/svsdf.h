@@ -162,6 +162,26 @@ int svsdf_shape_grad1(svsdf_ctx *ctx, int64_t n, const double *rel, double *grad
 int svsdf_cost_grad_device(svsdf_ctx *ctx, int N, const double *T, const double *coeffs, int repeats,
                            float *ms_per_eval, double *out_host);
 
+/* ---- "next" row: query-point construction on the device --------------------------------------
+ * R8  PlannerManager::generateTraj point collection  plan_manager/src/plan_manager.cpp:156-175
+ *     PCSmapManager::getPointsInAABBOutOfLastOne       map_manager/include/map_manager/PCSmap_manager.h:184-219
+ *     on the byte-packed map kernel of PCSmapManager::generateMapKernel2D (PCSmap_manager.h:81-108), z = 0 layer.
+ * svsdf_set_map copies the packed map ((X + 2h) rows of ceil((Y + 2h)/8) bytes, h = (kernel_size-1)/2, MSB first) to the
+ * device; svsdf_set_map_device adopts a device buffer (e.g. the NCCL-broadcast one) without copying.  origin = the
+ * map's boundary_xyzmin (x, y), res = grid resolution. */
+int svsdf_set_map(svsdf_ctx *ctx, const unsigned char *kernel_bytes, int X, int Y, int kernel_size, double origin_x,
+                  double origin_y, double res);
+int svsdf_set_map_device(svsdf_ctx *ctx, const unsigned char *dev_kernel_bytes, int X, int Y, int kernel_size,
+                         double origin_x, double origin_y, double res);
+/* Builds the context's resident query-point set from the map: occupied cells inside the AABB (half-size `half` in x and
+ * y) of waypoint w and outside the AABB of waypoint w-1, de-duplicated, in ascending (i*Y + j) order.
+ * waypoints_xy: W x 2.  keepout_xy / clearance (optional, n_keepout = 0 to disable; not part of the reference): drop
+ * cells closer than `clearance` to any keep-out sample.  n_points receives the count. */
+int svsdf_extract_points(svsdf_ctx *ctx, const double *waypoints_xy, int W, double half, const double *keepout_xy,
+                         int n_keepout, double clearance, int64_t *n_points);
+/* Copies the context's resident points (packed x, y) back to the host (tests). */
+int svsdf_get_points(svsdf_ctx *ctx, double *xy_out, int64_t capacity, int64_t *n_points);
+
 /* The device sin/cos used on the path (fdlibm restatement, csrc/svsdf_sincos.cuh), exposed for parity tests. */
 int svsdf_sincos(svsdf_ctx *ctx, int64_t n, const double *x, double *sin_out, double *cos_out);
 
