@@ -170,15 +170,17 @@ struct OuterResult {
 // Decisions are the sequential loop's: the slope's sign always comes from the finite difference on lanes 30/31, and the
 // accepted halving is the first (largest step) whose candidate decreases f.
 template <int SHAPE, bool XFORM>
-__device__ __forceinline__ OuterResult solve_outer(const TrajView &tv, const ShapeParams &S, double px, double py) {
+__device__ __forceinline__ OuterResult solve_outer(const TrajView &tv, const ShapeParams &S, double px, double py,
+                                                   bool have_seed = false, double seed_in = 0.0, double min_in = 1e9) {
     const int lane = threadIdx.x & 31;
     const double D = tv.D;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     int evals = 0;
 
     // ---- choiceTInit layer 1: shared lattice t_k (accumulated 0.15 adds) with the pose table ----
-    double min_dis = 1e9, seed = 0.0;
-    for (int base = 0; base < tv.K1; base += 32) {
+    // (skipped when the caller already ran choiceTInit thread-per-point: thread_choice_t_init)
+    double min_dis = have_seed ? min_in : 1e9, seed = have_seed ? seed_in : 0.0;
+    for (int base = have_seed ? tv.K1 : 0; base < tv.K1; base += 32) {
         int k = base + lane;
         double f = INF;
         if (k < tv.K1) {
@@ -202,6 +204,14 @@ __device__ __forceinline__ OuterResult solve_outer(const TrajView &tv, const Sha
     double x = 0.0, fx = 0.0, prev_x = 10000000.0, t_min = 0.0, t_max = 0.0;
     int iter = 0, pred = 0, sgn = 0;
     bool stop = false, running = true;
+    if (have_seed) {  // enter the state machine at the gradientDescent set-up (:856-857)
+        t_min = smaxd(0.0, seed - 3.4);
+        t_max = smind(seed + 3.4, D);
+        x = seed;
+        fx = min_dis;
+        mode = __any_sync(FULL, min_dis >= 1e9) ? M_F0 : M_A;
+        if (mode == M_A) prev_x = x;  // first outer step: `prev_x = x` after the (true) loop test
+    }
 #pragma unroll 1
     while (running) {
         // ---------------- sample time of this lane for the current round ----------------
@@ -437,6 +447,80 @@ __device__ __forceinline__ Contribution point_contribution(const TrajView &tv, c
 }
 
 // ------------------------------------------------------------------------------------------------
+// Thread-per-point pieces used by the batched path of k_outer (32 points per warp at a time): the parts of the
+// per-point work that have no intra-point parallelism worth a warp are run one point per LANE, literally as the
+// reference's loops, and only gradientDescent (29-way speculative) stays one point per WARP.
+// ------------------------------------------------------------------------------------------------
+// choiceTInit<false>(p, 0.15) (sw_manager.hpp:538-581); layer 1 reads the shared pose table
+template <int SHAPE, bool XFORM>
+__device__ __forceinline__ void thread_choice_t_init(const TrajView &tv, const ShapeParams &S, double px, double py,
+                                                     double &seed, double &min_dis, int &evals) {
+    min_dis = 1e9;
+    seed = 0.0;
+    const double *ps = tv.pose;
+#pragma unroll 1
+    for (int k = 0; k < tv.K1; ++k) {
+        double rx, ry;
+        rel_from_pose(px, py, ps[k], ps[tv.K1pad + k], ps[2 * tv.K1pad + k], ps[3 * tv.K1pad + k], rx, ry);
+        const double f = dev::shape_sdf<SHAPE, XFORM>(S, rx, ry);
+        if (f < min_dis) {
+            min_dis = f;
+            seed = tv.lat[k];
+        }
+    }
+    evals += tv.K1;
+    double dt = 0.15;
+#pragma unroll 1
+    for (int layer = 2; layer <= 4; ++layer) {
+        dt *= 0.1;
+        double t = smaxd(0.0, seed - 10 * dt);
+        const double term = smind(tv.D, seed + 10 * dt);
+#pragma unroll 1
+        for (; t <= term; t += dt) {
+            const double f = eval_sdf<SHAPE, XFORM>(tv, S, px, py, t);
+            ++evals;
+            if (f < min_dis) {
+                seed = t;
+                min_dis = f;
+            }
+        }
+    }
+}
+
+// getGradPrelAtTimeStamp (sw_manager.hpp:779-795) -> getonlyGrad1 (Shape.hpp:35-53), one point per thread
+template <int SHAPE, bool XFORM>
+__device__ __forceinline__ void thread_grad_prel(const TrajView &tv, const ShapeParams &S, double px, double py, double t,
+                                                 double &gx, double &gy) {
+    double x, y, yaw, sy, cy, rx, ry;
+    traj_pos(tv, t, x, y, yaw);
+    dev::sincos_portable(yaw, sy, cy);
+    rel_from_pose(px, py, x, y, cy, sy, rx, ry);
+    if (SHAPE == SH_POLYGON) {
+        dev::PolyHit H = dev::polygon_scan(S, rx, ry);
+        double vx = rx - H.cx, vy = ry - H.cy;
+        double z = vx * vx + vy * vy;
+        if (z > 0.0) {
+            double n = sqrt(z);
+            vx /= n; vy /= n;
+        }
+        if (H.rs % 2 != 0) { vx = -vx; vy = -vy; }
+        gx = vx; gy = vy;
+        return;
+    }
+    const double dx = 0.000001;
+    double f[4];
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {  // (x-dx), (x-dx)+2dx, (y-dx), (y-dx)+2dx — one evaluation site
+        double qx = rx, qy = ry;
+        if (q < 2) { qx -= dx; if (q == 1) qx += 2 * dx; }
+        else { qy -= dx; if (q == 3) qy += 2 * dx; }
+        f[q] = dev::shape_sdf<SHAPE, XFORM>(S, qx, qy);
+    }
+    gx = (f[1] - f[0]) / (2 * dx);
+    gy = (f[3] - f[2]) / (2 * dx);
+}
+
+// ------------------------------------------------------------------------------------------------
 // TMA bulk copy of the trajectory blob into shared memory (cp.async.bulk + mbarrier)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -511,34 +595,75 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, SVSDF_OUTER_MIN_CTAS)
     __syncwarp();
 
     const int64_t wstride = (int64_t)gridDim.x * kWarpsPerBlock;
+    const int64_t first = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
     unsigned long long my_evals = 0;
-    for (int64_t pt = (int64_t)blockIdx.x * kWarpsPerBlock + warp; pt < A.P; pt += wstride) {
-        const double px = __ldg(A.points_xy + 2 * pt), py = __ldg(A.points_xy + 2 * pt + 1);
-        OuterResult R = solve_outer<SHAPE, XFORM>(tv, S, px, py);
-        double gx, gy;
-        grad_prel<SHAPE, XFORM>(tv, S, px, py, R.tstar, gx, gy);
-        my_evals += (unsigned long long)R.evals + 4ull;
-        const bool inside = A.want_gsip && !(R.sdf > 0);  // getTrueSDFofSweptVolume: `if (argmin_dis > 0) return`
-        if (lane == 0) {
-            if (A.out_sdf) A.out_sdf[pt] = R.sdf;
-            if (A.out_tstar) A.out_tstar[pt] = R.tstar;
-            if (A.out_grad) { A.out_grad[3 * pt] = gx; A.out_grad[3 * pt + 1] = gy; A.out_grad[3 * pt + 2] = 0.0; }
-            if (A.out_rounds) A.out_rounds[pt] = 0;
-            if (A.inside_flag) A.inside_flag[pt] = inside ? 1 : 0;
-            if (inside && A.inside_tstar) A.inside_tstar[pt] = R.tstar;
+    // The warp owns points first, first + wstride, ...; it walks them in batches of 32 (lane i <-> i-th point of the
+    // batch).  Batched path (many points per warp): choiceTInit and the FD gradient / penalty / chain rule run one point
+    // per lane; gradientDescent runs one point per warp, one batch member after the other.  Sparse path (few points per
+    // warp, i.e. small problems): everything one point per warp, as solve_outer / grad_prel do.
+    for (int64_t bfirst = first; bfirst < A.P; bfirst += 32 * wstride) {
+        const int64_t my_pt = bfirst + (int64_t)lane * wstride;
+        const bool my_valid = my_pt < A.P;
+        const int nb = (int)min((int64_t)32, (A.P - bfirst + wstride - 1) / wstride);  // batch size (warp-uniform)
+        const int64_t ld_pt = my_valid ? my_pt : bfirst;
+        const double mpx = __ldg(A.points_xy + 2 * ld_pt), mpy = __ldg(A.points_xy + 2 * ld_pt + 1);
+        const bool batched = A.batched && nb >= 12;
+        double m_seed = 0.0, m_min = 1e9, m_sdf = 0.0, m_ts = 0.0, m_gx = 0.0, m_gy = 0.0;
+        if (batched) {
+            int ev = 0;
+            if (my_valid) thread_choice_t_init<SHAPE, XFORM>(tv, S, mpx, mpy, m_seed, m_min, ev);
+            my_evals += (unsigned long long)__reduce_add_sync(FULL, ev);
+            __syncwarp();
         }
-        if (A.want_reduce && !inside) {
-            Contribution C = point_contribution(tv, A.cp, px, py, R.sdf, R.tstar, gx, gy);
-            if (C.active) {
+#pragma unroll 1
+        for (int i = 0; i < nb; ++i) {
+            const double px = __shfl_sync(FULL, mpx, i), py = __shfl_sync(FULL, mpy, i);
+            const double sd = __shfl_sync(FULL, m_seed, i), mn = __shfl_sync(FULL, m_min, i);
+            const OuterResult R = solve_outer<SHAPE, XFORM>(tv, S, px, py, batched, sd, mn);
+            my_evals += (unsigned long long)R.evals;
+            if (lane == i) { m_sdf = R.sdf; m_ts = R.tstar; }
+            if (!batched) {
+                double gx, gy;
+                grad_prel<SHAPE, XFORM>(tv, S, px, py, R.tstar, gx, gy);
+                if (lane == i) { m_gx = gx; m_gy = gy; }
+            }
+        }
+        my_evals += 4ull * (unsigned long long)nb;
+        if (batched && my_valid) thread_grad_prel<SHAPE, XFORM>(tv, S, mpx, mpy, m_ts, m_gx, m_gy);
+        // ---- per-lane epilogue: outputs, interior flag, penalty + chain rule (one point per lane) ----
+        const bool inside = my_valid && A.want_gsip && !(m_sdf > 0);  // getTrueSDFofSweptVolume: `if (argmin_dis > 0) return`
+        if (my_valid) {
+            if (A.out_sdf) A.out_sdf[my_pt] = m_sdf;
+            if (A.out_tstar) A.out_tstar[my_pt] = m_ts;
+            if (A.out_grad) { A.out_grad[3 * my_pt] = m_gx; A.out_grad[3 * my_pt + 1] = m_gy; A.out_grad[3 * my_pt + 2] = 0.0; }
+            if (A.out_rounds) A.out_rounds[my_pt] = 0;
+            if (A.inside_flag) A.inside_flag[my_pt] = inside ? 1 : 0;
+            if (inside && A.inside_tstar) A.inside_tstar[my_pt] = m_ts;
+        }
+        if (A.want_reduce) {
+            Contribution C;
+            C.active = false;
+            if (my_valid && !inside) C = point_contribution(tv, A.cp, mpx, mpy, m_sdf, m_ts, m_gx, m_gy);
+            // accumulate the active lanes' contributions in batch order (deterministic)
+            unsigned m = __ballot_sync(FULL, C.active);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const int piece = __shfl_sync(FULL, C.piece, src);
+                const double s1 = __shfl_sync(FULL, C.s1, src);
+                const double g0 = __shfl_sync(FULL, C.G[0], src), g1 = __shfl_sync(FULL, C.G[1], src),
+                             g2 = __shfl_sync(FULL, C.G[2], src);
+                const double gdT = __shfl_sync(FULL, C.gdT, src), pena = __shfl_sync(FULL, C.pena, src);
                 if (lane < 18) {
-                    int d = lane / 6, q = lane - 6 * d;
-                    double s1 = C.s1, s2 = s1 * s1, s3 = s2 * s1, s4 = s2 * s2, s5 = s4 * s1;
-                    double beta = (q == 0) ? 1.0 : (q == 1) ? s1 : (q == 2) ? s2 : (q == 3) ? s3 : (q == 4) ? s4 : s5;
-                    acc[C.piece * 18 + lane] += beta * C.G[d];
+                    const int d = lane / 6, q = lane - 6 * d;
+                    const double s2 = s1 * s1, s3 = s2 * s1, s4 = s2 * s2, s5 = s4 * s1;
+                    const double beta = (q == 0) ? 1.0 : (q == 1) ? s1 : (q == 2) ? s2 : (q == 3) ? s3 : (q == 4) ? s4 : s5;
+                    const double gd = (d == 0) ? g0 : (d == 1) ? g1 : g2;
+                    acc[piece * 18 + lane] += beta * gd;
                 } else if (lane == 18) {
-                    acc[18 * tv.N + C.piece] += C.gdT;
+                    acc[18 * tv.N + piece] += gdT;
                 } else if (lane == 19) {
-                    acc[19 * tv.N] += C.pena;
+                    acc[19 * tv.N] += pena;
                 }
                 __syncwarp();
             }

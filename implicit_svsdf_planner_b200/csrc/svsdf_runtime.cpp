@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -321,7 +322,11 @@ int run_kernels(svsdf_ctx *ctx, const double *d_points, int64_t P, bool reduce, 
     if (rc) return rc;
     rc = refresh_occupancy(ctx);
     if (rc) return rc;
-    const int grid = grid_for(ctx, P);
+    int grid = grid_for(ctx, P);
+    if (const char *fg = std::getenv("SVSDF_FORCE_GRID_OUTER")) {  // test hook: exercise the batched path on small inputs
+        const int g = std::atoi(fg);
+        if (g > 0) grid = g;
+    }
     const int nacc = 19 * N + 1;
     if (reduce) {
         int64_t need = (int64_t)grid * nacc;
@@ -355,6 +360,9 @@ int run_kernels(svsdf_ctx *ctx, const double *d_points, int64_t P, bool reduce, 
     A.partials = ctx->d_partials;
     A.want_reduce = reduce ? 1 : 0;
     A.want_gsip = gsip ? 1 : 0;
+    // batched path pays off once every warp owns a couple of dozen points; small problems keep one point per warp
+    A.batched = (P >= (int64_t)16 * grid * kWarpsPerBlock) ? 1 : 0;
+    if (const char *fb = std::getenv("SVSDF_FORCE_BATCHED")) A.batched = std::atoi(fb);
     A.inside_flag = ctx->d_flag;
     A.inside_tstar = ctx->d_inside_tstar;
     A.inside_list = ctx->d_inside_list;

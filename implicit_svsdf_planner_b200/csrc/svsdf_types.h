@@ -106,6 +106,7 @@ struct KernelArgs {
     double *partials;          // [gridDim.x][19N+1] block partial sums (K1)
     int want_reduce;
     int want_gsip;             // 0: stop after the outer solve (getSDFofSweptVolume semantics)
+    int batched;               // k_outer: run choiceTInit / gradient / chain rule one point per lane (large P)
     // inside-point bookkeeping
     unsigned char *inside_flag;  // P
     double *inside_tstar;        // P (sparse: written for inside points only)

@@ -153,6 +153,38 @@ def test_query_agrees_with_other_reference_builds_up_to_flat_minima(oracle_mod, 
         assert (np.abs(g_g - g_c).max(axis=1) < 1e-5).mean() > 0.99
 
 
+def test_batched_path_is_bit_identical_to_sparse_path(oracle_mod, scene2k, scene_small_inside, monkeypatch):
+    """k_outer has two schedules: one point per warp throughout (small problems) and the batched one (choiceTInit, FD
+    gradient and chain rule one point per lane, 32 points per warp at a time).  Both must give the oracle's bits."""
+    for sc in (scene2k, scene_small_inside):
+        co = sc.coeffs_colmajor()
+        p = pts0(sc)
+        orc = oracle_mod.Oracle("star", threads=oracle_mod.num_procs())
+        orc.set_traj(sc.T, co)
+        s_c, t_c, g_c, r_c = orc.query(p)
+        res = {}
+        for mode, grid in (("sparse", None), ("batched", "3"), ("batched-ragged", "7")):
+            if grid is None:
+                monkeypatch.delenv("SVSDF_FORCE_GRID_OUTER", raising=False)
+                monkeypatch.setenv("SVSDF_FORCE_BATCHED", "0")
+            else:
+                monkeypatch.setenv("SVSDF_FORCE_GRID_OUTER", grid)  # 3 CTAs = 24 warps -> batches of 32 / 16 points per warp
+                monkeypatch.setenv("SVSDF_FORCE_BATCHED", "1")
+            ctx = api.Context("star")
+            s_g, t_g, g_g, r_g = ctx.query(sc.T, co, p)
+            out = r_c == 0
+            assert np.array_equal(r_g, r_c), mode
+            assert np.array_equal(s_g[out], s_c[out]) and np.array_equal(t_g[out], t_c[out]) and np.array_equal(g_g[out], g_c[out]), mode
+            ctx.set_points(sc.points)
+            res[mode] = ctx.cost_grad(sc.T, co)
+        c0, gT0, gC0 = res["sparse"]
+        for mode in ("batched", "batched-ragged"):
+            c1, gT1, gC1 = res[mode]
+            assert abs(c1 - c0) <= 1e-13 * abs(c0) and nrel(gC1, gC0) <= 1e-12 and gT_err(gT1, gT0, gC0) <= 1e-12, mode
+    monkeypatch.delenv("SVSDF_FORCE_GRID_OUTER", raising=False)
+    monkeypatch.delenv("SVSDF_FORCE_BATCHED", raising=False)
+
+
 def test_query_matches_committed_golden():
     for name in ("config1_star_2k.npz", "config_inside_400.npz"):
         G = np.load(os.path.join(HERE, "golden", name))
