@@ -232,7 +232,8 @@ __device__ __forceinline__ OuterResult solve_outer(const TrajView &tv, const Sha
             if (mode == M_A) { j = (lane < 15) ? lane : lane - 15; sdir = (lane < 15) ? 1 : -1; }
             else if (mode == M_B) { j = 15 + lane; sdir = sgn; }
             else { j = lane; sdir = (mode == M_P) ? pred : sgn; }
-            const double tau = scalbn(0.01, -j);  // alpha halved j times (exact)
+            // alpha = 0.01 halved j times: exact, so subtract j from the exponent field (0.01 * 2^-46 is still normal)
+            const double tau = __hiloint2double(__double2hiint(0.01) - (j << 20), __double2loint(0.01));
             tq = smaxd(smind(x + (-tau * (double)sdir), t_max), t_min);
             if (mode != M_B) {
                 tq = (lane == 30) ? smaxd(0.0, x - 0.000001) : tq;  // getSDF_DOTAtTimeStamp :798-806
