@@ -1,0 +1,197 @@
+// svsdf.hpp — header-only C++ mirror of the reference's call surface for the SVSDF path, on top of the C ABI (svsdf.h).
+//
+// Same class / method names, argument meaning and error behaviour as the reference, minus Eigen and ROS (plain
+// std::vector / pointers in the reference's own memory layouts), so reference-side code ports almost verbatim:
+//   svsdf::Config                      <- struct Config            (src/utils/include/utils/config.hpp:96-165, hot-path subset)
+//   svsdf::shape::BasicShape           <- shape::BasicShape        (src/utils/include/utils/Shape.hpp:96-431) getonlySDF / getonlyGrad1 /
+//                                         getSDFwithGrad1; shapeConstructors registry keys (sw_manager.hpp:187-235)
+//   svsdf::SweptVolumeManager          <- SweptVolumeManager       (src/swept_volume/include/swept_volume/sw_manager.hpp) updateTraj :376-385,
+//                                         getSDFofSweptVolume :844-866, getTrueSDFofSweptVolume :916-1018
+//   svsdf::TrajOptimizer               <- TrajOptimizer            (src/planner_algorithm/include/planner_algorithm/back_end_optimizer.hpp)
+//                                         setParam :877-932, setEnvironment :935, parallel_points(_num), costFunctionLmbmParallel :344-408,
+//                                         addSaftyPenaOnSweptVolumeParallelTrueSDF :774-869, optimize_traj_lmbm (back_end_optimizer.cpp:3-97)
+// Errors: like the reference there are no exceptions on the hot path; methods return the solver / status code and
+// last_error() gives the text.  Construction throws std::runtime_error when no sm_100 GPU is usable (no CPU fallback).
+#pragma once
+#include <array>
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+extern "C" {
+#include "svsdf.h"
+}
+
+namespace svsdf {
+
+struct Config {                       // yaml keys of src/plan_manager/config/<shape>.yaml read by the hot path
+    std::string inputdata = "shapes/star.obj";
+    std::vector<double> poly_params{0.0, 0.0, 0.0};
+    double weight_p = 60.0, safety_hor = 0.7, rho = 3.8, inittime = 2.5;
+    int threads_num = 12;            // ignored (the GPU replaces the OpenMP team)
+    int kernel_size = 17;
+    double occupancy_resolution = 1.0, momentum = 0.0;
+    int mem_size = 16, past = 3;     // outer L-BFGS (mid-end yaml keys of the reference)
+    double min_step = 1.0e-32, g_epsilon = 0.0, relCostTol = 1.0e-6;
+    int device = 0;
+    bool strict_fp = true;
+    std::vector<double> polygon_xy;  // vertices for the Polygon fallback (empty -> the reference's 12 x 0.2 rectangle)
+
+    // registry key = basename of inputdata without extension (sw_manager.hpp:350-354)
+    std::string shapetype() const {
+        size_t s = inputdata.find_last_of('/');
+        s = (s == std::string::npos) ? 0 : s + 1;
+        size_t e = inputdata.find_last_of('.');
+        if (e == std::string::npos || e < s) e = inputdata.size();
+        return inputdata.substr(s, e - s);
+    }
+};
+
+namespace detail {
+struct Ctx {
+    svsdf_ctx *h = nullptr;
+    std::string key;
+    explicit Ctx(const Config &c) : key(c.shapetype()) {
+        svsdf_config cfg;
+        svsdf_default_config(&cfg);
+        cfg.shape = key.c_str();
+        for (int i = 0; i < 3; ++i) cfg.poly_params[i] = i < (int)c.poly_params.size() ? c.poly_params[i] : 0.0;
+        cfg.weight_p = c.weight_p; cfg.safety_hor = c.safety_hor; cfg.rho = c.rho;
+        cfg.device = c.device; cfg.strict_fp = c.strict_fp ? 1 : 0;
+        if (c.polygon_xy.size() >= 6) { cfg.polygon_xy = c.polygon_xy.data(); cfg.polygon_n = (int)(c.polygon_xy.size() / 2); }
+        if (svsdf_create(&cfg, &h) != SVSDF_OK || !h) throw std::runtime_error("svsdf_create failed (no sm_100 CUDA device? there is no CPU fallback)");
+    }
+    ~Ctx() { svsdf_destroy(h); }
+    Ctx(const Ctx &) = delete;
+    Ctx &operator=(const Ctx &) = delete;
+};
+}  // namespace detail
+
+namespace shape {
+// The functor API of shape::BasicShape (Shape.hpp:266-270).  pos_rel: body-frame point (x, y, z); z is ignored by the 2-D shapes.
+class BasicShape {
+   public:
+    explicit BasicShape(std::shared_ptr<detail::Ctx> c) : ctx_(std::move(c)) {}
+    double getonlySDF(const double pos_rel[3]) const {
+        double out = 0.0;
+        svsdf_shape_sdf(ctx_->h, 1, pos_rel, &out);
+        return out;
+    }
+    std::array<double, 3> getonlyGrad1(const double pos_rel[3]) const {
+        std::array<double, 3> g{0, 0, 0};
+        svsdf_shape_grad1(ctx_->h, 1, pos_rel, g.data());
+        return g;
+    }
+    double getSDFwithGrad1(const double pos_rel[3], double grad[3]) const {
+        svsdf_shape_grad1(ctx_->h, 1, pos_rel, grad);
+        return getonlySDF(pos_rel);
+    }
+    // batched forms (n rows of 3 doubles): one kernel launch instead of n
+    int getonlySDF(int64_t n, const double *pos_rel, double *sdf_out) const { return svsdf_shape_sdf(ctx_->h, n, pos_rel, sdf_out); }
+    int getonlyGrad1(int64_t n, const double *pos_rel, double *grad3_out) const { return svsdf_shape_grad1(ctx_->h, n, pos_rel, grad3_out); }
+
+   private:
+    std::shared_ptr<detail::Ctx> ctx_;
+};
+// registry lookup: id of a key of shapeConstructors; unknown names -> the Polygon fallback id (sw_manager.hpp:363-372)
+inline int registry_id(const std::string &name) { return svsdf_shape_id(name.c_str()); }
+}  // namespace shape
+
+class SweptVolumeManager {
+   public:
+    typedef std::shared_ptr<SweptVolumeManager> Ptr;
+    explicit SweptVolumeManager(const Config &conf) : ctx_(std::make_shared<detail::Ctx>(conf)), current_robot_shape(new shape::BasicShape(ctx_)) {}
+
+    // updateTraj (:376-385).  T: N durations, coeffs: MINCO b (6N x 3, column-major).  Returns 0 or a negative svsdf_status
+    // (the reference silently ignores durations >= 300 s; this reports SVSDF_ERR_INVALID).
+    int updateTraj(int N, const double *T, const double *coeffs) {
+        N_ = N; T_.assign(T, T + N); c_.assign(coeffs, coeffs + 18 * (size_t)N);
+        return svsdf_set_traj(ctx_->h, N, T, coeffs);
+    }
+    // getTrueSDFofSweptVolume<true>(pos_eva, time_seed_f, grad_prel, set_ts) (:916-1018); set_ts is ignored like the reference's
+    // call sites pass false (the scan always runs).
+    double getTrueSDFofSweptVolume(const double pos_eva[3], double &time_seed_f, double grad_prel[3], bool /*set_ts*/ = false) {
+        double sdf = 0.0;
+        svsdf_query(ctx_->h, N_, T_.data(), c_.data(), 1, pos_eva, &sdf, &time_seed_f, grad_prel, nullptr, 0);
+        return sdf;
+    }
+    // getSDFofSweptVolume<false, true> (:844-866)
+    double getSDFofSweptVolume(const double pos_eva[3], double &time_seed_f, double grad_prel[3]) {
+        double sdf = 0.0;
+        svsdf_query(ctx_->h, N_, T_.data(), c_.data(), 1, pos_eva, &sdf, &time_seed_f, grad_prel, nullptr, 1);
+        return sdf;
+    }
+    // batched query (P rows of 3 doubles): what a caller with many points should use
+    int getTrueSDFofSweptVolume(int64_t P, const double *pos_eva, double *sdf, double *tstar, double *grad3, int *rounds = nullptr) {
+        return svsdf_query(ctx_->h, N_, T_.data(), c_.data(), P, pos_eva, sdf, tstar, grad3, rounds, 0);
+    }
+    const char *last_error() const { return svsdf_last_error(ctx_->h); }
+    svsdf_ctx *handle() const { return ctx_->h; }
+
+   private:
+    std::shared_ptr<detail::Ctx> ctx_;
+    int N_ = 0;
+    std::vector<double> T_, c_;
+
+   public:
+    std::unique_ptr<shape::BasicShape> current_robot_shape;
+};
+
+class TrajOptimizer {
+   public:
+    typedef std::shared_ptr<TrajOptimizer> Ptr;
+    // reference members kept public on purpose (plan_manager.cpp:168-175 fills them directly)
+    std::vector<std::array<double, 3>> parallel_points;
+    int parallel_points_num = 0;
+    double cost_pos = 0, cost_other = 0, cost_total = 0;
+    int pieceN = 0, temporalDim = 0, spatialDim = 0;
+
+    void setParam(const Config &config) { conf = config; }                       // :877-932
+    void setEnvironment(SweptVolumeManager::Ptr sv) { sv_manager = std::move(sv); }  // :935
+
+    // call after parallel_points / parallel_points_num have been filled
+    int uploadPoints() {
+        if (!sv_manager) return SVSDF_ERR_NOT_READY;
+        return svsdf_set_points(sv_manager->handle(), parallel_points_num ? parallel_points[0].data() : nullptr, parallel_points_num, 3);
+    }
+
+    // addSaftyPenaOnSweptVolumeParallelTrueSDF(ptr, T, coeffs, cost, gradT, gradC) (:774-869): accumulates
+    static int addSaftyPenaOnSweptVolumeParallelTrueSDF(void *ptr, int N, const double *T, const double *coeffs, double &cost,
+                                                        double *gradT, double *gradC) {
+        TrajOptimizer &obj = *static_cast<TrajOptimizer *>(ptr);
+        return svsdf_cost_grad(obj.sv_manager->handle(), N, T, coeffs, &cost, gradT, gradC);
+    }
+    // costFunctionLmbmParallel(ptr, x, g, n) (:344-408): lmbm_evaluate_t compatible
+    static double costFunctionLmbmParallel(void *ptr, const double *x_variable, double *g, const int n) {
+        TrajOptimizer &obj = *static_cast<TrajOptimizer *>(ptr);
+        const double f = svsdf_evaluate(obj.sv_manager->handle(), x_variable, g, n);
+        double c3[3];
+        if (svsdf_last_costs(obj.sv_manager->handle(), c3) == SVSDF_OK) { obj.cost_pos = c3[0]; obj.cost_other = c3[1]; obj.cost_total = c3[2]; }
+        return f;
+    }
+    int setConditions(const double *initS, const double *finalS, int N) {
+        pieceN = N; temporalDim = N; spatialDim = 3 * (N - 1);
+        return svsdf_set_boundary(sv_manager->handle(), initS, finalS, N);
+    }
+    // optimize_traj_lmbm(initS, finalS, opt_x, N, traj) (back_end_optimizer.cpp:3-97): returns >= 0 on success (0 remapped to 1),
+    // the negative solver code otherwise; opt_x and the trajectory (T, coeffs) are written either way.  The outer solver is
+    // this build's host L-BFGS (lbfgs_ref.hpp semantics); LMBM can drive costFunctionLmbmParallel instead.
+    int optimize_traj_lmbm(const double *initS, const double *finalS, std::vector<double> &opt_x, const int N,
+                           std::vector<double> &traj_T, std::vector<double> &traj_coeffs, svsdf_opt_stats *stats = nullptr) {
+        pieceN = N; temporalDim = N; spatialDim = 3 * (N - 1);
+        if ((int)opt_x.size() != temporalDim + spatialDim) return SVSDF_ERR_INVALID;
+        svsdf_lbfgs_params p;
+        svsdf_default_lbfgs_params(&p);
+        p.mem_size = conf.mem_size; p.past = conf.past; p.min_step = conf.min_step; p.g_epsilon = conf.g_epsilon; p.delta = conf.relCostTol;
+        traj_T.assign(N, 0.0);
+        traj_coeffs.assign(18 * (size_t)N, 0.0);
+        return svsdf_optimize(sv_manager->handle(), initS, finalS, opt_x.data(), N, &p, nullptr, nullptr, traj_T.data(), traj_coeffs.data(), stats);
+    }
+
+    Config conf;
+    SweptVolumeManager::Ptr sv_manager;
+};
+
+}  // namespace svsdf

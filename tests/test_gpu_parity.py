@@ -307,6 +307,29 @@ def test_other_shapes_and_piece_counts(oracle_mod, shape, N):
     assert nrel(gC1, gC0) <= 1e-8 and gT_err(gT1, gT0, gC0) <= 1e-8, (shape, nrel(gC1, gC0), gT_err(gT1, gT0, gC0))
 
 
+@pytest.mark.parametrize("shape", ALL_SHAPES)
+def test_every_registry_shape_end_to_end(oracle_mod, shape):
+    """Every key of the reference's shapeConstructors registry (+ Circle and the Polygon fallback) through the whole path:
+    per-point query bit-identical outside the swept volume, cost / gradient to summation order."""
+    sc = scenes.make_scene("star", 8, 240, clearance=1.6, seed_map=4242)
+    co = sc.coeffs_colmajor()
+    ctx = api.Context(shape)
+    orc = oracle_mod.Oracle(shape, threads=oracle_mod.num_procs())
+    p = pts0(sc)
+    orc.set_traj(sc.T, co)
+    s_c, t_c, g_c, r_c = orc.query(p)
+    s_g, t_g, g_g, r_g = ctx.query(sc.T, co, p)
+    out = r_c == 0
+    assert np.array_equal(r_g, r_c)
+    assert np.array_equal(s_g[out], s_c[out]) and np.array_equal(t_g[out], t_c[out]) and np.array_equal(g_g[out], g_c[out])
+    assert np.abs(s_g - s_c).max() <= 1e-9
+    ctx.set_points(sc.points)
+    orc.set_points(sc.points)
+    c0, gT0, gC0, _, _ = orc.cost_grad(sc.T, co)
+    c1, gT1, gC1 = ctx.cost_grad(sc.T, co)
+    assert abs(c1 - c0) <= 1e-12 * max(1.0, abs(c0)) and nrel(gC1, gC0) <= 1e-8 and gT_err(gT1, gT0, gC0) <= 1e-8
+
+
 def test_body_frame_offset_of_the_shape(oracle_mod):
     sc = scenes.make_scene("star", 8, 500, clearance=2.6)
     co = sc.coeffs_colmajor()
