@@ -385,6 +385,21 @@ def test_optimize_reduces_cost_and_final_point_agrees_with_oracle(oracle_mod):
         assert abs(st["final_cost"] - f1) <= 1e-9 * abs(f1)
 
 
+def test_replay_of_the_reference_lmbm_trace():
+    """tests/golden/lmbm_trace_star_400.npz holds iterates visited by the reference's OWN outer solver (the prebuilt LMBM
+    binary with its default parameters) while minimising the oracle's cost callback.  The CUDA callback must return the
+    same cost and gradient at each of them — so plugging svsdf_evaluate into lmbm_optimize retraces the reference run."""
+    G = np.load(os.path.join(HERE, "golden", "lmbm_trace_star_400.npz"))
+    opt = api.TrajOptimizer(str(G["shape"]), weight_p=float(G["weight_p"]), safety_hor=float(G["safety_hor"]), rho=float(G["rho"]))
+    opt.parallel_points = G["points"]
+    opt.setConditions(G["init_s"], G["final_s"], int(G["N"]))
+    assert G["xs"].shape[0] >= 30 and float(G["final_f"]) < 0.6 * float(G["fs"][0])  # LMBM made real progress
+    for x, f0, g0 in zip(G["xs"], G["fs"], G["gs"]):
+        f1, g1 = opt.costFunction(x)
+        assert abs(f1 - f0) <= 1e-11 * abs(f0), (f1, f0)
+        assert nrel(g1, g0) <= 1e-7, nrel(g1, g0)
+
+
 def test_progress_callback_can_cancel(scene2k):
     sc = scene2k
     opt = api.TrajOptimizer("star")
