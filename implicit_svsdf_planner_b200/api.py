@@ -41,6 +41,10 @@ class _Config(C.Structure):
         ("strict_fp", C.c_int),
         ("polygon_xy", dp),
         ("polygon_n", C.c_int),
+        ("mesh_vertices", dp),
+        ("mesh_nv", C.c_int),
+        ("mesh_faces", C.POINTER(C.c_int32)),
+        ("mesh_nf", C.c_int),
     ]
 
 
@@ -83,7 +87,7 @@ EXPORTED_SYMBOLS = [
     "svsdf_optimize", "svsdf_minco_forward", "svsdf_minco_propagate", "svsdf_forward_T", "svsdf_backward_T",
     "svsdf_shape_sdf", "svsdf_shape_grad1", "svsdf_cost_grad_device", "svsdf_kernel_launches",
     "svsdf_executed_evals", "svsdf_fp64_peak", "svsdf_device_ptr_points", "svsdf_lbfgs_minimize", "svsdf_last_kernel_ms", "svsdf_sincos", "svsdf_set_map", "svsdf_set_map_device",
-    "svsdf_extract_points", "svsdf_get_points",
+    "svsdf_extract_points", "svsdf_get_points", "svsdf_read_obj", "svsdf_free",
 ]
 
 
@@ -105,6 +109,8 @@ def lib():
     L.svsdf_last_error.restype = C.c_char_p
     L.svsdf_last_error.argtypes = [vp]
     L.svsdf_shape_id.argtypes = [C.c_char_p]
+    L.svsdf_read_obj.argtypes = [C.c_char_p, C.POINTER(dp), C.POINTER(C.c_int), C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int)]
+    L.svsdf_free.argtypes = [vp]
     L.svsdf_set_points.argtypes = [vp, dp, C.c_int64, C.c_int]
     L.svsdf_set_points_device.argtypes = [vp, vp, C.c_int64]
     L.svsdf_set_traj.argtypes = [vp, C.c_int, dp, dp]
@@ -218,11 +224,28 @@ def backward_T(T):
     return tau
 
 
+def read_obj(path: str):
+    """svsdf_read_obj: (V [nv, 3] float64, F [nf, 3] int32) of a Wavefront .obj (host code only, needs no GPU)."""
+    L = lib()
+    v, f = dp(), C.POINTER(C.c_int32)()
+    nv, nf = C.c_int(), C.c_int()
+    rc = L.svsdf_read_obj(os.fsencode(path), C.byref(v), C.byref(nv), C.byref(f), C.byref(nf))
+    if rc != 0:
+        raise SvsdfError(f"svsdf_read_obj({path!r}) failed with status {rc}")
+    try:
+        V = np.ctypeslib.as_array(v, shape=(nv.value, 3)).copy()
+        F = np.ctypeslib.as_array(f, shape=(nf.value, 3)).copy()
+    finally:
+        L.svsdf_free(C.cast(v, C.c_void_p))
+        L.svsdf_free(C.cast(f, C.c_void_p))
+    return V, F
+
+
 class Context:
     """Owns one svsdf_ctx (one GPU, one stream)."""
 
     def __init__(self, shape="star", poly_params=(0.0, 0.0, 0.0), weight_p=60.0, safety_hor=0.7, rho=3.8, device=0,
-                 strict_fp=True, polygon=None):
+                 strict_fp=True, polygon=None, mesh=None):
         L = lib()
         cfg = _Config()
         L.svsdf_default_config(C.byref(cfg))
@@ -236,6 +259,13 @@ class Context:
             self._poly = _f64(polygon).reshape(-1)
             cfg.polygon_xy = _p(self._poly)
             cfg.polygon_n = self._poly.size // 2
+        if mesh is not None:  # (V [nv, 3], F [nf, 3]): the triangle-mesh functor (getonlySDF_igl) replaces the registry shape
+            self._mesh_v = _f64(mesh[0]).reshape(-1, 3)
+            self._mesh_f = np.ascontiguousarray(mesh[1], dtype=np.int32).reshape(-1, 3)
+            cfg.mesh_vertices = _p(self._mesh_v)
+            cfg.mesh_nv = self._mesh_v.shape[0]
+            cfg.mesh_faces = self._mesh_f.ctypes.data_as(C.POINTER(C.c_int32))
+            cfg.mesh_nf = self._mesh_f.shape[0]
         h = C.c_void_p()
         rc = L.svsdf_create(C.byref(cfg), C.byref(h))
         if rc != 0 or not h:
@@ -445,8 +475,8 @@ class TrajOptimizer:
     """Mirror of the reference's TrajOptimizer for the back-end SVSDF cost (back_end_optimizer.hpp)."""
 
     def __init__(self, shape="star", poly_params=(0.0, 0.0, 0.0), weight_p=60.0, safety_hor=0.7, rho=3.8, device=0,
-                 strict_fp=True, polygon=None):
-        self.ctx = Context(shape, poly_params, weight_p, safety_hor, rho, device, strict_fp, polygon)
+                 strict_fp=True, polygon=None, mesh=None):
+        self.ctx = Context(shape, poly_params, weight_p, safety_hor, rho, device, strict_fp, polygon, mesh)
         self.sv_manager = SweptVolumeManager(self.ctx)
         self._points = None
         self.pieceN = 0

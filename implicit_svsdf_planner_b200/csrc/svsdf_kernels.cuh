@@ -581,7 +581,7 @@ __global__ void k_pose_table(double *blob) {
 #define SVSDF_OUTER_MIN_CTAS 3
 #endif
 template <int SHAPE, bool XFORM>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, SVSDF_OUTER_MIN_CTAS)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, (SHAPE == SH_MESH) ? 2 : SVSDF_OUTER_MIN_CTAS)
     k_outer(const __grid_constant__ KernelArgs A, const __grid_constant__ ShapeParams S) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -1052,6 +1052,7 @@ static cudaError_t dispatch(const KernelArgs &A, const ShapeParams &S, const Lau
         SVSDF_CASE(SH_CIRCLE)
 #undef SVSDF_CASE
         case SH_POLYGON: return launch_shape<SH_POLYGON, false>(A, S, cfg, N);
+        case SH_MESH: return launch_shape<SH_MESH, false>(A, S, cfg, N);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -1095,6 +1096,7 @@ cudaError_t query_occupancy(const ShapeParams &S, int N, int blob_doubles, int *
         SVSDF_CASE(SH_CIRCLE)
 #undef SVSDF_CASE
         case SH_POLYGON: return occ_shape<SH_POLYGON, false>(so, sg, occ_outer, occ_gsip);
+        case SH_MESH: return occ_shape<SH_MESH, false>(so, sg, occ_outer, occ_gsip);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -1162,6 +1164,7 @@ cudaError_t launch_shape_eval(const ShapeParams &S, const double *rel_xy, int64_
         SVSDF_CASE(SH_CIRCLE)
 #undef SVSDF_CASE
         case SH_POLYGON: return launch_shape_fn<SH_POLYGON, false>(S, rel_xy, n, out, grad, stream);
+        case SH_MESH: return launch_shape_fn<SH_MESH, false>(S, rel_xy, n, out, grad, stream);
         default: return cudaErrorInvalidValue;
     }
 }

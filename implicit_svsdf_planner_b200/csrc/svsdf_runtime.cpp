@@ -41,6 +41,7 @@ struct svsdf_ctx {
     int64_t launches = 0;
 
     // query points
+    double *d_mesh_tri = nullptr;  // SH_MESH: 9 doubles per face
     double *d_points = nullptr;  // packed xy
     bool own_points = true;
     int64_t P = 0;
@@ -142,6 +143,10 @@ void build_shape(const svsdf_config &cfg, ShapeParams &S) {
     S.has_xform = !(S.trans[0] == 0.0 && S.trans[1] == 0.0 && S.rot[0] == 1.0 && S.rot[1] == 0.0 && S.rot[2] == 0.0 &&
                     S.rot[3] == 1.0);
     S.radius = 1.0;
+    if (cfg.mesh_faces && cfg.mesh_nf > 0) {  // triangle-mesh functor requested: overrides the registry name
+        S.id = SH_MESH;
+        return;
+    }
     switch (S.id) {
         case SH_HORSESHOE: S.cst[0] = std::cos(20.5); S.cst[1] = std::sin(20.5); break;  // Shape.hpp:855
         case SH_PIE: S.cst[0] = std::cos(43.0); S.cst[1] = std::sin(43.0); break;        // :1235
@@ -477,6 +482,57 @@ void svsdf_default_config(svsdf_config *cfg) {
 
 int svsdf_shape_id(const char *name) { return shape_id_from_name(name); }
 
+// Wavefront .obj -> (V, F): `v x y z` and `f i[/..] j[/..] k[/..] ...` records (1-based or negative indices), polygons
+// fan-triangulated — what igl::read_triangle_mesh yields for the reference's shapes/*.obj (Shape.hpp:285).
+int svsdf_read_obj(const char *path, double **vertices_out, int *nv_out, int32_t **faces_out, int *nf_out) {
+    if (!path || !vertices_out || !nv_out || !faces_out || !nf_out) return SVSDF_ERR_INVALID;
+    *vertices_out = nullptr; *faces_out = nullptr; *nv_out = 0; *nf_out = 0;
+    std::FILE *fp = std::fopen(path, "r");
+    if (!fp) return SVSDF_ERR_INVALID;
+    std::vector<double> V;
+    std::vector<int32_t> F;
+    char line[4096];
+    bool bad = false;
+    while (std::fgets(line, sizeof(line), fp)) {
+        char *p = line;
+        while (*p == ' ' || *p == '\t') ++p;
+        if (p[0] == 'v' && (p[1] == ' ' || p[1] == '\t')) {
+            double x, y, z;
+            if (std::sscanf(p + 1, "%lf %lf %lf", &x, &y, &z) != 3) { bad = true; break; }
+            V.push_back(x); V.push_back(y); V.push_back(z);
+        } else if (p[0] == 'f' && (p[1] == ' ' || p[1] == '\t')) {
+            std::vector<int32_t> idx;
+            char *q = p + 1;
+            for (;;) {
+                while (*q == ' ' || *q == '\t') ++q;
+                if (*q == 0 || *q == '\n' || *q == '\r' || *q == '#') break;
+                char *end = nullptr;
+                long i = std::strtol(q, &end, 10);
+                if (end == q) { bad = true; break; }
+                const long nv = (long)(V.size() / 3);
+                idx.push_back((int32_t)(i > 0 ? i - 1 : nv + i));
+                q = end;
+                while (*q && *q != ' ' && *q != '\t' && *q != '\n' && *q != '\r') ++q;  // skip /vt/vn
+            }
+            if (bad) break;
+            for (size_t k = 1; k + 1 < idx.size(); ++k) { F.push_back(idx[0]); F.push_back(idx[k]); F.push_back(idx[k + 1]); }
+        }
+    }
+    std::fclose(fp);
+    const int nv = (int)(V.size() / 3), nf = (int)(F.size() / 3);
+    for (int32_t i : F)
+        if (i < 0 || i >= nv) bad = true;
+    if (bad || nv == 0 || nf == 0) return SVSDF_ERR_INVALID;
+    double *vo = (double *)std::malloc(V.size() * sizeof(double));
+    int32_t *fo = (int32_t *)std::malloc(F.size() * sizeof(int32_t));
+    if (!vo || !fo) { std::free(vo); std::free(fo); return SVSDF_ERR_INVALID; }
+    std::memcpy(vo, V.data(), V.size() * sizeof(double));
+    std::memcpy(fo, F.data(), F.size() * sizeof(int32_t));
+    *vertices_out = vo; *faces_out = fo; *nv_out = nv; *nf_out = nf;
+    return SVSDF_OK;
+}
+void svsdf_free(void *p) { std::free(p); }
+
 int svsdf_create(const svsdf_config *cfg, svsdf_ctx **out) {
     if (!cfg || !out) return SVSDF_ERR_INVALID;
     *out = nullptr;
@@ -484,6 +540,12 @@ int svsdf_create(const svsdf_config *cfg, svsdf_ctx **out) {
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return SVSDF_ERR_CUDA;  // no CPU fallback
     if (cfg->device < 0 || cfg->device >= ndev) return SVSDF_ERR_INVALID;
     if (cfg->polygon_xy && (cfg->polygon_n < 3 || cfg->polygon_n > kMaxPolyEdges)) return SVSDF_ERR_INVALID;
+    if (cfg->mesh_nf < 0 || cfg->mesh_nv < 0 || cfg->mesh_nf > kMaxMeshFaces) return SVSDF_ERR_INVALID;
+    if (cfg->mesh_nf > 0) {
+        if (!cfg->mesh_faces || !cfg->mesh_vertices || cfg->mesh_nv < 3) return SVSDF_ERR_INVALID;
+        for (int64_t k = 0; k < 3 * (int64_t)cfg->mesh_nf; ++k)
+            if (cfg->mesh_faces[k] < 0 || cfg->mesh_faces[k] >= cfg->mesh_nv) return SVSDF_ERR_INVALID;
+    }
     svsdf_ctx *ctx = new svsdf_ctx();
     ctx->cfg = *cfg;
     ctx->shape_name = cfg->shape ? cfg->shape : "";
@@ -521,6 +583,27 @@ int svsdf_create(const svsdf_config *cfg, svsdf_ctx **out) {
     cudaMemset(ctx->d_ticket, 0, sizeof(unsigned int));
     cudaMemset(ctx->d_n_inside, 0, sizeof(int));
     cudaMemset(ctx->d_eval_counter, 0, sizeof(unsigned long long));
+    ctx->cfg.mesh_vertices = nullptr;  // caller's arrays are not kept
+    ctx->cfg.mesh_faces = nullptr;
+    ctx->cfg.polygon_xy = nullptr;
+    if (ctx->shape.id == SH_MESH) {
+        // BasicShape ctor (Shape.hpp:285-309): every vertex becomes R v + trans, then the per-face soup
+        const ShapeParams &S = ctx->shape;
+        const double R[3][3] = {{S.rot[0], S.rot[1], 0.0}, {S.rot[2], S.rot[3], 0.0}, {0.0, 0.0, 1.0}};
+        const double tr[3] = {S.trans[0], S.trans[1], 0.0};
+        std::vector<double> tri((size_t)cfg->mesh_nf * 9);
+        for (int f = 0; f < cfg->mesh_nf; ++f)
+            for (int k = 0; k < 3; ++k) {
+                const double *v = cfg->mesh_vertices + 3 * (size_t)cfg->mesh_faces[3 * f + k];
+                for (int j = 0; j < 3; ++j)
+                    tri[(size_t)f * 9 + 3 * k + j] = ((v[0] * R[j][0] + v[1] * R[j][1]) + v[2] * R[j][2]) + tr[j];
+            }
+        if ((e = cudaMalloc(&ctx->d_mesh_tri, tri.size() * sizeof(double))) != cudaSuccess) return fail(e);
+        if ((e = cudaMemcpy(ctx->d_mesh_tri, tri.data(), tri.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e);
+        ctx->shape.mesh_tri = ctx->d_mesh_tri;
+        ctx->shape.mesh_nf = cfg->mesh_nf;
+        ctx->shape.has_xform = 0;
+    }
     *out = ctx;
     return SVSDF_OK;
 }
@@ -530,6 +613,7 @@ void svsdf_destroy(svsdf_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->own_points) cudaFree(ctx->d_points);
+    cudaFree(ctx->d_mesh_tri);
     cudaFree(ctx->d_flag); cudaFree(ctx->d_inside_tstar); cudaFree(ctx->d_inside_list);
     cudaFree(ctx->d_gsip_contrib); cudaFree(ctx->d_gsip_piece); cudaFree(ctx->d_n_inside);
     cudaFree(ctx->d_eval_counter); cudaFree(ctx->d_tot); cudaFree(ctx->d_ticket); cudaFree(ctx->d_blob); cudaFree(ctx->d_partials); cudaFree(ctx->d_out);

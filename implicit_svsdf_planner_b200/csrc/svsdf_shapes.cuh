@@ -345,11 +345,114 @@ struct ShapeFn<SH_POLYGON> {
     }
 };
 
+// Triangle-mesh functor — BasicShape::getonlySDF_igl (Shape.hpp:332-340): sdf = (1 - 2 w) * sqrt(d2).
+//   w  = winding number: the reference asks igl::fast_winding_number (fast_winding_number.cpp:439-457), a float BVH whose
+//        leaves evaluate the per-triangle solid angle exactly (UTsignedSolidAngleTri, FastWindingNumberForSoups.h:6071-6110)
+//        and whose far clusters approximate the same sum; here: the sum itself, in double, same per-triangle formula.
+//   d2 = squared distance to the closest triangle: igl::AABB::squared_distance (AABB.cpp:1130-1200) is a pruned minimum over
+//        point_simplex_squared_distance (point_simplex_squared_distance.cpp:43-116, Ericson's closest point); here the plain
+//        minimum over all faces — the same number.
+// The query is (qx, qy, 0): the path zeroes the z of both the pose and the point (sw_manager.hpp:767,
+// back_end_optimizer.hpp:791).  One pass over the faces does both sums; every lane of a warp reads the same face at the
+// same time (uniform __ldg -> one L1 transaction per operand).
+template <>
+struct ShapeFn<SH_MESH> {
+    static __device__ __forceinline__ double solid_angle(double ax, double ay, double az, double bx, double by, double bz,
+                                                         double cx, double cy, double cz) {
+        const double al = sqrt((ax * ax + ay * ay) + az * az);
+        const double bl = sqrt((bx * bx + by * by) + bz * bz);
+        const double cl = sqrt((cx * cx + cy * cy) + cz * cz);
+        if (al == 0 || bl == 0 || cl == 0) return 0.0;
+        const double ia = 1.0 / al, ib = 1.0 / bl, ic = 1.0 / cl;
+        ax *= ia; ay *= ia; az *= ia;
+        bx *= ib; by *= ib; bz *= ib;
+        cx *= ic; cy *= ic; cz *= ic;
+        const double ux = bx - ax, uy = by - ay, uz = bz - az;
+        const double vx = cx - ax, vy = cy - ay, vz = cz - az;
+        const double nx = uy * vz - uz * vy, ny = uz * vx - ux * vz, nz = ux * vy - uy * vx;
+        const double num = (ax * nx + ay * ny) + az * nz;
+        if (num == 0) return 0.0;
+        const double dab = (ax * bx + ay * by) + az * bz;
+        const double dac = (ax * cx + ay * cy) + az * cz;
+        const double dbc = (bx * cx + by * cy) + bz * cz;
+        const double den = ((1.0 + dab) + dac) + dbc;
+        return 2.0 * atan2_portable(num, den);
+    }
+    // squared distance from p to triangle (a, b, c); ap = p - a etc. are passed in (shared with the solid angle)
+    static __device__ __forceinline__ double sqr_distance(double ax, double ay, double az, double bx, double by, double bz,
+                                                          double cx, double cy, double cz, double px, double py, double pz) {
+        const double abx = bx - ax, aby = by - ay, abz = bz - az;
+        const double acx = cx - ax, acy = cy - ay, acz = cz - az;
+        const double apx = px - ax, apy = py - ay, apz = pz - az;
+        double qx = ax, qy = ay, qz = az;
+        const double d1 = (abx * apx + aby * apy) + abz * apz;
+        const double d2 = (acx * apx + acy * apy) + acz * apz;
+        if (!(d1 <= 0.0 && d2 <= 0.0)) {
+            const double bpx = px - bx, bpy = py - by, bpz = pz - bz;
+            const double d3 = (abx * bpx + aby * bpy) + abz * bpz;
+            const double d4 = (acx * bpx + acy * bpy) + acz * bpz;
+            if (d3 >= 0.0 && d4 <= d3) {
+                qx = bx; qy = by; qz = bz;
+            } else {
+                const double vc = d1 * d4 - d3 * d2;
+                const bool a_ne_b = (ax != bx) || (ay != by) || (az != bz);
+                if (a_ne_b && vc <= 0.0 && d1 >= 0.0 && d3 <= 0.0) {
+                    const double v = d1 / (d1 - d3);
+                    qx = ax + v * abx; qy = ay + v * aby; qz = az + v * abz;
+                } else {
+                    const double cpx = px - cx, cpy = py - cy, cpz = pz - cz;
+                    const double d5 = (abx * cpx + aby * cpy) + abz * cpz;
+                    const double d6 = (acx * cpx + acy * cpy) + acz * cpz;
+                    if (d6 >= 0.0 && d5 <= d6) {
+                        qx = cx; qy = cy; qz = cz;
+                    } else {
+                        const double vb = d5 * d2 - d1 * d6;
+                        if (vb <= 0.0 && d2 >= 0.0 && d6 <= 0.0) {
+                            const double w = d2 / (d2 - d6);
+                            qx = ax + w * acx; qy = ay + w * acy; qz = az + w * acz;
+                        } else {
+                            const double va = d3 * d6 - d5 * d4;
+                            if (va <= 0.0 && (d4 - d3) >= 0.0 && (d5 - d6) >= 0.0) {
+                                const double w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+                                qx = bx + w * (cx - bx); qy = by + w * (cy - by); qz = bz + w * (cz - bz);
+                            } else {
+                                const double denom = 1.0 / ((va + vb) + vc);
+                                const double v = vb * denom, w = vc * denom;
+                                qx = (ax + abx * v) + acx * w; qy = (ay + aby * v) + acy * w; qz = (az + abz * v) + acz * w;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        const double ex = px - qx, ey = py - qy, ez = pz - qz;
+        return (ex * ex + ey * ey) + ez * ez;
+    }
+    static __device__ __forceinline__ double sdf(const ShapeParams &S, double qx, double qy) {
+        const double PI = 3.14159265358979323846;
+        const double qz = 0.0;
+        double omega = 0.0, best = __longlong_as_double(0x7ff0000000000000LL);
+        const double *t = S.mesh_tri;
+#pragma unroll 1
+        for (int f = 0; f < S.mesh_nf; ++f, t += 9) {
+            const double ax = __ldg(t), ay = __ldg(t + 1), az = __ldg(t + 2);
+            const double bx = __ldg(t + 3), by = __ldg(t + 4), bz = __ldg(t + 5);
+            const double cx = __ldg(t + 6), cy = __ldg(t + 7), cz = __ldg(t + 8);
+            omega += solid_angle(ax - qx, ay - qy, az - qz, bx - qx, by - qy, bz - qz, cx - qx, cy - qy, cz - qz);
+            const double d = sqr_distance(ax, ay, az, bx, by, bz, cx, cy, cz, qx, qy, qz);
+            if (d < best) best = d;
+        }
+        const double w = omega / (4.0 * PI);
+        const double s = 1. - 2. * w;
+        return s * sqrt(best);
+    }
+};
+
 // ((pos_rel - trans) * Rotate).head(2): row-vector times matrix (Shape.hpp:281-294 and e.g. :586).
 // With has_xform == 0 (trans = 0, Rotate = I) the product is the identity bit-for-bit and is skipped.
 template <int SHAPE, bool XFORM>
 __device__ __forceinline__ double shape_sdf(const ShapeParams &S, double rx, double ry) {
-    if (SHAPE != SH_POLYGON && XFORM) {
+    if (SHAPE != SH_POLYGON && SHAPE != SH_MESH && XFORM) {
         double v0 = rx - S.trans[0], v1 = ry - S.trans[1];
         rx = v0 * S.rot[0] + v1 * S.rot[2];
         ry = v0 * S.rot[1] + v1 * S.rot[3];

@@ -32,10 +32,12 @@ enum ShapeId : int {
     SH_UNEVENCAPSULE,
     SH_CIRCLE,
     SH_POLYGON,
+    SH_MESH,   // triangle-mesh functor, BasicShape::getonlySDF_igl (Shape.hpp:332-340); selected by svsdf_config.mesh_*
     SH_COUNT
 };
 
 constexpr int kMaxPolyEdges = 64;
+constexpr int kMaxMeshFaces = 1 << 20;  // SH_MESH: faces of the triangle soup (brute-force functor; see svsdf_shapes.cuh)
 constexpr int kMaxPieces = 64;       // pieces per trajectory supported by the per-warp accumulators
 constexpr int kWarpsPerBlock = 8;    // k_outer block = 256 threads
 constexpr int kGsipWarps = 22;       // k_gsip block = 704 threads: one warp per ring sample (<= 21 per round)
@@ -54,6 +56,9 @@ struct ShapeParams {
     int poly_n;         // Polygon edge count
     int pad_;
     double poly_sx[kMaxPolyEdges], poly_sy[kMaxPolyEdges], poly_ex[kMaxPolyEdges], poly_ey[kMaxPolyEdges];
+    const double *mesh_tri;  // SH_MESH: device pointer, 9 doubles per face (a, b, c), vertices already R v + trans (Shape.hpp:296-302)
+    int mesh_nf;
+    int pad2_;
 };
 
 // Trajectory blob: one contiguous, 16-byte aligned buffer that the kernels pull into shared memory with a

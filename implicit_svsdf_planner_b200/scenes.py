@@ -228,3 +228,72 @@ def make_batch_problems(n_problems: int, seed: int = SEED_BATCH, extent=(2.0, 58
     short = L < 25.0
     sg[short, 2:] = sg[short, :2] + d[short] / np.maximum(L[short, None], 1e-9) * 25.0
     return sg
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Triangle meshes for the mesh-SDF functor (BasicShape::getonlySDF_igl, Shape.hpp:332-340)
+# ---------------------------------------------------------------------------------------------------------------------
+def load_obj(path: str):
+    """Minimal Wavefront .obj reader (what igl::read_triangle_mesh does for the reference's shapes/*.obj, Shape.hpp:285):
+    `v x y z` and `f i[/..] j[/..] k[/..] ...` records, 1-based or negative indices, polygons fan-triangulated.
+    Returns (V [nv, 3] float64, F [nf, 3] int32)."""
+    V, F = [], []
+    with open(path, "r") as fh:
+        for line in fh:
+            tok = line.split()
+            if not tok:
+                continue
+            if tok[0] == "v":
+                V.append([float(tok[1]), float(tok[2]), float(tok[3])])
+            elif tok[0] == "f":
+                idx = []
+                for t in tok[1:]:
+                    i = int(t.split("/")[0])
+                    idx.append(i - 1 if i > 0 else len(V) + i)
+                for k in range(1, len(idx) - 1):
+                    F.append([idx[0], idx[k], idx[k + 1]])
+    return np.asarray(V, dtype=np.float64).reshape(-1, 3), np.asarray(F, dtype=np.int32).reshape(-1, 3)
+
+
+def extrude_outline(outline_xy: np.ndarray, half_height: float = 0.49, center=(0.0, 0.0)):
+    """Closed, outward-oriented slab mesh of a 2-D outline that is star-shaped about `center` (counter-clockwise
+    vertices): side quads split into two triangles, caps fanned from the centre — the same kind of thin extrusion the
+    reference's shapes/*.obj are, generated here so that GPU tests need no reference file.
+    Returns (V, F)."""
+    o = np.asarray(outline_xy, dtype=np.float64).reshape(-1, 2)
+    n = o.shape[0]
+    h = float(half_height)
+    V = np.zeros((2 * n + 2, 3))
+    V[:n, :2] = o
+    V[:n, 2] = -h
+    V[n : 2 * n, :2] = o
+    V[n : 2 * n, 2] = h
+    V[2 * n] = [center[0], center[1], -h]
+    V[2 * n + 1] = [center[0], center[1], h]
+    F = []
+    for i in range(n):
+        j = (i + 1) % n
+        F.append([i, j, n + j])          # side, outward for a CCW outline
+        F.append([i, n + j, n + i])
+        F.append([2 * n, j, i])          # bottom cap (normal -z)
+        F.append([2 * n + 1, n + i, n + j])  # top cap (normal +z)
+    return V, np.asarray(F, dtype=np.int32)
+
+
+def star_outline(r_out: float = 2.8, r_in: float = 1.4, tips: int = 5, n_per_edge: int = 1) -> np.ndarray:
+    """Counter-clockwise outline of a `tips`-pointed star (first tip on +y), optionally with extra vertices per edge: a
+    synthetic robot outline for the mesh-SDF functor (roughly the reference's star, outer radius 2.8; not its level set)."""
+    pts = []
+    for k in range(2 * tips):
+        ang = np.pi / 2 + k * np.pi / tips
+        rad = r_out if k % 2 == 0 else r_in
+        pts.append([rad * np.cos(ang), rad * np.sin(ang)])
+    pts = np.asarray(pts)
+    if n_per_edge > 1:
+        out = []
+        for i in range(2 * tips):
+            a, b = pts[i], pts[(i + 1) % (2 * tips)]
+            for q in range(n_per_edge):
+                out.append(a + (b - a) * (q / n_per_edge))
+        pts = np.asarray(out)
+    return pts

@@ -62,6 +62,14 @@ typedef struct {
                                  only within the reference's ~1e-5 contraction noise floor) */
     const double *polygon_xy; /* optional polygon vertices (x0,y0,x1,y1,...) for the fallback shape */
     int polygon_n;            /* number of vertices (<= 64) */
+    /* Optional triangle mesh.  When mesh_nf > 0 the robot shape is the reference's mesh functor
+       BasicShape::getonlySDF_igl (utils/Shape.hpp:332-340: (1 - 2 * winding number) * distance to the mesh, gradient by
+       the same central differences, :35-53) instead of a registry shape; `shape` is then ignored.  poly_params are
+       applied to the vertices (R v + trans, Shape.hpp:285-302) at creation; the arrays are copied. */
+    const double *mesh_vertices; /* mesh_nv x 3, row-major (x, y, z) */
+    int mesh_nv;
+    const int32_t *mesh_faces;   /* mesh_nf x 3, 0-based vertex indices */
+    int mesh_nf;
 } svsdf_config;
 
 /* Fill a config with the reference's star.yaml defaults. */
@@ -72,6 +80,10 @@ void svsdf_destroy(svsdf_ctx *ctx);
 const char *svsdf_last_error(const svsdf_ctx *ctx);
 /* Shape registry lookup: returns the internal id (>= 0); unknown names map to the Polygon fallback id. */
 int svsdf_shape_id(const char *name);
+/* Read a Wavefront .obj (what igl::read_triangle_mesh does for yaml `inputdata`, utils/Shape.hpp:284-285): vertices
+   (nv x 3 doubles) and fan-triangulated faces (nf x 3, 0-based), malloc'ed; release both with svsdf_free. */
+int svsdf_read_obj(const char *path, double **vertices_out, int *nv_out, int32_t **faces_out, int *nf_out);
+void svsdf_free(void *p);
 
 /* R6: parallel_points.  pts: P rows of `stride` doubles (x, y, [z ...]); z is ignored like the reference
  * does (back_end_optimizer.hpp:791).  Copies to device memory (host -> device inside this call). */

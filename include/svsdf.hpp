@@ -38,6 +38,11 @@ struct Config {                       // yaml keys of src/plan_manager/config/<s
     int device = 0;
     bool strict_fp = true;
     std::vector<double> polygon_xy;  // vertices for the Polygon fallback (empty -> the reference's 12 x 0.2 rectangle)
+    // Triangle-mesh functor (BasicShape::getonlySDF_igl, Shape.hpp:332-340) instead of a registry shape: either give the mesh
+    // directly, or set mesh_sdf = true and let the constructor read `inputdata` as a .obj file path (Shape.hpp:284-285).
+    bool mesh_sdf = false;
+    std::vector<double> mesh_vertices;  // nv x 3
+    std::vector<int32_t> mesh_faces;    // nf x 3, 0-based
 
     // registry key = basename of inputdata without extension (sw_manager.hpp:350-354)
     std::string shapetype() const {
@@ -61,7 +66,19 @@ struct Ctx {
         cfg.weight_p = c.weight_p; cfg.safety_hor = c.safety_hor; cfg.rho = c.rho;
         cfg.device = c.device; cfg.strict_fp = c.strict_fp ? 1 : 0;
         if (c.polygon_xy.size() >= 6) { cfg.polygon_xy = c.polygon_xy.data(); cfg.polygon_n = (int)(c.polygon_xy.size() / 2); }
-        if (svsdf_create(&cfg, &h) != SVSDF_OK || !h) throw std::runtime_error("svsdf_create failed (no sm_100 CUDA device? there is no CPU fallback)");
+        double *fv = nullptr; int32_t *ff = nullptr;
+        if (!c.mesh_faces.empty()) {
+            cfg.mesh_vertices = c.mesh_vertices.data(); cfg.mesh_nv = (int)(c.mesh_vertices.size() / 3);
+            cfg.mesh_faces = c.mesh_faces.data(); cfg.mesh_nf = (int)(c.mesh_faces.size() / 3);
+        } else if (c.mesh_sdf) {
+            int nv = 0, nf = 0;
+            if (svsdf_read_obj(c.inputdata.c_str(), &fv, &nv, &ff, &nf) != SVSDF_OK) throw std::runtime_error("cannot read mesh " + c.inputdata);
+            cfg.mesh_vertices = fv; cfg.mesh_nv = nv; cfg.mesh_faces = ff; cfg.mesh_nf = nf;
+        }
+        const int rc_create = svsdf_create(&cfg, &h);
+        svsdf_free(fv); svsdf_free(ff);
+        if (rc_create != SVSDF_OK) h = nullptr;
+        if (!h) throw std::runtime_error("svsdf_create failed (no sm_100 CUDA device? there is no CPU fallback)");
     }
     ~Ctx() { svsdf_destroy(h); }
     Ctx(const Ctx &) = delete;

@@ -49,6 +49,38 @@ void orc_atan2(int64_t n, const double *y, const double *x, double *out) {
     for (int64_t i = 0; i < n; ++i) out[i] = psc::atan2(y[i], x[i]);
 }
 
+// ---- triangle-mesh functor (BasicShape::getonlySDF_igl, Shape.hpp:332-340); V: nv x 3 row-major, F: nf x 3 ----
+static Shape make_mesh_shape(const double *poly_params, const double *V, int nv, const int *F, int nf) {
+    Shape S;
+    S.id = SH_MESH;
+    if (poly_params) S.set_poly_params(poly_params[0], poly_params[1], poly_params[2]);
+    S.set_mesh(V, nv, F, nf);
+    return S;
+}
+// what: 0 sdf, 1 winding number, 2 squared distance, 3 FD gradient (out has 3 doubles per point)
+void orc_mesh_eval(const double *poly_params, const double *V, int nv, const int *F, int nf, int what, int64_t n,
+                   const double *rel, double *out) {
+    Shape S = make_mesh_shape(poly_params, V, nv, F, nf);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        const double x = rel[3 * i], y = rel[3 * i + 1], z = rel[3 * i + 2];
+        if (what == 0) out[i] = shape_sdf(S, x, y, z);
+        else if (what == 1) out[i] = mesh_winding(S, x, y, z);
+        else if (what == 2) out[i] = mesh_sqr_distance(S, x, y, z);
+        else shape_grad1(S, x, y, z, out + 3 * i);
+    }
+}
+void *orc_create_mesh(const double *poly_params, const double *V, int nv, const int *F, int nf, double weight_p,
+                      double safety_hor, double rho, int threads) {
+    TrajOptimizerOracle *o = new TrajOptimizerOracle();
+    o->sv.shape = make_mesh_shape(poly_params, V, nv, F, nf);
+    o->cp.weight_p = weight_p;
+    o->cp.safety_hor = safety_hor;
+    o->cp.threads = threads > 0 ? threads : 1;
+    o->rho = rho;
+    return o;
+}
+
 void *orc_create(const char *name, const double *poly_params, const double *poly_xy, int poly_n, double weight_p,
                  double safety_hor, double rho, int threads) {
     TrajOptimizerOracle *o = new TrajOptimizerOracle();

@@ -76,6 +76,9 @@ def lib(variant: str = "default"):
         L.orc_get_coeffs.argtypes = [C.c_void_p, dp, dp]
         L.orc_lbfgs.restype = C.c_int
         L.orc_lbfgs.argtypes = [C.c_void_p, dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_double, dp]
+        L.orc_mesh_eval.argtypes = [dp, dp, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int64, dp, dp]
+        L.orc_create_mesh.restype = C.c_void_p
+        L.orc_create_mesh.argtypes = [dp, dp, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]
         L.orc_max_threads.restype = C.c_int
         L.orc_num_procs.restype = C.c_int
         _libs[variant] = L
@@ -105,6 +108,23 @@ def shape_grad1(name, rel, poly_params=(0.0, 0.0, 0.0), polygon=None):
     pp = _f64(poly_params)
     poly = _f64(polygon).reshape(-1) if polygon is not None else None
     lib().orc_shape_grad1(name.encode(), _p(pp), _p(poly), 0 if poly is None else poly.size // 2, rel.shape[0], _p(rel), _p(out))
+    return out
+
+
+def _mesh_args(mesh):
+    V = _f64(mesh[0]).reshape(-1, 3)
+    F = np.ascontiguousarray(mesh[1], dtype=np.int32).reshape(-1, 3)
+    return V, F
+
+
+def mesh_eval(mesh, rel, what="sdf", poly_params=(0.0, 0.0, 0.0)):
+    """BasicShape::getonlySDF_igl restatement over body-frame points; what in sdf | winding | sqr_distance | grad1."""
+    V, F = _mesh_args(mesh)
+    rel = _f64(rel).reshape(-1, 3)
+    code = {"sdf": 0, "winding": 1, "sqr_distance": 2, "grad1": 3}[what]
+    out = np.empty((rel.shape[0], 3)) if code == 3 else np.empty(rel.shape[0])
+    pp = _f64(poly_params)
+    lib().orc_mesh_eval(_p(pp), _p(V), V.shape[0], F.ctypes.data_as(C.c_void_p), F.shape[0], code, rel.shape[0], _p(rel), _p(out))
     return out
 
 
@@ -141,10 +161,15 @@ class Oracle:
     """Handle on the CPU restatement of TrajOptimizer + SweptVolumeManager for one shape."""
 
     def __init__(self, shape="star", poly_params=(0.0, 0.0, 0.0), weight_p=60.0, safety_hor=0.7, rho=3.8, threads=1, polygon=None,
-                 variant="default"):
+                 variant="default", mesh=None):
         pp = _f64(poly_params)
         poly = _f64(polygon).reshape(-1) if polygon is not None else None
         self.L = lib(variant)
+        self.N = 0
+        if mesh is not None:  # (V, F): the triangle-mesh functor (getonlySDF_igl) instead of a registry shape
+            V, F = _mesh_args(mesh)
+            self.h = self.L.orc_create_mesh(_p(pp), _p(V), V.shape[0], F.ctypes.data_as(C.c_void_p), F.shape[0], weight_p, safety_hor, rho, threads)
+            return
         self.h = self.L.orc_create(shape.encode(), _p(pp), _p(poly), 0 if poly is None else poly.size // 2, weight_p, safety_hor, rho, threads)
         self.N = 0
 

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -37,6 +38,7 @@ enum ShapeId {
     SH_UNEVENCAPSULE,
     SH_CIRCLE,
     SH_POLYGON,  // fallback for unknown names: sw_manager.hpp:363-372
+    SH_MESH,     // triangle-mesh functor BasicShape::getonlySDF_igl (Shape.hpp:332-340), selected explicitly
     SH_COUNT
 };
 
@@ -60,6 +62,9 @@ struct Shape {
     // polygon fallback (edges start->end), Shape.hpp:1429-1446
     std::vector<double> poly_sx, poly_sy, poly_ex, poly_ey;
     double circle_radius = 1.0;
+    // triangle soup of the mesh functor: 9 doubles per face (a, b, c), vertices already moved by the base-class
+    // constructor's R v + trans (Shape.hpp:287-302)
+    std::vector<double> mesh_tri;
 
     void set_poly_params(double p0, double p1, double p2_deg) {
         const double PI = 3.14159265358979323846;  // Shape.hpp:31
@@ -83,6 +88,18 @@ struct Shape {
             poly_ex.push_back(xy[2 * j]);
             poly_ey.push_back(xy[2 * j + 1]);
         }
+    }
+    // BasicShape ctor, Shape.hpp:285-309: V <- hnormalized(homogeneous(V) * Trans^T), i.e. R v + trans per vertex;
+    // V: nv x 3 row-major, F: nf x 3 (0-based)
+    void set_mesh(const double *V, int nv, const int *F, int nf) {
+        mesh_tri.assign((size_t)nf * 9, 0.0);
+        for (int f = 0; f < nf; ++f)
+            for (int k = 0; k < 3; ++k) {
+                const double *v = V + 3 * (size_t)F[3 * f + k];
+                (void)nv;
+                for (int j = 0; j < 3; ++j)
+                    mesh_tri[(size_t)f * 9 + 3 * k + j] = ((v[0] * Rot[j][0] + v[1] * Rot[j][1]) + v[2] * Rot[j][2]) + trans[j];
+            }
     }
     void set_default_rect() {  // sw_manager.hpp:365-369
         const double rect[8] = {6, -0.1, 6, 0.1, -6, 0.1, -6, -0.1};
@@ -353,9 +370,118 @@ inline double sd_polygon(const Shape &S, double qx, double qy) {
     return (H.rs % 2 == 0) ? H.dis : -H.dis;
 }
 
+// ---- Triangle-mesh functor: BasicShape::getonlySDF_igl, Shape.hpp:332-340 ----
+//   sdf = (1 - 2 w) * sqrt(d2),  w = winding number of the mesh about the point, d2 = squared distance to the mesh.
+// The reference gets w from igl::fast_winding_number (fast_winding_number.cpp:439-457 -> HDK UT_SolidAngle<float,float>,
+// a float BVH whose leaves evaluate the exact per-triangle solid angle, UTsignedSolidAngleTri
+// FastWindingNumberForSoups.h:6071-6110, and whose far clusters use an order-2 Taylor approximation of the same sum) and
+// d2 from igl::AABB::squared_distance (AABB.cpp:1130-1200 -> point_simplex_squared_distance.cpp:43-116, Ericson's
+// closest point on a triangle).  Restated here as the quantities those trees approximate/accelerate: the exact
+// double-precision sum of per-triangle solid angles (same formula as the reference's leaf evaluation) and the minimum of
+// the per-triangle squared distances (the same number the AABB tree returns — pruning does not change a minimum).
+// tests/test_oracle_mesh.py measures the difference to the reference's own float FWN code compiled into oracle/_ref.
+inline double tri_solid_angle(const double *t, double qx, double qy, double qz) {
+    double ax = t[0] - qx, ay = t[1] - qy, az = t[2] - qz;
+    double bx = t[3] - qx, by = t[4] - qy, bz = t[5] - qz;
+    double cx = t[6] - qx, cy = t[7] - qy, cz = t[8] - qz;
+    const double al = std::sqrt((ax * ax + ay * ay) + az * az);
+    const double bl = std::sqrt((bx * bx + by * by) + bz * bz);
+    const double cl = std::sqrt((cx * cx + cy * cy) + cz * cz);
+    if (al == 0 || bl == 0 || cl == 0) return 0.0;
+    const double ia = 1.0 / al, ib = 1.0 / bl, ic = 1.0 / cl;
+    ax *= ia; ay *= ia; az *= ia;
+    bx *= ib; by *= ib; bz *= ib;
+    cx *= ic; cy *= ic; cz *= ic;
+    const double ux = bx - ax, uy = by - ay, uz = bz - az;
+    const double vx = cx - ax, vy = cy - ay, vz = cz - az;
+    const double nx = uy * vz - uz * vy, ny = uz * vx - ux * vz, nz = ux * vy - uy * vx;
+    const double num = (ax * nx + ay * ny) + az * nz;
+    if (num == 0) return 0.0;
+    const double dab = (ax * bx + ay * by) + az * bz;
+    const double dac = (ax * cx + ay * cy) + az * cz;
+    const double dbc = (bx * cx + by * cy) + bz * cz;
+    const double den = ((1.0 + dab) + dac) + dbc;
+    return 2.0 * psc::atan2(num, den);
+}
+inline double tri_sqr_distance(const double *t, double px, double py, double pz) {
+    // ClosestBaryPtPointTriangle (Real-Time Collision Detection ch. 5; point_simplex_squared_distance.cpp:43-106)
+    const double ax = t[0], ay = t[1], az = t[2], bx = t[3], by = t[4], bz = t[5], cx = t[6], cy = t[7], cz = t[8];
+    const double abx = bx - ax, aby = by - ay, abz = bz - az;
+    const double acx = cx - ax, acy = cy - ay, acz = cz - az;
+    const double apx = px - ax, apy = py - ay, apz = pz - az;
+    double qx, qy, qz;  // closest point
+    const double d1 = (abx * apx + aby * apy) + abz * apz;
+    const double d2 = (acx * apx + acy * apy) + acz * apz;
+    bool done = false;
+    if (d1 <= 0.0 && d2 <= 0.0) { qx = ax; qy = ay; qz = az; done = true; }
+    double d3 = 0, d4 = 0, d5 = 0, d6 = 0, vc = 0, vb = 0;
+    if (!done) {
+        const double bpx = px - bx, bpy = py - by, bpz = pz - bz;
+        d3 = (abx * bpx + aby * bpy) + abz * bpz;
+        d4 = (acx * bpx + acy * bpy) + acz * bpz;
+        if (d3 >= 0.0 && d4 <= d3) { qx = bx; qy = by; qz = bz; done = true; }
+    }
+    if (!done) {
+        vc = d1 * d4 - d3 * d2;
+        const bool a_ne_b = (ax != bx) || (ay != by) || (az != bz);
+        if (a_ne_b && vc <= 0.0 && d1 >= 0.0 && d3 <= 0.0) {
+            const double v = d1 / (d1 - d3);
+            qx = ax + v * abx; qy = ay + v * aby; qz = az + v * abz; done = true;
+        }
+    }
+    if (!done) {
+        const double cpx = px - cx, cpy = py - cy, cpz = pz - cz;
+        d5 = (abx * cpx + aby * cpy) + abz * cpz;
+        d6 = (acx * cpx + acy * cpy) + acz * cpz;
+        if (d6 >= 0.0 && d5 <= d6) { qx = cx; qy = cy; qz = cz; done = true; }
+    }
+    if (!done) {
+        vb = d5 * d2 - d1 * d6;
+        if (vb <= 0.0 && d2 >= 0.0 && d6 <= 0.0) {
+            const double w = d2 / (d2 - d6);
+            qx = ax + w * acx; qy = ay + w * acy; qz = az + w * acz; done = true;
+        }
+    }
+    if (!done) {
+        const double va = d3 * d6 - d5 * d4;
+        if (va <= 0.0 && (d4 - d3) >= 0.0 && (d5 - d6) >= 0.0) {
+            const double w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+            qx = bx + w * (cx - bx); qy = by + w * (cy - by); qz = bz + w * (cz - bz);
+        } else {
+            const double denom = 1.0 / ((va + vb) + vc);
+            const double v = vb * denom, w = vc * denom;
+            qx = (ax + abx * v) + acx * w; qy = (ay + aby * v) + acy * w; qz = (az + abz * v) + acz * w;
+        }
+    }
+    const double ex = px - qx, ey = py - qy, ez = pz - qz;
+    return (ex * ex + ey * ey) + ez * ez;
+}
+inline double mesh_winding(const Shape &S, double qx, double qy, double qz) {
+    const double PI = 3.14159265358979323846;
+    double omega = 0.0;
+    const size_t nf = S.mesh_tri.size() / 9;
+    for (size_t f = 0; f < nf; ++f) omega += tri_solid_angle(&S.mesh_tri[9 * f], qx, qy, qz);
+    return omega / (4.0 * PI);  // fast_winding_number.cpp:453
+}
+inline double mesh_sqr_distance(const Shape &S, double qx, double qy, double qz) {
+    double best = std::numeric_limits<double>::infinity();
+    const size_t nf = S.mesh_tri.size() / 9;
+    for (size_t f = 0; f < nf; ++f) {
+        const double d = tri_sqr_distance(&S.mesh_tri[9 * f], qx, qy, qz);
+        if (d < best) best = d;
+    }
+    return best;
+}
+inline double sd_mesh(const Shape &S, double qx, double qy, double qz) {
+    const double w = mesh_winding(S, qx, qy, qz);
+    const double s = 1. - 2. * w;
+    return s * std::sqrt(mesh_sqr_distance(S, qx, qy, qz));
+}
+
 // BasicShape::getonlySDF(pos_rel) dispatch (virtual call in the reference, Shape.hpp:266)
 inline double shape_sdf(const Shape &S, double rx, double ry, double rz) {
     if (S.id == SH_POLYGON) return sd_polygon(S, rx, ry);  // ignores trans/Rotate (:1451)
+    if (S.id == SH_MESH) return sd_mesh(S, rx, ry, rz);    // the vertices carry the transform (:296-302)
     double px, py;
     pretransform(S, rx, ry, rz, px, py);
     switch (S.id) {

@@ -117,6 +117,9 @@ struct SweptVolume {
         double yaw = xt[2];
         double s, c;
         psc::sincos(yaw, s, c);
+        // the mesh functor goes through getSDFAtTimeStamp_igl (:760-777), which zeroes the pose's third component (the
+        // yaw) before posEva2Rel (`xt(2)=0`, :767); the analytic path leaves it in (its functors ignore z)
+        if (shape.id == SH_MESH) xt[2] = 0;
         double d0 = p[0] - xt[0], d1 = p[1] - xt[1], d2 = p[2] - xt[2];
         rel[0] = c * d0 + s * d1 + 0.0 * d2;
         rel[1] = -s * d0 + c * d1 + 0.0 * d2;

@@ -3,6 +3,8 @@
   config 1: star, N=8, 2k points        (parity scene; GPU vs CPU oracle on all points)
   config 2: star, N=8, 200k points      (bench.py's workload; here: cost+grad and a full L-BFGS run, GPU and CPU)
   config 3: sdHorseshoe, N=16, 500k points
+  config 4m: the reference's shapes/star.obj (152 v / 300 f, tests/golden/fwn_ref.npz) through the triangle-mesh functor
+            (BasicShape::getonlySDF_igl restated exactly), N=16, 500k
   config 4: mesh shape: outline of the reference's shapes/star.obj (40 vertices) through the Polygon fallback functor (what this
             release of the reference uses for non-analytic shapes; the libigl path is unreachable there), N=16, 500k
 """
@@ -22,10 +24,10 @@ def star_obj_polygon():
     return xy[np.argsort(np.arctan2(xy[:, 1], xy[:, 0]))].reshape(-1)
 
 
-def run(name, shape, N, P, clearance, cpu_points, lbfgs_iters=60, scene_shape=None, polygon=None):
+def run(name, shape, N, P, clearance, cpu_points, lbfgs_iters=60, scene_shape=None, polygon=None, mesh=None):
     sc = scenes.make_scene(scene_shape or shape, N, P, clearance=clearance)
     co = sc.coeffs_colmajor()
-    ctx = api.Context(shape, weight_p=sc.weight_p, safety_hor=sc.safety_hor, rho=sc.rho, polygon=polygon)
+    ctx = api.Context(shape, weight_p=sc.weight_p, safety_hor=sc.safety_hor, rho=sc.rho, polygon=polygon, mesh=mesh)
     ctx.set_points(sc.points)
     ctx.cost_grad_device(sc.T, co, repeats=2, fetch=False)
     ms, out = ctx.cost_grad_device(sc.T, co, repeats=5)
@@ -37,16 +39,16 @@ def run(name, shape, N, P, clearance, cpu_points, lbfgs_iters=60, scene_shape=No
     nproc = O.num_procs()
     best = None
     for th in sorted({nproc, max(1, nproc // 2), max(1, nproc // 4), int(1.5 * nproc)}):
-        orc = O.Oracle(shape, weight_p=sc.weight_p, safety_hor=sc.safety_hor, rho=sc.rho, threads=th, variant="glibc", polygon=polygon)
+        orc = O.Oracle(shape, weight_p=sc.weight_p, safety_hor=sc.safety_hor, rho=sc.rho, threads=th, variant="glibc", polygon=polygon, mesh=mesh)
         orc.set_points(sub)
         sec, _ = orc.time_cost_grad(sc.T, co, warm=1, reps=2)
         if best is None or sec < best[0]: best = (sec, th)
     cpu_pts_s = sub.shape[0] / best[0]
     # parity on the sample: strict GPU vs default oracle (bitwise per point), cost/grad
-    orc = O.Oracle(shape, weight_p=sc.weight_p, safety_hor=sc.safety_hor, rho=sc.rho, threads=best[1], polygon=polygon)
+    orc = O.Oracle(shape, weight_p=sc.weight_p, safety_hor=sc.safety_hor, rho=sc.rho, threads=best[1], polygon=polygon, mesh=mesh)
     orc.set_points(sub)
     c0, gT0, gC0, _, inside = orc.cost_grad(sc.T, co)
-    ctx2 = api.Context(shape, weight_p=sc.weight_p, safety_hor=sc.safety_hor, rho=sc.rho, polygon=polygon)
+    ctx2 = api.Context(shape, weight_p=sc.weight_p, safety_hor=sc.safety_hor, rho=sc.rho, polygon=polygon, mesh=mesh)
     ctx2.set_points(sub)
     c1, gT1, gC1 = ctx2.cost_grad(sc.T, co)
     rec = dict(config=name, shape=shape, N=N, P=P, gpu_ms_per_eval=ms, gpu_pts_per_s=P / ms * 1e3, kernel_ms=km,
@@ -71,4 +73,9 @@ if __name__ == "__main__":
     if "1" in which: run("1", "star", 8, 2000, 2.75, 2000)
     if "2" in which: run("2", "star", 8, 200_000, 2.75, 50_000)
     if "3" in which: run("3", "sdHorseshoe", 16, 500_000, 2.15, 50_000)
+    if "4m" in which:  # the same mesh through the triangle-mesh functor (getonlySDF_igl restated exactly)
+        g = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "fwn_ref.npz"))
+        P4 = int(os.environ.get("SVSDF_MESH_P", "500000"))
+        run("4m", "star_obj_mesh_sdf", 16, P4, 2.75, 3000, lbfgs_iters=int(os.environ.get("SVSDF_MESH_LBFGS", "4")), scene_shape="sdHorseshoe",
+            mesh=(g["star_V"], g["star_F"]))
     if "4" in which: run("4", "star_obj_outline_polygon", 16, 500_000, 2.75, 25_000, scene_shape="sdHorseshoe", polygon=star_obj_polygon())
