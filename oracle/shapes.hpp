@@ -3,8 +3,9 @@
 // Plain-C++ (no Eigen) restatement of the reference's 2-D robot-shape SDF functors
 //   /root/reference/src/utils/include/utils/Shape.hpp
 // one function per shape class, same operation order as the reference source, double precision.
-// PARITY UNPINNED: the reference ships no golden vectors / known-answer tests for these functions
-// and cannot be compiled in this environment (needs Eigen/ROS/PCL/libigl); see DESIGN.md §oracle.
+// PARITY UNPINNED for the analytic functors: the reference ships no golden vectors / known-answer tests for these
+// functions and Shape.hpp cannot be compiled in this environment (needs Eigen/ROS/PCL); see DESIGN.md §4.  The mesh
+// functor's winding number IS pinned against the reference's own compiled code (oracle/_ref, tests/golden/fwn_ref.npz).
 // The pins we do have are in tests/: closed-form known answers, the Eikonal property, and the
 // reference's own shapes/*.obj outlines (tests/golden/obj_outlines.json).
 #pragma once

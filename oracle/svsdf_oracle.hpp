@@ -7,7 +7,9 @@
 // PARITY UNPINNED: the reference (ZJU-FAST-Lab/Implicit-SVSDF-Planner @ f18fd91) ships no golden
 // vectors or tests for this path and cannot be compiled here (hot-path headers need Eigen, ROS, PCL,
 // libigl — none present), so this restatement is pinned only by its own known-answer
-// and finite-difference tests (tests/test_oracle_*.py) and by the reference's shape meshes.
+// and finite-difference tests (tests/test_oracle_*.py), by the reference's shape meshes, by a trace of the reference's
+// own LMBM binary driving it (tests/golden/lmbm_trace_star_400.npz) and — mesh functor only — by the reference's own
+// fast-winding-number code compiled into oracle/_ref (tests/golden/fwn_ref.npz).
 //
 // Every function cites the reference file:line it follows (paths relative to /root/reference/src).
 #pragma once
