@@ -591,13 +591,19 @@ int svsdf_create(const svsdf_config *cfg, svsdf_ctx **out) {
         const ShapeParams &S = ctx->shape;
         const double R[3][3] = {{S.rot[0], S.rot[1], 0.0}, {S.rot[2], S.rot[3], 0.0}, {0.0, 0.0, 1.0}};
         const double tr[3] = {S.trans[0], S.trans[1], 0.0};
-        std::vector<double> tri((size_t)cfg->mesh_nf * 9);
-        for (int f = 0; f < cfg->mesh_nf; ++f)
+        std::vector<double> tri((size_t)cfg->mesh_nf * kMeshStride);
+        for (int f = 0; f < cfg->mesh_nf; ++f) {
+            double *rec = &tri[(size_t)f * kMeshStride];
             for (int k = 0; k < 3; ++k) {
                 const double *v = cfg->mesh_vertices + 3 * (size_t)cfg->mesh_faces[3 * f + k];
                 for (int j = 0; j < 3; ++j)
-                    tri[(size_t)f * 9 + 3 * k + j] = ((v[0] * R[j][0] + v[1] * R[j][1]) + v[2] * R[j][2]) + tr[j];
+                    rec[3 * k + j] = ((v[0] * R[j][0] + v[1] * R[j][1]) + v[2] * R[j][2]) + tr[j];
             }
+            // rmax: farthest point of the face from vertex a (one of the other two vertices), padded upwards
+            const double ab = std::sqrt((rec[3] - rec[0]) * (rec[3] - rec[0]) + (rec[4] - rec[1]) * (rec[4] - rec[1]) + (rec[5] - rec[2]) * (rec[5] - rec[2]));
+            const double ac = std::sqrt((rec[6] - rec[0]) * (rec[6] - rec[0]) + (rec[7] - rec[1]) * (rec[7] - rec[1]) + (rec[8] - rec[2]) * (rec[8] - rec[2]));
+            rec[9] = std::max(ab, ac) * (1.0 + 1e-12) + 1e-300;
+        }
         if ((e = cudaMalloc(&ctx->d_mesh_tri, tri.size() * sizeof(double))) != cudaSuccess) return fail(e);
         if ((e = cudaMemcpy(ctx->d_mesh_tri, tri.data(), tri.size() * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return fail(e);
         ctx->shape.mesh_tri = ctx->d_mesh_tri;

@@ -428,19 +428,31 @@ struct ShapeFn<SH_MESH> {
         const double ex = px - qx, ey = py - qy, ez = pz - qz;
         return (ex * ex + ey * ey) + ez * ez;
     }
+    // One pass over the faces.  Record layout (kMeshStride doubles per face): a, b, c (9) and rmax = the largest distance
+    // from vertex a to a point of the face, max(|ab|, |ac|), padded upwards on the host.  By the triangle inequality every
+    // point of the face is at least |a - q| - rmax away from q, so when that bound (with a 1e-12 relative margin, four
+    // orders above the rounding of the quantities involved) exceeds the best squared distance so far the face cannot
+    // lower the minimum and its closest-point computation is skipped: a conservative prune, the minimum is unchanged
+    // bit for bit (the oracle takes the plain minimum over all faces).  Skipped only when every lane of the warp agrees.
     static __device__ __forceinline__ double sdf(const ShapeParams &S, double qx, double qy) {
         const double PI = 3.14159265358979323846;
         const double qz = 0.0;
         double omega = 0.0, best = __longlong_as_double(0x7ff0000000000000LL);
         const double *t = S.mesh_tri;
 #pragma unroll 1
-        for (int f = 0; f < S.mesh_nf; ++f, t += 9) {
+        for (int f = 0; f < S.mesh_nf; ++f, t += kMeshStride) {
             const double ax = __ldg(t), ay = __ldg(t + 1), az = __ldg(t + 2);
             const double bx = __ldg(t + 3), by = __ldg(t + 4), bz = __ldg(t + 5);
             const double cx = __ldg(t + 6), cy = __ldg(t + 7), cz = __ldg(t + 8);
-            omega += solid_angle(ax - qx, ay - qy, az - qz, bx - qx, by - qy, bz - qz, cx - qx, cy - qy, cz - qz);
-            const double d = sqr_distance(ax, ay, az, bx, by, bz, cx, cy, cz, qx, qy, qz);
-            if (d < best) best = d;
+            const double rmax = __ldg(t + 9);
+            const double rax = ax - qx, ray = ay - qy, raz = az - qz;
+            omega += solid_angle(rax, ray, raz, bx - qx, by - qy, bz - qz, cx - qx, cy - qy, cz - qz);
+            const double lb = sqrt((rax * rax + ray * ray) + raz * raz) - rmax;  // lower bound of the distance to the face
+            const bool need = !(lb > 0.0 && lb * lb > best * (1.0 + 1e-12));
+            if (__any_sync(__activemask(), need)) {
+                const double d = sqr_distance(ax, ay, az, bx, by, bz, cx, cy, cz, qx, qy, qz);
+                if (d < best) best = d;
+            }
         }
         const double w = omega / (4.0 * PI);
         const double s = 1. - 2. * w;

@@ -37,6 +37,7 @@ enum ShapeId : int {
 };
 
 constexpr int kMaxPolyEdges = 64;
+constexpr int kMeshStride = 10;          // doubles per face record: a, b, c, rmax (see ShapeFn<SH_MESH>)
 constexpr int kMaxMeshFaces = 1 << 20;  // SH_MESH: faces of the triangle soup (brute-force functor; see svsdf_shapes.cuh)
 constexpr int kMaxPieces = 64;       // pieces per trajectory supported by the per-warp accumulators
 constexpr int kWarpsPerBlock = 8;    // k_outer block = 256 threads
@@ -56,7 +57,7 @@ struct ShapeParams {
     int poly_n;         // Polygon edge count
     int pad_;
     double poly_sx[kMaxPolyEdges], poly_sy[kMaxPolyEdges], poly_ex[kMaxPolyEdges], poly_ey[kMaxPolyEdges];
-    const double *mesh_tri;  // SH_MESH: device pointer, 9 doubles per face (a, b, c), vertices already R v + trans (Shape.hpp:296-302)
+    const double *mesh_tri;  // SH_MESH: device pointer, kMeshStride doubles per face (a, b, c, rmax), vertices already R v + trans (Shape.hpp:296-302)
     int mesh_nf;
     int pad2_;
 };

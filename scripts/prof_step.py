@@ -9,8 +9,12 @@ N = int(os.environ.get("SVSDF_N", "8"))
 shape = os.environ.get("SVSDF_SHAPE", "star")
 strict = os.environ.get("SVSDF_STRICT", "1") == "1"
 reps = int(os.environ.get("SVSDF_REPS", "3"))
+mesh = None
+if os.environ.get("SVSDF_MESH", "0") == "1":  # the reference's star.obj through the triangle-mesh functor
+    g = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "fwn_ref.npz"))
+    mesh = (g["star_V"], g["star_F"])
 sc = scenes.make_scene(shape, N, P)
-ctx = api.Context(shape, strict_fp=strict)
+ctx = api.Context(shape, strict_fp=strict, mesh=mesh)
 ctx.set_points(sc.points)
 co = sc.coeffs_colmajor()
 for _ in range(reps):
