@@ -85,7 +85,39 @@ __device__ __forceinline__ int locate_piece(const TrajView &tv, double &t) {
     return idx;
 }
 
+// locatePieceIdx with a guess.  The reference's loop yields piece h and local time t_h = ((t - T_0) - T_1) ... - T_{h-1}
+// (one rounding per subtraction) iff every test before h passed and the test at h failed.  fl(a - b) > 0 <=> a > b, so
+// "all earlier tests passed" is equivalent to t_h > 0 (induction: t_h > 0 => t_{h-1} > T_{h-1} > 0 => ...).  With the
+// guess taken from the caller's previous sample (consecutive samples of a scan or of a descent almost always fall into
+// the same piece) the search is the bare subtraction chain plus two compares; a wrong guess (or NaN, or the idx == N
+// wrap-around case) falls back to the reference loop.  Same result bit for bit.
+__device__ __forceinline__ int locate_piece(const TrajView &tv, double &t, int &hint) {
+    const double *T = tv.T;
+    const int h = hint;
+    double tl = t;
+#pragma unroll 1
+    for (int i = 0; i < h; ++i) tl -= T[i];
+    if ((h == 0 || tl > 0.0) && !(tl > T[h])) {
+        t = tl;
+        return h;
+    }
+    hint = locate_piece(tv, t);
+    return hint;
+}
+
 // Piece<5>::getPos (trajectory.hpp:104-114): ascending powers with tn *= t (not Horner).
+__device__ __forceinline__ void traj_pos_at(const TrajView &tv, int i, double t, double &x, double &y, double &yaw) {
+    const double *c = tv.c + 18 * i;
+    x = 0.0; y = 0.0; yaw = 0.0;
+    double tn = 1.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        x += tn * c[k];
+        y += tn * c[6 + k];
+        yaw += tn * c[12 + k];
+        tn *= t;
+    }
+}
 __device__ __forceinline__ void traj_pos(const TrajView &tv, double t, double &x, double &y, double &yaw) {
     int i = locate_piece(tv, t);
     const double *c = tv.c + 18 * i;
@@ -133,6 +165,16 @@ __device__ __forceinline__ double eval_sdf(const TrajView &tv, const ShapeParams
     rel_from_pose(px, py, x, y, cy, sy, rx, ry);
     return dev::shape_sdf<SHAPE, XFORM>(S, rx, ry);
 }
+// same with a piece-index guess carried by the caller from its previous sample
+template <int SHAPE, bool XFORM>
+__device__ __forceinline__ double eval_sdf(const TrajView &tv, const ShapeParams &S, double px, double py, double t, int &hint) {
+    double x, y, yaw, sy, cy, rx, ry;
+    const int i = locate_piece(tv, t, hint);
+    traj_pos_at(tv, i, t, x, y, yaw);
+    dev::sincos_portable(yaw, sy, cy);
+    rel_from_pose(px, py, x, y, cy, sy, rx, ry);
+    return dev::shape_sdf<SHAPE, XFORM>(S, rx, ry);
+}
 
 // Warp arg-min with the sequential loop's semantics: the FIRST lane holding the minimum value wins; NaN never wins
 // (callers map NaN to +inf; the reference's test is `dis < min_dis`).  Two 32-bit REDUX.MIN over an order-preserving
@@ -158,10 +200,8 @@ struct OuterResult {
 // getSDFofSweptVolume<false,*> (sw_manager.hpp:844-866) = choiceTInit (:538-581) + gradientDescent (:1249-1325),
 // executed cooperatively by one warp. All lanes return the same values.
 //
-// After the table-driven layer 1, everything is organised as ROUNDS of one SDF evaluation per lane, driven by a small
-// warp-uniform state machine with a single eval_sdf call site (the evaluation is ~250 instructions; inlining it once
-// keeps the kernel inside the 32 KB L1.5 instruction cache):
-//   M_LAT  choiceTInit layers 2..4: 21-sample window around the seed, dt *= 0.1 per layer
+// After the table-driven layer 1 and the three 21-sample layers of choiceTInit, the descent is organised as ROUNDS of one
+// SDF evaluation per lane, driven by a small warp-uniform state machine with a single eval_sdf call site:
 //   M_F0   f(x0) when no sample was below the initial 1e9 (degenerate input; the reference evaluates it at iter == 0)
 //   M_A    first descent step: lanes 0-14 x - tau_j (slope sign +1), 15-29 x + tau_j (sign -1), j = 0..14; 30/31 slope
 //   M_B    halvings j = 15..28 in the known direction (only if M_A found no decreasing candidate)
@@ -198,112 +238,113 @@ __device__ __forceinline__ OuterResult solve_outer(const TrajView &tv, const Sha
         }
     }
 
-    enum { M_LAT = 0, M_F0, M_A, M_B, M_P, M_M };
-    int mode = M_LAT, layer = 2;
-    double dt = 0.15, term = 0.0;
-    double x = 0.0, fx = 0.0, prev_x = 10000000.0, t_min = 0.0, t_max = 0.0;
-    int iter = 0, pred = 0, sgn = 0;
-    bool stop = false, running = true;
-    if (have_seed) {  // enter the state machine at the gradientDescent set-up (:856-857)
-        t_min = smaxd(0.0, seed - 3.4);
-        t_max = smind(seed + 3.4, D);
-        x = seed;
-        fx = min_dis;
-        mode = __any_sync(FULL, min_dis >= 1e9) ? M_F0 : M_A;
-        if (mode == M_A) prev_x = x;  // first outer step: `prev_x = x` after the (true) loop test
-    }
+    // ---- choiceTInit layers 2..4: 21-sample window around the seed, dt *= 0.1 per layer, one sample per lane ----
+    if (!have_seed) {
+        double dt = 0.15;
+        int hint = 0;
 #pragma unroll 1
-    while (running) {
-        // ---------------- sample time of this lane for the current round ----------------
-        double tq;
-        if (mode == M_LAT) {
+        for (int layer = 2; layer <= 4; ++layer) {
             dt *= 0.1;
             double t = smaxd(0.0, seed - 10 * dt);
-            term = smind(D, seed + 10 * dt);
+            const double term = smind(D, seed + 10 * dt);
 #pragma unroll
             for (int i = 0; i < 20; ++i)
                 if (i < lane) t += dt;  // lane k (<= 20) holds t0 + dt added k times (same rounding as the loop)
-            tq = t;
-        } else if (mode == M_F0) {
-            tq = x;
-        } else {
-            // descent candidates: x + (-tau_j * s), clamped (gradientDescent :1301-1304); slope samples on lanes 30/31
-            int j, sdir;
-            if (mode == M_A) { j = (lane < 15) ? lane : lane - 15; sdir = (lane < 15) ? 1 : -1; }
-            else if (mode == M_B) { j = 15 + lane; sdir = sgn; }
-            else { j = lane; sdir = (mode == M_P) ? pred : sgn; }
-            // alpha = 0.01 halved j times: exact, so subtract j from the exponent field (0.01 * 2^-46 is still normal)
-            const double tau = __hiloint2double(__double2hiint(0.01) - (j << 20), __double2loint(0.01));
-            tq = smaxd(smind(x + (-tau * (double)sdir), t_max), t_min);
-            if (mode != M_B) {
-                tq = (lane == 30) ? smaxd(0.0, x - 0.000001) : tq;  // getSDF_DOTAtTimeStamp :798-806
-                tq = (lane == 31) ? smind(D, x + 0.000001) : tq;
-            }
-        }
-        // ---------------- the one evaluation site ----------------
-        double fq = eval_sdf<SHAPE, XFORM>(tv, S, px, py, tq);
-
-        // ---------------- decisions (warp-uniform) ----------------
-        int next_mode = mode;
-        bool step_end = false;   // an outer step of gradientDescent ended (accepted or failed), or the descent starts
-        int src = -1;            // lane holding the accepted candidate
-        int jacc = -1;
-        bool failed = false;
-        if (mode == M_LAT) {
-            const bool lat_valid = (lane <= 20) && (tq <= term);
+            const double fq = eval_sdf<SHAPE, XFORM>(tv, S, px, py, t, hint);
+            const bool lat_valid = (lane <= 20) && (t <= term);
             double fl = (lat_valid && (fq == fq)) ? fq : INF;
             evals += __popc(__ballot_sync(FULL, lat_valid));
             const int kb = warp_argmin_lane(fl);  // fl := warp minimum
-            const double tb = __shfl_sync(FULL, tq, kb);
+            const double tb = __shfl_sync(FULL, t, kb);
             if (__any_sync(FULL, fl < min_dis)) {
                 min_dis = fl;
                 seed = tb;
             }
-            ++layer;
-            if (layer > 4) {
-                // gradientDescent set-up: bounds [ts-3.4, ts+3.4] ∩ [0, D] (:856-857), x0 = seed
-                t_min = smaxd(0.0, seed - 3.4);
-                t_max = smind(seed + 3.4, D);
-                x = seed;
-                fx = min_dis;  // f(x0): x0 is the scan's arg-min (same function, same argument)
-                if (__any_sync(FULL, min_dis >= 1e9)) next_mode = M_F0;  // nothing below 1e9: evaluate f(x0) explicitly
-                else step_end = true;
+        }
+    }
+
+    // ---- gradientDescent (:1249-1325) from x0 = seed, bounds [ts-3.4, ts+3.4] ∩ [0, D] (:856-857) ----
+    // ROUNDS of one evaluation per lane.  Per-lane round constants: tau (step of this lane's candidate), sbit (sign bit
+    // of the offset: candidates move against the slope direction the round assumes) and the clamp interval — the
+    // descent interval for candidates, [0, +inf) / (-inf, D] for the two finite-difference samples on lanes 30 / 31
+    // (smaxd(0, x - 1e-6), smind(D, x + 1e-6): :798-806).  They change only when the round type changes.
+    enum { M_F0 = 0, M_A, M_B, M_P, M_M };
+    const double t_min = smaxd(0.0, seed - 3.4), t_max = smind(seed + 3.4, D);
+    const bool slope_lane = lane >= 30;
+    const double lo_l = slope_lane ? (lane == 30 ? 0.0 : -INF) : t_min;
+    const double hi_l = slope_lane ? (lane == 30 ? INF : D) : t_max;
+    const int hi001 = __double2hiint(0.01), lo001 = __double2loint(0.01);
+    // alpha = 0.01 halved j times: exact, so subtract j from the exponent field (0.01 * 2^-46 is still normal)
+    const int tauP_hi = slope_lane ? __double2hiint(0.000001) : hi001 - (lane << 20);
+    const int tau_lo = slope_lane ? __double2loint(0.000001) : lo001;
+    const unsigned sbit_fix = (lane == 30) ? 0x80000000u : 0u;  // lane 30: x - 1e-6, lane 31: x + 1e-6
+    double x = seed, fx = min_dis, prev_x = 10000000.0;
+    int iter = 0, pred = 0, sgn = 0, hint = 0;
+    int mode;
+    int tau_hi;        // this lane's step, high word
+    unsigned sbit;     // this lane's offset sign bit
+    if (__any_sync(FULL, min_dis >= 1e9)) {
+        // nothing below the initial 1e9 (degenerate input): the reference evaluates f(x0) at iter == 0
+        mode = M_F0;
+        tau_hi = 0; sbit = 0;   // offset +0.0: the sample is x itself
+    } else {
+        mode = M_A;
+        prev_x = x;             // `prev_x = x` after the (true) first loop test
+        tau_hi = slope_lane ? tauP_hi : hi001 - (((lane < 15) ? lane : lane - 15) << 20);
+        sbit = slope_lane ? sbit_fix : ((lane < 15) ? 0x80000000u : 0u);
+    }
+    bool running = true;
+#pragma unroll 1
+    while (running) {
+        const double off = __hiloint2double(tau_hi ^ (int)sbit, (mode == M_F0) ? 0 : tau_lo);
+        const double tq = smaxd(smind(x + off, hi_l), lo_l);
+        const double fq = eval_sdf<SHAPE, XFORM>(tv, S, px, py, tq, hint);
+        const unsigned m_dec = __ballot_sync(FULL, (fq - fx) < 0);  // candidates that decrease f
+        int jacc = -1, src = 0;
+        bool failed = false, step_end = true;
+        if (mode == M_P) {
+            // 29 halvings in the predicted direction + the slope: the common round
+            evals += 31;
+            const double g = (__shfl_sync(FULL, fq, 31) - __shfl_sync(FULL, fq, 30)) * 500000;
+            sgn = (int)__any_sync(FULL, g > 0) - (int)__any_sync(FULL, g < 0);  // (int)(g > 0) - (g < 0)
+            const unsigned m = m_dec & 0x1fffffffu;
+            if (sgn != 0 && sgn != pred) {  // mispredicted: redo the halvings in the actual direction
+                mode = M_M;
+                sbit = (sgn > 0) ? 0x80000000u : 0u;
+                step_end = false;
+            } else if (sgn != 0 && m) {
+                jacc = __ffs(m) - 1; src = jacc;
+            } else failed = true;
+        } else if (mode == M_M) {
+            evals += 29;
+            const unsigned m = m_dec & 0x1fffffffu;
+            if (m) { jacc = __ffs(m) - 1; src = jacc; }
+            else failed = true;
+        } else if (mode == M_A) {
+            // first step: lanes 0-14 x - tau_j (slope sign +1), 15-29 x + tau_j (sign -1), j = 0..14; 30/31 slope
+            evals += 32;
+            const double g = (__shfl_sync(FULL, fq, 31) - __shfl_sync(FULL, fq, 30)) * 500000;
+            sgn = (int)__any_sync(FULL, g > 0) - (int)__any_sync(FULL, g < 0);
+            const unsigned grp = (sgn > 0) ? (m_dec & 0x7fffu) : ((m_dec >> 15) & 0x7fffu);
+            if (sgn == 0) failed = true;
+            else if (grp) { jacc = __ffs(grp) - 1; src = (sgn > 0) ? jacc : jacc + 15; }
+            else {  // halvings j = 15..28 in the known direction
+                mode = M_B;
+                tau_hi = hi001 - ((15 + lane) << 20);
+                sbit = (sgn > 0) ? 0x80000000u : 0u;
+                step_end = false;
             }
-        } else if (mode == M_F0) {
+        } else if (mode == M_B) {
+            evals += 14;
+            const unsigned mb = m_dec & 0x3fffu;
+            if (mb) { src = __ffs(mb) - 1; jacc = 15 + src; }
+            else failed = true;
+        } else {  // M_F0
             fx = __shfl_sync(FULL, fq, 0);
             evals += 1;
-            step_end = true;
-        } else {
-            const unsigned m_dec = __ballot_sync(FULL, (fq - fx) < 0);  // candidates that decrease f
-            if (mode == M_A || mode == M_P) {
-                const double g = (__shfl_sync(FULL, fq, 31) - __shfl_sync(FULL, fq, 30)) * 500000;
-                sgn = (int)__any_sync(FULL, g > 0) - (int)__any_sync(FULL, g < 0);  // (int)(g > 0) - (g < 0)
-            }
-            if (mode == M_A) {
-                evals += 32;
-                const unsigned grp = (sgn > 0) ? (m_dec & 0x7fffu) : ((m_dec >> 15) & 0x7fffu);
-                if (sgn == 0) { failed = true; step_end = true; }
-                else if (grp) { jacc = __ffs(grp) - 1; src = (sgn > 0) ? jacc : jacc + 15; step_end = true; }
-                else next_mode = M_B;
-            } else if (mode == M_B) {
-                evals += 14;
-                const unsigned mb = m_dec & 0x3fffu;
-                if (mb) { src = __ffs(mb) - 1; jacc = 15 + src; }
-                else failed = true;
-                step_end = true;
-            } else {
-                evals += (mode == M_P) ? 31 : 29;
-                if (mode == M_P && sgn != 0 && sgn != pred) next_mode = M_M;  // mispredicted: redo in the actual direction
-                else {
-                    const unsigned m = m_dec & 0x1fffffffu;
-                    if (sgn != 0 && m) { jacc = __ffs(m) - 1; src = jacc; }
-                    else failed = true;
-                    step_end = true;
-                }
-            }
         }
-        const double xacc = __shfl_sync(FULL, tq, src & 31), facc = __shfl_sync(FULL, fq, src & 31);
         if (jacc >= 0) {
+            const double xacc = __shfl_sync(FULL, tq, src), facc = __shfl_sync(FULL, fq, src);
             // a full, unclamped stride means we are still walking downhill: same slope sign next; otherwise the step
             // overshot the minimiser (tau_j is the largest decreasing step) and the slope flips
             const bool walking = (jacc == 0) && __all_sync(FULL, xacc == x + (-0.01 * (double)sgn));
@@ -313,15 +354,21 @@ __device__ __forceinline__ OuterResult solve_outer(const TrajView &tv, const Sha
             iter += jacc + 1;
         } else if (failed) {
             iter += 29;
-            stop = true;
         }
         if (step_end) {
             // while (iter < max_iter && !stop && abs(x - prev_x) > tol)   (:1288)
-            running = (iter < 1000) && !stop && __all_sync(FULL, fabs(x - prev_x) > 1e-16);
+            running = (iter < 1000) && !failed && __all_sync(FULL, fabs(x - prev_x) > 1e-16);
             prev_x = x;
-            next_mode = (pred == 0) ? M_A : M_P;
+            if (pred == 0) {  // only after M_F0: first descent step
+                mode = M_A;
+                tau_hi = slope_lane ? tauP_hi : hi001 - (((lane < 15) ? lane : lane - 15) << 20);
+                sbit = slope_lane ? sbit_fix : ((lane < 15) ? 0x80000000u : 0u);
+            } else {
+                mode = M_P;
+                tau_hi = tauP_hi;
+                sbit = slope_lane ? sbit_fix : ((pred > 0) ? 0x80000000u : 0u);
+            }
         }
-        mode = next_mode;
     }
     OuterResult R;
     R.sdf = fx;
@@ -471,6 +518,7 @@ __device__ __forceinline__ void thread_choice_t_init(const TrajView &tv, const S
     }
     evals += tv.K1;
     double dt = 0.15;
+    int hint = 0;  // piece of the previous sample (the windows are <= 0.3 s wide)
 #pragma unroll 1
     for (int layer = 2; layer <= 4; ++layer) {
         dt *= 0.1;
@@ -478,7 +526,7 @@ __device__ __forceinline__ void thread_choice_t_init(const TrajView &tv, const S
         const double term = smind(tv.D, seed + 10 * dt);
 #pragma unroll 1
         for (; t <= term; t += dt) {
-            const double f = eval_sdf<SHAPE, XFORM>(tv, S, px, py, t);
+            const double f = eval_sdf<SHAPE, XFORM>(tv, S, px, py, t, hint);
             ++evals;
             if (f < min_dis) {
                 seed = t;
