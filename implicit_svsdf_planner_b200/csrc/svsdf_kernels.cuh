@@ -53,7 +53,20 @@ struct TrajView {
     const double *lat;   // [K1]
     const double *pose;  // [4][K1pad] SoA: x, y, cos, sin
     int K1pad;
+    // the same arrays as 32-bit shared-window addresses (valid when the view is on the shared-memory copy of the blob):
+    // the hot loops read through these with ld.shared so the address is one register + immediate instead of a
+    // generic pointer whose shared-window base the compiler re-derives (S2R SR_CgaCtaId + LEA) at every use
+    uint32_t sT, sc, slat, spose;
 };
+
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void lds_v2(uint32_t a, double &v0, double &v1) {
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v0), "=d"(v1) : "r"(a));
+}
 
 __device__ __forceinline__ TrajView make_view(const double *blob) {
     TrajView tv;
@@ -66,6 +79,14 @@ __device__ __forceinline__ TrajView make_view(const double *blob) {
     tv.lat = blob + L.off_lat;
     tv.pose = blob + L.off_pose;
     tv.K1pad = L.K1pad;
+    // (meaningless for a view on global memory, k_pose_table).  The blob is read-only once the TMA copy has landed; the
+    // empty volatile asm orders every ld.shared that derives its address from `sb` after the mbarrier wait.
+    uint32_t sb = (uint32_t)__cvta_generic_to_shared(blob);
+    asm volatile("" : "+r"(sb) : : "memory");
+    tv.sT = sb + 8u * (uint32_t)L.off_T;
+    tv.sc = sb + 8u * (uint32_t)L.off_c;
+    tv.slat = sb + 8u * (uint32_t)L.off_lat;
+    tv.spose = sb + 8u * (uint32_t)L.off_pose;
     return tv;
 }
 
@@ -92,12 +113,23 @@ __device__ __forceinline__ int locate_piece(const TrajView &tv, double &t) {
 // the same piece) the search is the bare subtraction chain plus two compares; a wrong guess (or NaN, or the idx == N
 // wrap-around case) falls back to the reference loop.  Same result bit for bit.
 __device__ __forceinline__ int locate_piece(const TrajView &tv, double &t, int &hint) {
-    const double *T = tv.T;
     const int h = hint;
     double tl = t;
+    uint32_t a = tv.sT;  // 16-byte aligned
+    int i = 0;
 #pragma unroll 1
-    for (int i = 0; i < h; ++i) tl -= T[i];
-    if ((h == 0 || tl > 0.0) && !(tl > T[h])) {
+    for (; i + 2 <= h; i += 2, a += 16) {
+        double d0, d1;
+        lds_v2(a, d0, d1);
+        tl -= d0;
+        tl -= d1;
+    }
+    if (i < h) {
+        tl -= lds_f64(a);
+        a += 8;
+    }
+    const double Th = lds_f64(a);  // T[h]
+    if ((h == 0 || tl > 0.0) && !(tl > Th)) {
         t = tl;
         return h;
     }
@@ -107,7 +139,10 @@ __device__ __forceinline__ int locate_piece(const TrajView &tv, double &t, int &
 
 // Piece<5>::getPos (trajectory.hpp:104-114): ascending powers with tn *= t (not Horner).
 __device__ __forceinline__ void traj_pos_at(const TrajView &tv, int i, double t, double &x, double &y, double &yaw) {
-    const double *c = tv.c + 18 * i;
+    const uint32_t a = tv.sc + 144u * (uint32_t)i;  // 18 doubles per piece, 16-byte aligned
+    double c[18];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) lds_v2(a + 16u * k, c[2 * k], c[2 * k + 1]);
     x = 0.0; y = 0.0; yaw = 0.0;
     double tn = 1.0;
 #pragma unroll
@@ -224,9 +259,9 @@ __device__ __forceinline__ OuterResult solve_outer(const TrajView &tv, const Sha
         int k = base + lane;
         double f = INF;
         if (k < tv.K1) {
-            const double *ps = tv.pose + k;
+            const uint32_t ps = tv.spose + 8u * (uint32_t)k, row = 8u * (uint32_t)tv.K1pad;
             double rx, ry;
-            rel_from_pose(px, py, ps[0], ps[tv.K1pad], ps[2 * tv.K1pad], ps[3 * tv.K1pad], rx, ry);
+            rel_from_pose(px, py, lds_f64(ps), lds_f64(ps + row), lds_f64(ps + 2 * row), lds_f64(ps + 3 * row), rx, ry);
             f = dev::shape_sdf<SHAPE, XFORM>(S, rx, ry);
             if (!(f == f)) f = INF;
         }
@@ -234,7 +269,7 @@ __device__ __forceinline__ OuterResult solve_outer(const TrajView &tv, const Sha
         const int kb = base + warp_argmin_lane(f);
         if (__any_sync(FULL, f < min_dis)) {  // f is warp-uniform; the vote lets the compiler know the branch is too
             min_dis = f;
-            seed = tv.lat[kb];
+            seed = lds_f64(tv.slat + 8u * (uint32_t)kb);
         }
     }
 
@@ -505,15 +540,16 @@ __device__ __forceinline__ void thread_choice_t_init(const TrajView &tv, const S
                                                      double &seed, double &min_dis, int &evals) {
     min_dis = 1e9;
     seed = 0.0;
-    const double *ps = tv.pose;
+    uint32_t ps = tv.spose;
+    const uint32_t row = 8u * (uint32_t)tv.K1pad;
 #pragma unroll 1
-    for (int k = 0; k < tv.K1; ++k) {
+    for (int k = 0; k < tv.K1; ++k, ps += 8) {
         double rx, ry;
-        rel_from_pose(px, py, ps[k], ps[tv.K1pad + k], ps[2 * tv.K1pad + k], ps[3 * tv.K1pad + k], rx, ry);
+        rel_from_pose(px, py, lds_f64(ps), lds_f64(ps + row), lds_f64(ps + 2 * row), lds_f64(ps + 3 * row), rx, ry);
         const double f = dev::shape_sdf<SHAPE, XFORM>(S, rx, ry);
         if (f < min_dis) {
             min_dis = f;
-            seed = tv.lat[k];
+            seed = lds_f64(tv.slat + 8u * (uint32_t)k);
         }
     }
     evals += tv.K1;
