@@ -1,18 +1,27 @@
 #!/bin/bash
 # Run on the GPU box (under gpurun): collects the evidence that scripts/summarise_profiles.py turns into profiles/.
+# usage: collect_profiles.sh [a|b]   a = tests, bench, launch list, configs, batch; b = the two `ncu --set full` captures
+# (gpurun merges at most 64 MiB back per call, the two reports alone are ~60 MB)
 set -x
 mkdir -p gpurun_out
+PART=${1:-ab}
+if [[ $PART == *a* ]]; then
 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_r1.log 2>&1
 python bench.py --steps 20 --warmup 3 > gpurun_out/bench_r1.json 2> gpurun_out/bench_r1.err
 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_reference_r1.json 2>> gpurun_out/bench_r1.err
 # launch list of the bench command (per-launch times under ncu are cold-cache and serialised: compare shares)
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r1.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-lbfgs > gpurun_out/bench_under_ncu_r1.log 2>&1
+fi
+if [[ $PART == *b* ]]; then
 # one full capture of the dominant kernel and of the interior-branch kernel
 ncu --set full --clock-control none --import-source on -k regex:k_outer -s 2 -c 1 -f -o gpurun_out/prof_outer_r1 \
     python scripts/prof_step.py > gpurun_out/prof_r1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_gsip -s 2 -c 1 -f -o gpurun_out/prof_gsip_r1 \
+ncu --set full --clock-control none -k regex:k_gsip -s 2 -c 1 -f -o gpurun_out/prof_gsip_r1 \
     python scripts/prof_step.py >> gpurun_out/prof_r1.log 2>&1
-python scripts/run_configs.py 1 2 3 4 > gpurun_out/configs_r1.jsonl 2> gpurun_out/configs_r1.err
+fi
+if [[ $PART == *a* ]]; then
+python scripts/run_configs.py 1 2 3 4 4m > gpurun_out/configs_r1.jsonl 2> gpurun_out/configs_r1.err
 python scripts/run_batch.py --problems 16 --max-iter 20 > gpurun_out/batch_1gpu_r1.json 2> gpurun_out/batch_r1.err
 tail -3 gpurun_out/pytest_gpu_r1.log
+fi
