@@ -72,8 +72,7 @@ def test_mesh_query_is_bit_identical_to_oracle(oracle_mod, scene_small_inside):
     outside = r_c == 0
     assert np.array_equal(s_g[outside], s_c[outside]) and np.array_equal(g_g[outside], g_c[outside])
     inside = ~outside
-    assert np.abs(s_g[inside] - s_c[inside]).max() <= 1e-9
-    assert np.abs(g_g[inside] - g_c[inside]).max() <= 1e-9
+    assert np.array_equal(s_g[inside], s_c[inside]) and np.array_equal(g_g[inside], g_c[inside])
 
 
 @pytest.mark.parametrize("which", ["synthetic", "reference_star_obj"])

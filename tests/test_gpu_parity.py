@@ -6,8 +6,8 @@ Parity statement (north_star: cost and gradient within 1e-6 relative of the refe
   * strict build (product default, -fmad=false) vs the oracle's default build: both sides perform the same IEEE
     operations in the same order and use the same published sin/cos algorithm (fdlibm; the oracle's copy is
     oracle/portable_sincos.hpp), so every per-point result of the outer solve — sdf, t*, FD gradient — is BIT-IDENTICAL;
-    cost / gradC / gradT differ only by summation order (<= 1e-11 relative); interior (GSIP) points agree to 1e-9
-    (their ring direction starts from atan2, which is libm on both sides).
+    cost / gradC / gradT differ only by summation order (<= 1e-11 relative); interior (GSIP) points are bitwise too
+    (atan2 of the ring direction is the same pinned fdlibm restatement on both sides).
   * versus the oracle built with glibc's sin/cos ("glibc" variant = the reference's actual x86-64 behaviour) the cost
     agrees to 1e-12 and the gradient to ~1e-5: the reference's sign-descent is ill-conditioned where the robot is at
     rest (trajectory ends) and a 1-ulp difference in sin/cos moves t* by ~1e-5 there.  The same happens when the
@@ -129,10 +129,9 @@ def test_strict_query_is_bit_identical_to_oracle(oracle_mod, scene2k, scene_smal
         assert np.array_equal(s_g[outside], s_c[outside]) and np.array_equal(t_g[outside], t_c[outside])
         assert np.array_equal(g_g[outside], g_c[outside])
         inside = ~outside
-        if inside.any():
-            assert np.abs(s_g[inside] - s_c[inside]).max() <= 1e-9
-            assert np.abs(t_g[inside] - t_c[inside]).max() <= 1e-6
-            assert np.abs(g_g[inside] - g_c[inside]).max() <= 1e-9  # world-frame unit direction
+        if inside.any():  # interior (GSIP) branch: same ring samples, same solves, same arg-min -> bitwise as well
+            assert np.array_equal(s_g[inside], s_c[inside]) and np.array_equal(t_g[inside], t_c[inside])
+            assert np.array_equal(g_g[inside], g_c[inside])  # world-frame unit direction
             assert np.abs(np.linalg.norm(g_g[inside], axis=1) - 1.0).max() < 1e-12
 
 
