@@ -88,6 +88,7 @@ EXPORTED_SYMBOLS = [
     "svsdf_shape_sdf", "svsdf_shape_grad1", "svsdf_cost_grad_device", "svsdf_kernel_launches",
     "svsdf_executed_evals", "svsdf_fp64_peak", "svsdf_device_ptr_points", "svsdf_lbfgs_minimize", "svsdf_last_kernel_ms", "svsdf_sincos", "svsdf_set_map", "svsdf_set_map_device",
     "svsdf_extract_points", "svsdf_get_points", "svsdf_read_obj", "svsdf_free",
+    "svsdf_front_init", "svsdf_front_get_kernels", "svsdf_front_cspace", "svsdf_front_check_kernel_value",
 ]
 
 
@@ -111,6 +112,10 @@ def lib():
     L.svsdf_shape_id.argtypes = [C.c_char_p]
     L.svsdf_read_obj.argtypes = [C.c_char_p, C.POINTER(dp), C.POINTER(C.c_int), C.POINTER(C.POINTER(C.c_int32)), C.POINTER(C.c_int)]
     L.svsdf_free.argtypes = [vp]
+    L.svsdf_front_init.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_double]
+    L.svsdf_front_get_kernels.argtypes = [vp, dp, vp, vp]
+    L.svsdf_front_cspace.argtypes = [vp, vp, C.POINTER(C.c_float), C.POINTER(vp)]
+    L.svsdf_front_check_kernel_value.argtypes = [vp, C.c_int64, dp, vp, vp, dp]
     L.svsdf_set_points.argtypes = [vp, dp, C.c_int64, C.c_int]
     L.svsdf_set_points_device.argtypes = [vp, vp, C.c_int64]
     L.svsdf_set_traj.argtypes = [vp, C.c_int, dp, dp]
@@ -415,6 +420,45 @@ class Context:
         if n.value:
             self._ck(lib().svsdf_get_points(self.h, _p(out), n.value, C.byref(n)), "svsdf_get_points")
         return out
+
+    # ---- A* front-end collision kernels ----
+    def front_init(self, kernel_size=17, kernel_yaw_num=18, occupancy_resolution=1.0, front_end_safeh=0.0):
+        """BasicShape::initShape on the device (Shape.hpp:386-430)."""
+        self._front = (int(kernel_size), int(kernel_yaw_num))
+        self._ck(lib().svsdf_front_init(self.h, int(kernel_size), int(kernel_yaw_num), float(occupancy_resolution), float(front_end_safeh)),
+                 "svsdf_front_init")
+
+    def front_kernels(self):
+        """(yaw [K], bool kernels [K, ks, ks], byte kernels [K, ks, ceil(ks / 8)])."""
+        ks, K = self._front
+        yaw = np.empty(K)
+        cells = np.zeros((K, ks, ks), dtype=np.uint8)
+        byt = np.zeros((K, ks, (ks + 7) // 8), dtype=np.uint8)
+        self._ck(lib().svsdf_front_get_kernels(self.h, _p(yaw), cells.ctypes.data_as(C.c_void_p), byt.ctypes.data_as(C.c_void_p)),
+                 "svsdf_front_get_kernels")
+        return yaw, cells.astype(bool), byt
+
+    def front_cspace(self, X, Y, fetch=True):
+        """kernelConv for every yaw kernel and cell of the map set with set_map: (free [K, X, Y] bool or None, device ms)."""
+        ks, K = self._front
+        W = (Y + 31) // 32
+        words = np.zeros((K, X, W), dtype=np.uint32) if fetch else None
+        ms = C.c_float()
+        self._ck(lib().svsdf_front_cspace(self.h, words.ctypes.data_as(C.c_void_p) if fetch else None, C.byref(ms), None), "svsdf_front_cspace")
+        if not fetch:
+            return None, ms.value
+        bits = (words[..., None] >> (31 - np.arange(32, dtype=np.uint32))) & 1
+        return bits.reshape(K, X, 32 * W)[:, :, :Y].astype(bool), ms.value
+
+    def front_check_kernel_value(self, father_yaw, ind_xy):
+        """SweptVolumeManager::checkKernelValue for a batch of nodes: (ok [n] bool, child_yaw [n])."""
+        fy = _f64(father_yaw).reshape(-1)
+        ind = np.ascontiguousarray(ind_xy, dtype=np.int32).reshape(-1, 2)
+        ok = np.zeros(fy.size, dtype=np.uint8)
+        cy = np.empty(fy.size)
+        self._ck(lib().svsdf_front_check_kernel_value(self.h, fy.size, _p(fy), ind.ctypes.data_as(C.c_void_p), ok.ctypes.data_as(C.c_void_p), _p(cy)),
+                 "svsdf_front_check_kernel_value")
+        return ok.astype(bool), cy
 
     def sincos(self, x):
         x = _f64(x).reshape(-1)

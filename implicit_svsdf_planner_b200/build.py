@@ -28,6 +28,7 @@ UNITS = [
     ("svsdf_kernels_fast.cu", "svsdf_kernels_fast.o", []),
     ("svsdf_kernels_strict.cu", "svsdf_kernels_strict.o", ["-fmad=false"]),
     ("svsdf_extract.cu", "svsdf_extract.o", ["-fmad=false"]),  # cell centres must round like the host formula
+    ("svsdf_frontend.cu", "svsdf_frontend.o", ["-fmad=false"]),  # shape kernels: same rounding as the strict functors
     ("svsdf_runtime.cpp", "svsdf_runtime.o", []),
 ]
 HEADERS = [

@@ -1,0 +1,194 @@
+// svsdf_frontend.cu — K5: the collision kernels of the reference's A* front end on the device.
+//
+// Reference (paths relative to /root/reference/src):
+//   BasicShape::initShape                 utils/include/utils/Shape.hpp:386-430   yaw-indexed occupancy kernels of the robot shape:
+//                                         cell (a, b) of kernel k is set iff getonlySDF((x_a, y_b, 0), Rz(yaw_k)) <= safemargin
+//   getonlySDF(pos_rel, R_obj)            Shape.hpp:481-485 ... (every analytic class): ((p - trans) * Rotate * R_obj).head(2)
+//   byteShapeKernel::generateByteKernel   Shape.hpp:194-216  (MSB-first rows, or_mask)
+//   SweptVolumeManager::kernelConv<true>  swept_volume/include/swept_volume/sw_manager.hpp:1068-1095: byte-AND of the shape's byte
+//                                         kernel with the window of the inflated, byte-packed map kernel (generateMapKernel2D)
+//   visit_kernels_by_distance, checkKernelValue   sw_manager.hpp:1099-1169
+//
+// B200 formulation.  The A* calls kernelConv once per (expanded cell, yaw) — 51 byte operations each, latency bound on
+// the host.  Here the whole configuration-space obstacle map is produced in one pass instead: free[k][x][y] for every yaw
+// kernel k and every cell, 32 cells (one output word) per thread, each kernel row applied as shifted ORs of the two map
+// words under it (funnel shifts; the map's MSB-first bit order is kept so the words are the map's own bytes).  Integer
+// work on an L2-resident input (the packed map is X*Y/8 bytes); output K*X*Y/8 bytes — after that a collision test is
+// one bit lookup.  k_check_kernel_value restates the per-node test literally (byte by byte) on top of the same data and
+// is what the tests compare the word-parallel kernel with.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "svsdf_shapes.cuh"
+#include "svsdf_types.h"
+
+namespace svsdf {
+
+namespace {
+
+template <int SHAPE, bool XFORM>
+__global__ void __launch_bounds__(256) k_shape_kernel_cells(const __grid_constant__ ShapeParams S, FrontParams F,
+                                                            const double *yaws, unsigned char *cells) {
+    const int ks = F.kernel_size;
+    const int n = F.kernel_count * ks * ks;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int k = idx / (ks * ks), a = (idx / ks) % ks, b = idx % ks;
+    double s, c;
+    dev::sincos_portable(yaws[k], s, c);
+    const int size_side = (int)(0.5 * (ks - 1));
+    const double x = F.res * a - size_side * F.res;  // Shape.hpp:413-414
+    const double y = F.res * b - size_side * F.res;
+    double w0 = x, w1 = y;
+    if (XFORM) {
+        const double v0 = x - S.trans[0], v1 = y - S.trans[1];
+        w0 = v0 * S.rot[0] + v1 * S.rot[2];
+        w1 = v0 * S.rot[1] + v1 * S.rot[3];
+    }
+    const double u0 = w0 * c + w1 * s;      // R_obj = [[c, -s], [s, c]], row vector on the left
+    const double u1 = w0 * (-s) + w1 * c;
+    const double sdf = dev::ShapeFn<SHAPE>::sdf(S, u0, u1);
+    cells[idx] = (sdf <= F.safemargin) ? 1 : 0;
+}
+
+// 32 consecutive map bits of inflated row `row`, starting at inflated column 32 * w, MSB = lowest column
+__device__ __forceinline__ unsigned map_word(const unsigned char *row, int row_bytes, int w) {
+    const int b0 = 4 * w;
+    unsigned v = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (b0 + q < row_bytes) v |= (unsigned)__ldg(row + b0 + q) << (24 - 8 * q);
+    return v;
+}
+
+// out[k][x][yw]: bit (31 - t) of the word <-> cell y = 32 * yw + t; 1 = kernelConv(k, (x, y)) is true (free)
+__global__ void __launch_bounds__(256) k_cspace(FrontParams F, const unsigned char *map, const unsigned *rowmask, unsigned *out) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int W = F.out_words;
+    const int64_t n = (int64_t)F.kernel_count * F.X * W;
+    if (idx >= n) return;
+    const int yw = (int)(idx % W), x = (int)((idx / W) % F.X), k = (int)(idx / ((int64_t)W * F.X));
+    const unsigned *rm = rowmask + k * F.kernel_size;
+    unsigned coll = 0u;
+    for (int i = 0; i < F.kernel_size; ++i) {
+        unsigned m = rm[i];
+        if (m == 0u) continue;
+        const unsigned char *row = map + (int64_t)(x + i) * F.row_bytes;  // window rows start at inflated row x
+        const unsigned w0 = map_word(row, F.row_bytes, yw), w1 = map_word(row, F.row_bytes, yw + 1);
+        while (m) {
+            const int j = __clz(m);  // kernel column j (MSB first)
+            m &= ~(0x80000000u >> j);
+            coll |= __funnelshift_l(w1, w0, j);  // map bits at columns (y + j) for the 32 cells of this word
+        }
+    }
+    unsigned fr = ~coll;
+    const int y0 = 32 * yw;
+    if (y0 + 32 > F.Y) fr &= (F.Y - y0 >= 32) ? 0xffffffffu : ~(0xffffffffu >> (F.Y - y0));  // cells beyond Y: not free
+    out[idx] = fr;
+}
+
+// kernelConv<true>, literally (sw_manager.hpp:1068-1095)
+__device__ __forceinline__ bool kernel_conv_byte(const FrontParams &F, const unsigned char *map, const unsigned char *kbytes, int kernel_i,
+                                                 int ind_x, int ind_y) {
+    const int bpr = (F.kernel_size + 7) / 8;
+    const int64_t total = (int64_t)(F.X + 2 * F.h) * F.row_bytes;
+    for (int i = 0; i < F.kernel_size; i++) {
+        const int64_t start = (int64_t)(ind_x + i) * F.row_bytes + (ind_y / 8);
+        const int off = ind_y % 8;
+        for (int j = 0; j < bpr; j++) {
+            const unsigned m0 = (start + j < total) ? __ldg(map + start + j) : 0u;
+            const unsigned m1 = (start + j + 1 < total) ? __ldg(map + start + j + 1) : 0u;
+            const unsigned block = ((m0 << off) | (m1 >> (8 - off))) & 0xffu;
+            if (kbytes[((int64_t)kernel_i * F.kernel_size + i) * bpr + j] & block) return false;
+        }
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(128) k_check_kernel_value(FrontParams F, const unsigned char *map, const unsigned char *kbytes, int64_t n,
+                                                            const double *father_yaw, const int *ind_xy, unsigned char *ok_out,
+                                                            double *child_yaw_out) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const double pi = 3.1415926536;  // sw_manager.hpp:20
+    const int count = F.kernel_count;
+    const double fy = father_yaw[q];
+    int father_i = int(count * ((fy + pi) / (2 * pi)));
+    father_i = father_i < 0 ? 0 : (father_i >= count ? count - 1 : father_i);
+    const int ix = ind_xy[2 * q], iy = ind_xy[2 * q + 1];
+    // visit_kernels_by_distance: breadth-first over the yaw ring, at most maxdeepth + 1 = 11 kernels
+    unsigned long long visited = 1ull << father_i;
+    int queue[24];
+    int head = 0, tail = 0, deep = 0;
+    queue[tail++] = father_i;
+    bool ok = false;
+    int ret = father_i;
+    while (head < tail) {
+        deep++;
+        const int x = queue[head++];
+        if (kernel_conv_byte(F, map, kbytes, x, ix, iy)) { ret = x; ok = true; break; }
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+            int nx = x + (d == 0 ? -1 : 1);
+            if (nx < 0) nx = count - 1;
+            if (nx >= count) nx = 0;
+            if ((visited >> nx) & 1ull) continue;
+            visited |= 1ull << nx;
+            if (tail < 24) queue[tail++] = nx;
+        }
+        if (deep > 10) break;
+    }
+    ok_out[q] = ok ? 1 : 0;
+    child_yaw_out[q] = ok ? (2 * pi * (ret) / count - pi) : fy;
+}
+
+template <int SHAPE, bool XFORM>
+cudaError_t launch_cells_t(const ShapeParams &S, const FrontParams &F, const double *yaws, unsigned char *cells, cudaStream_t st) {
+    const int n = F.kernel_count * F.kernel_size * F.kernel_size;
+    k_shape_kernel_cells<SHAPE, XFORM><<<(n + 255) / 256, 256, 0, st>>>(S, F, yaws, cells);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_front_cells(const ShapeParams &S, const FrontParams &F, const double *yaws, unsigned char *cells, cudaStream_t st) {
+    switch (S.id) {
+#define SVSDF_CASE(ID) \
+    case ID: return S.has_xform ? launch_cells_t<ID, true>(S, F, yaws, cells, st) : launch_cells_t<ID, false>(S, F, yaws, cells, st);
+        SVSDF_CASE(SH_STAR)
+        SVSDF_CASE(SH_HORSESHOE)
+        SVSDF_CASE(SH_PIE)
+        SVSDF_CASE(SH_PIE2)
+        SVSDF_CASE(SH_ARC)
+        SVSDF_CASE(SH_TUNNEL)
+        SVSDF_CASE(SH_CUTDISK)
+        SVSDF_CASE(SH_TRAPEZOID)
+        SVSDF_CASE(SH_RHOMBUS)
+        SVSDF_CASE(SH_HEART)
+        SVSDF_CASE(SH_ROUNDEDX)
+        SVSDF_CASE(SH_BIGX)
+        SVSDF_CASE(SH_ROUNDEDCROSS)
+        SVSDF_CASE(SH_VESICA)
+        SVSDF_CASE(SH_MOON)
+        SVSDF_CASE(SH_UNEVENCAPSULE)
+        SVSDF_CASE(SH_CIRCLE)
+#undef SVSDF_CASE
+        default: return cudaErrorInvalidValue;  // Polygon / mesh: the reference defines no rotated kernels for them
+    }
+}
+
+cudaError_t launch_front_cspace(const FrontParams &F, const unsigned char *map, const unsigned *rowmask, unsigned *out, cudaStream_t st) {
+    const int64_t n = (int64_t)F.kernel_count * F.X * F.out_words;
+    if (n == 0) return cudaSuccess;
+    k_cspace<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(F, map, rowmask, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_front_check(const FrontParams &F, const unsigned char *map, const unsigned char *kbytes, int64_t n, const double *father_yaw,
+                               const int *ind_xy, unsigned char *ok_out, double *child_yaw_out, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    k_check_kernel_value<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(F, map, kbytes, n, father_yaw, ind_xy, ok_out, child_yaw_out);
+    return cudaGetLastError();
+}
+
+}  // namespace svsdf

@@ -28,4 +28,9 @@ cudaError_t launch_extract_count(const ExtractArgs &E, int *block_counts, int n_
                                  cudaStream_t stream);
 cudaError_t launch_extract_write(const ExtractArgs &E, const int *block_offsets, int n_blocks, double *out_xy,
                                  int64_t cap, cudaStream_t stream);
+// K5 (svsdf_frontend.cu)
+cudaError_t launch_front_cells(const ShapeParams &S, const FrontParams &F, const double *yaws, unsigned char *cells, cudaStream_t st);
+cudaError_t launch_front_cspace(const FrontParams &F, const unsigned char *map, const unsigned *rowmask, unsigned *out, cudaStream_t st);
+cudaError_t launch_front_check(const FrontParams &F, const unsigned char *map, const unsigned char *kbytes, int64_t n, const double *father_yaw,
+                               const int *ind_xy, unsigned char *ok_out, double *child_yaw_out, cudaStream_t st);
 }  // namespace svsdf

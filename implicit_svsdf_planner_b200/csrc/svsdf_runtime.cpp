@@ -42,6 +42,15 @@ struct svsdf_ctx {
 
     // query points
     double *d_mesh_tri = nullptr;  // SH_MESH: 9 doubles per face
+    // K5: A* front-end collision kernels
+    bool front_ready = false;
+    FrontParams front{};
+    std::vector<double> front_yaw;
+    std::vector<unsigned char> front_cells, front_bytes;
+    unsigned char *d_front_bytes = nullptr;
+    unsigned *d_front_rowmask = nullptr;
+    unsigned *d_cspace = nullptr;
+    size_t cap_cspace = 0;
     double *d_points = nullptr;  // packed xy
     bool own_points = true;
     int64_t P = 0;
@@ -494,6 +503,8 @@ int svsdf_read_obj(const char *path, double **vertices_out, int *nv_out, int32_t
     char line[4096];
     bool bad = false;
     while (std::fgets(line, sizeof(line), fp)) {
+        const size_t len = std::strlen(line);
+        if (len + 1 == sizeof(line) && line[len - 1] != '\n') { bad = true; break; }  // record longer than the buffer
         char *p = line;
         while (*p == ' ' || *p == '\t') ++p;
         if (p[0] == 'v' && (p[1] == ' ' || p[1] == '\t')) {
@@ -532,6 +543,147 @@ int svsdf_read_obj(const char *path, double **vertices_out, int *nv_out, int32_t
     return SVSDF_OK;
 }
 void svsdf_free(void *p) { std::free(p); }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K5: collision kernels of the A* front end (csrc/svsdf_frontend.cu)
+// ---------------------------------------------------------------------------------------------------------------------
+int svsdf_front_init(svsdf_ctx *ctx, int kernel_size, int kernel_yaw_num, double occupancy_resolution, double front_end_safeh) {
+    if (!ctx) return SVSDF_ERR_INVALID;
+    if (kernel_size < 1 || kernel_size > kMaxKernelSize || (kernel_size % 2) == 0 || kernel_yaw_num < 1 || kernel_yaw_num > kMaxYawKernels ||
+        !(occupancy_resolution > 0.0)) {
+        ctx->err = "svsdf_front_init: kernel_size must be odd and <= 32, 1 <= kernel_yaw_num <= 64, resolution > 0";
+        return SVSDF_ERR_INVALID;
+    }
+    if (ctx->shape.id == SH_POLYGON || ctx->shape.id == SH_MESH) {
+        ctx->err = "svsdf_front_init: the reference defines no rotated kernels for the Polygon / mesh functors (Shape.hpp:1477 vs :267)";
+        return SVSDF_ERR_INVALID;
+    }
+    CK(cudaSetDevice(ctx->device));
+    ctx->front_ready = false;
+    FrontParams F{};
+    F.kernel_size = kernel_size;
+    F.kernel_count = kernel_yaw_num;
+    F.res = occupancy_resolution;
+    F.safemargin = std::max(front_end_safeh, occupancy_resolution / 2);  // Shape.hpp:399
+    const double PI = 3.14159265358979323846;                             // Shape.hpp:31
+    const double yaw_res = 2 * PI / kernel_yaw_num;
+    ctx->front_yaw.assign(kernel_yaw_num, 0.0);
+    int ind = 0;
+    for (double yaw = -PI; yaw < PI && ind < kernel_yaw_num; yaw += yaw_res, ind++) ctx->front_yaw[ind] = yaw;  // :401
+    const int K = kernel_yaw_num, ks = kernel_size, bpr = (ks + 7) / 8;
+    double *d_yaw = nullptr;
+    unsigned char *d_cells = nullptr;
+    CK(cudaMalloc(&d_yaw, K * sizeof(double)));
+    cudaError_t e = cudaMalloc(&d_cells, (size_t)K * ks * ks);
+    if (e != cudaSuccess) { cudaFree(d_yaw); ctx->err = cudaGetErrorString(e); return SVSDF_ERR_CUDA; }
+    ctx->front_cells.assign((size_t)K * ks * ks, 0);
+    e = cudaMemcpyAsync(d_yaw, ctx->front_yaw.data(), K * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = launch_front_cells(ctx->shape, F, d_yaw, d_cells, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ctx->front_cells.data(), d_cells, ctx->front_cells.size(), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_yaw); cudaFree(d_cells);
+    if (e != cudaSuccess) { ctx->err = std::string("svsdf_front_init: ") + cudaGetErrorString(e); return SVSDF_ERR_CUDA; }
+    ctx->launches += 1;
+    // generateByteKernel (Shape.hpp:194-216) + the same rows as 32-bit masks (bit 31 - b <-> column b)
+    static const unsigned char or_mask[8] = {0x80, 0x40, 0x20, 0x10, 0x08, 0x04, 0x02, 0x01};
+    ctx->front_bytes.assign((size_t)K * ks * bpr, 0);
+    std::vector<unsigned> rowmask((size_t)K * ks, 0u);
+    for (int k = 0; k < K; ++k)
+        for (int a = 0; a < ks; ++a)
+            for (int b = 0; b < ks; ++b)
+                if (ctx->front_cells[((size_t)k * ks + a) * ks + b]) {
+                    ctx->front_bytes[((size_t)k * ks + a) * bpr + b / 8] |= or_mask[b % 8];
+                    rowmask[(size_t)k * ks + a] |= 0x80000000u >> b;
+                }
+    cudaFree(ctx->d_front_bytes); cudaFree(ctx->d_front_rowmask);
+    ctx->d_front_bytes = nullptr; ctx->d_front_rowmask = nullptr;
+    CK(cudaMalloc(&ctx->d_front_bytes, ctx->front_bytes.size()));
+    CK(cudaMalloc(&ctx->d_front_rowmask, rowmask.size() * sizeof(unsigned)));
+    CK(cudaMemcpy(ctx->d_front_bytes, ctx->front_bytes.data(), ctx->front_bytes.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_front_rowmask, rowmask.data(), rowmask.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+    ctx->front = F;
+    ctx->front_ready = true;
+    return SVSDF_OK;
+}
+
+int svsdf_front_get_kernels(svsdf_ctx *ctx, double *yaw_out, unsigned char *cells_out, unsigned char *bytes_out) {
+    if (!ctx) return SVSDF_ERR_INVALID;
+    if (!ctx->front_ready) { ctx->err = "svsdf_front_get_kernels: call svsdf_front_init first"; return SVSDF_ERR_NOT_READY; }
+    if (yaw_out) std::memcpy(yaw_out, ctx->front_yaw.data(), ctx->front_yaw.size() * sizeof(double));
+    if (cells_out) std::memcpy(cells_out, ctx->front_cells.data(), ctx->front_cells.size());
+    if (bytes_out) std::memcpy(bytes_out, ctx->front_bytes.data(), ctx->front_bytes.size());
+    return SVSDF_OK;
+}
+
+static int front_params_with_map(svsdf_ctx *ctx, FrontParams &F, const char *who) {
+    if (!ctx->front_ready) { ctx->err = std::string(who) + ": call svsdf_front_init first"; return SVSDF_ERR_NOT_READY; }
+    if (!ctx->d_map) { ctx->err = std::string(who) + ": map not set (svsdf_set_map)"; return SVSDF_ERR_NOT_READY; }
+    F = ctx->front;
+    F.X = ctx->map_X; F.Y = ctx->map_Y; F.h = ctx->map_h; F.row_bytes = ctx->map_row_bytes;
+    F.out_words = (ctx->map_Y + 31) / 32;
+    if (F.h != (F.kernel_size - 1) / 2) {
+        ctx->err = std::string(who) + ": the map was packed for another kernel_size (its inflation must be (kernel_size - 1) / 2)";
+        return SVSDF_ERR_INVALID;
+    }
+    return SVSDF_OK;
+}
+
+int svsdf_front_cspace(svsdf_ctx *ctx, uint32_t *words_out, float *ms_out, const uint32_t **dev_words_out) {
+    if (!ctx) return SVSDF_ERR_INVALID;
+    FrontParams F;
+    int rc = front_params_with_map(ctx, F, "svsdf_front_cspace");
+    if (rc != SVSDF_OK) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)F.kernel_count * F.X * F.out_words;
+    if (n > ctx->cap_cspace) {
+        cudaFree(ctx->d_cspace);
+        ctx->d_cspace = nullptr;
+        ctx->cap_cspace = 0;
+        CK(cudaMalloc(&ctx->d_cspace, n * sizeof(unsigned)));
+        ctx->cap_cspace = n;
+    }
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(launch_front_cspace(F, ctx->d_map, ctx->d_front_rowmask, ctx->d_cspace, ctx->stream));
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->launches += 1;
+    if (words_out) CK(cudaMemcpyAsync(words_out, ctx->d_cspace, n * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ms_out) CK(cudaEventElapsedTime(ms_out, ctx->ev0, ctx->ev1));
+    if (dev_words_out) *dev_words_out = ctx->d_cspace;
+    return SVSDF_OK;
+}
+
+int svsdf_front_check_kernel_value(svsdf_ctx *ctx, int64_t n, const double *father_yaw, const int32_t *ind_xy, unsigned char *ok_out,
+                                   double *child_yaw_out) {
+    if (!ctx || n < 0 || (n > 0 && (!father_yaw || !ind_xy || !ok_out || !child_yaw_out))) return SVSDF_ERR_INVALID;
+    FrontParams F;
+    int rc = front_params_with_map(ctx, F, "svsdf_front_check_kernel_value");
+    if (rc != SVSDF_OK) return rc;
+    if (n == 0) return SVSDF_OK;
+    for (int64_t i = 0; i < n; ++i)
+        if (ind_xy[2 * i] < 0 || ind_xy[2 * i] >= F.X || ind_xy[2 * i + 1] < 0 || ind_xy[2 * i + 1] >= F.Y) {
+            ctx->err = "svsdf_front_check_kernel_value: cell index outside the map";
+            return SVSDF_ERR_INVALID;
+        }
+    CK(cudaSetDevice(ctx->device));
+    double *d_fy = nullptr, *d_cy = nullptr;
+    int *d_ind = nullptr;
+    unsigned char *d_ok = nullptr;
+    cudaError_t e = cudaMalloc(&d_fy, n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_cy, n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_ind, 2 * n * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&d_ok, n);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_fy, father_yaw, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_ind, ind_xy, 2 * n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = launch_front_check(F, ctx->d_map, ctx->d_front_bytes, n, d_fy, d_ind, d_ok, d_cy, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ok_out, d_ok, n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(child_yaw_out, d_cy, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_fy); cudaFree(d_cy); cudaFree(d_ind); cudaFree(d_ok);
+    if (e != cudaSuccess) { ctx->err = std::string("svsdf_front_check_kernel_value: ") + cudaGetErrorString(e); return SVSDF_ERR_CUDA; }
+    ctx->launches += 1;
+    return SVSDF_OK;
+}
 
 int svsdf_create(const svsdf_config *cfg, svsdf_ctx **out) {
     if (!cfg || !out) return SVSDF_ERR_INVALID;
@@ -620,6 +772,7 @@ void svsdf_destroy(svsdf_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->own_points) cudaFree(ctx->d_points);
     cudaFree(ctx->d_mesh_tri);
+    cudaFree(ctx->d_front_bytes); cudaFree(ctx->d_front_rowmask); cudaFree(ctx->d_cspace);
     cudaFree(ctx->d_flag); cudaFree(ctx->d_inside_tstar); cudaFree(ctx->d_inside_list);
     cudaFree(ctx->d_gsip_contrib); cudaFree(ctx->d_gsip_piece); cudaFree(ctx->d_n_inside);
     cudaFree(ctx->d_eval_counter); cudaFree(ctx->d_tot); cudaFree(ctx->d_ticket); cudaFree(ctx->d_blob); cudaFree(ctx->d_partials); cudaFree(ctx->d_out);

@@ -139,4 +139,14 @@ struct ExtractArgs {
     double keepout[2 * kMaxKeepout];
 };
 
+// K5 (svsdf_frontend.cu): collision kernels of the A* front end
+constexpr int kMaxYawKernels = 64;
+constexpr int kMaxKernelSize = 32;  // kernel rows are held as 32-bit masks
+struct FrontParams {
+    int kernel_size, kernel_count;
+    double res, safemargin;      // kernelresu (occupancy_resolution), max(front_end_safeh, res / 2)
+    int X, Y, h, row_bytes;      // map (svsdf_set_map)
+    int out_words;               // 32-cell words per output row: ceil(Y / 32)
+};
+
 }  // namespace svsdf

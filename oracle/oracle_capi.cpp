@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 
+#include "frontend_oracle.hpp"
 #include "minco_oracle.hpp"
 
 using namespace oracle;
@@ -79,6 +80,41 @@ void *orc_create_mesh(const double *poly_params, const double *V, int nv, const 
     o->cp.threads = threads > 0 ? threads : 1;
     o->rho = rho;
     return o;
+}
+
+// ---- A* front-end collision kernels (frontend_oracle.hpp) ----
+void orc_shape_kernels(const char *name, const double *poly_params, int ks, int K, double res, double safeh, double *yaw_out,
+                       uint8_t *cells_out, uint8_t *bytes_out) {
+    Shape S = make_shape(name, poly_params, nullptr, 0);
+    ShapeKernels SK = init_shape_kernels(S, ks, K, res, safeh);
+    std::memcpy(yaw_out, SK.yaw.data(), SK.yaw.size() * sizeof(double));
+    std::memcpy(cells_out, SK.cells.data(), SK.cells.size());
+    std::memcpy(bytes_out, SK.bytes.data(), SK.bytes.size());
+}
+// free-space map of the whole configuration space: out[k][x][y] = kernelConv(k, (x, y)); variant 0 bool kernels, 1 byte kernels
+void orc_cspace(const char *name, const double *poly_params, int ks, int K, double res, double safeh, const uint8_t *occ, int X,
+                int Y, int variant, uint8_t *out) {
+    Shape S = make_shape(name, poly_params, nullptr, 0);
+    ShapeKernels SK = init_shape_kernels(S, ks, K, res, safeh);
+    FrontMap M;
+    M.build(occ, X, Y, ks);
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int k = 0; k < K; ++k)
+        for (int x = 0; x < X; ++x)
+            for (int y = 0; y < Y; ++y)
+                out[((size_t)k * X + x) * Y + y] = variant ? kernel_conv_byte(SK, M, k, x, y) : kernel_conv_bool(SK, M, k, x, y);
+}
+void orc_check_kernel_value(const char *name, const double *poly_params, int ks, int K, double res, double safeh, const uint8_t *occ,
+                            int X, int Y, int64_t n, const double *father_yaw, const int *ind_xy, uint8_t *ok_out, double *child_yaw_out) {
+    Shape S = make_shape(name, poly_params, nullptr, 0);
+    ShapeKernels SK = init_shape_kernels(S, ks, K, res, safeh);
+    FrontMap M;
+    M.build(occ, X, Y, ks);
+    for (int64_t i = 0; i < n; ++i) {
+        double cy = father_yaw[i];
+        ok_out[i] = check_kernel_value(SK, M, father_yaw[i], cy, ind_xy[2 * i], ind_xy[2 * i + 1]);
+        child_yaw_out[i] = cy;
+    }
 }
 
 void *orc_create(const char *name, const double *poly_params, const double *poly_xy, int poly_n, double weight_p,

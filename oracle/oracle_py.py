@@ -79,6 +79,11 @@ def lib(variant: str = "default"):
         L.orc_mesh_eval.argtypes = [dp, dp, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int64, dp, dp]
         L.orc_create_mesh.restype = C.c_void_p
         L.orc_create_mesh.argtypes = [dp, dp, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int]
+        u8 = C.POINTER(C.c_uint8)
+        L.orc_shape_kernels.argtypes = [C.c_char_p, dp, C.c_int, C.c_int, C.c_double, C.c_double, dp, u8, u8]
+        L.orc_cspace.argtypes = [C.c_char_p, dp, C.c_int, C.c_int, C.c_double, C.c_double, u8, C.c_int, C.c_int, C.c_int, u8]
+        L.orc_check_kernel_value.argtypes = [C.c_char_p, dp, C.c_int, C.c_int, C.c_double, C.c_double, u8, C.c_int, C.c_int, C.c_int64, dp,
+                                             C.POINTER(C.c_int), u8, dp]
         L.orc_max_threads.restype = C.c_int
         L.orc_num_procs.restype = C.c_int
         _libs[variant] = L
@@ -126,6 +131,45 @@ def mesh_eval(mesh, rel, what="sdf", poly_params=(0.0, 0.0, 0.0)):
     pp = _f64(poly_params)
     lib().orc_mesh_eval(_p(pp), _p(V), V.shape[0], F.ctypes.data_as(C.c_void_p), F.shape[0], code, rel.shape[0], _p(rel), _p(out))
     return out
+
+
+def _u8p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def shape_kernels(name, kernel_size=17, kernel_count=18, res=1.0, safeh=0.0, poly_params=(0.0, 0.0, 0.0)):
+    """BasicShape::initShape: (yaw [K], bool kernels [K, ks, ks], byte kernels [K, ks, ceil(ks / 8)])."""
+    pp = _f64(poly_params)
+    bpr = (kernel_size + 7) // 8
+    yaw = np.empty(kernel_count)
+    cells = np.zeros((kernel_count, kernel_size, kernel_size), dtype=np.uint8)
+    byt = np.zeros((kernel_count, kernel_size, bpr), dtype=np.uint8)
+    lib().orc_shape_kernels(name.encode(), _p(pp), kernel_size, kernel_count, res, safeh, _p(yaw), _u8p(cells), _u8p(byt))
+    return yaw, cells.astype(bool), byt
+
+
+def cspace(name, occ, kernel_size=17, kernel_count=18, res=1.0, safeh=0.0, variant="byte", poly_params=(0.0, 0.0, 0.0)):
+    """kernelConv over every (yaw kernel, cell): bool array [K, X, Y], True = the shape kernel meets no occupied cell."""
+    occ = np.ascontiguousarray(occ, dtype=np.uint8)
+    X, Y = occ.shape
+    pp = _f64(poly_params)
+    out = np.zeros((kernel_count, X, Y), dtype=np.uint8)
+    lib().orc_cspace(name.encode(), _p(pp), kernel_size, kernel_count, res, safeh, _u8p(occ), X, Y, 1 if variant == "byte" else 0, _u8p(out))
+    return out.astype(bool)
+
+
+def check_kernel_value(name, occ, father_yaw, ind_xy, kernel_size=17, kernel_count=18, res=1.0, safeh=0.0, poly_params=(0.0, 0.0, 0.0)):
+    """SweptVolumeManager::checkKernelValue for a batch: (ok [n] bool, child_yaw [n])."""
+    occ = np.ascontiguousarray(occ, dtype=np.uint8)
+    X, Y = occ.shape
+    pp = _f64(poly_params)
+    fy = _f64(father_yaw)
+    ind = np.ascontiguousarray(ind_xy, dtype=np.int32).reshape(-1, 2)
+    ok = np.zeros(fy.shape[0], dtype=np.uint8)
+    cy = np.empty(fy.shape[0])
+    lib().orc_check_kernel_value(name.encode(), _p(pp), kernel_size, kernel_count, res, safeh, _u8p(occ), X, Y, fy.shape[0], _p(fy),
+                                 ind.ctypes.data_as(C.POINTER(C.c_int)), _u8p(ok), _p(cy))
+    return ok.astype(bool), cy
 
 
 def minco_forward(init_s, final_s, q, T):
