@@ -1,0 +1,40 @@
+"""K5 measurement: configuration-space obstacle map (kernelConv for every yaw kernel and cell) of the batch mode's map
+(60 m at 0.025 m = 2400 x 2400 cells, 18 yaw kernels of 17 x 17) on one GPU, next to the oracle's restatement of the
+reference's kernelConv<true> on the host cores (a crop, scaled).  Prints one JSON line."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from implicit_svsdf_planner_b200 import api, batch
+from oracle import oracle_py as O
+
+ks, K, res = 17, 18, 0.025
+gm = batch.make_random_map(extent=60.0, res=res, density=float(os.environ.get("SVSDF_DENSITY", "0.27")), seed=20240502)
+X, Y = gm.shape
+ctx = api.Context("star")
+t0 = time.perf_counter(); ctx.front_init(ks, K, res, 0.0); t_init = time.perf_counter() - t0
+ctx.set_map(batch.pack_map_kernel(gm.occ, ks), X, Y, ks, (0.0, 0.0), res)
+for _ in range(3):
+    ctx.front_cspace(X, Y, fetch=False)
+ms = [ctx.front_cspace(X, Y, fetch=False)[1] for _ in range(20)]
+ms_med = float(np.median(ms))
+W = (Y + 31) // 32
+out_bytes = K * X * W * 4
+in_bytes = (X + ks - 1) * ((Y + ks - 1 + 7) // 8)
+peaks = {}
+pp = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+if os.path.exists(pp):
+    peaks = json.load(open(pp))
+hbm = peaks.get("hbm_gbs", 6650.0)
+# CPU: the oracle's kernelConv<true> over a crop, all host threads (OpenMP), scaled by cell count
+n = 400
+crop = gm.occ[:n, :n]
+t0 = time.perf_counter(); O.cspace("star", crop, ks, K, res, 0.0, variant="byte"); t_cpu = time.perf_counter() - t0
+cells = K * X * Y
+rec = {"kernel": "k_cspace", "map_cells": [X, Y], "yaw_kernels": K, "kernel_size": ks, "gpu_ms": ms_med, "gpu_ms_min": float(min(ms)),
+       "kernel_conv_per_s_gpu": cells / (ms_med * 1e-3), "front_init_s": t_init,
+       "roofline": {"bound": "hbm", "algorithmic_bytes": out_bytes + in_bytes, "achieved": (out_bytes + in_bytes) / (ms_med * 1e-3) / 1e9,
+                    "peak": hbm, "unit": "GB/s", "frac": (out_bytes + in_bytes) / (ms_med * 1e-3) / 1e9 / hbm,
+                    "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"},
+       "cpu": {"kernel_conv_per_s": K * n * n / t_cpu, "threads": O.num_procs(), "sample": f"{n} x {n} crop, {K} kernels, oracle kernelConv<true> restatement"},
+       "speedup": (cells / (ms_med * 1e-3)) / (K * n * n / t_cpu)}
+print(json.dumps(rec))
