@@ -88,7 +88,7 @@ EXPORTED_SYMBOLS = [
     "svsdf_shape_sdf", "svsdf_shape_grad1", "svsdf_cost_grad_device", "svsdf_kernel_launches",
     "svsdf_executed_evals", "svsdf_fp64_peak", "svsdf_device_ptr_points", "svsdf_lbfgs_minimize", "svsdf_last_kernel_ms", "svsdf_sincos", "svsdf_set_map", "svsdf_set_map_device",
     "svsdf_extract_points", "svsdf_get_points", "svsdf_read_obj", "svsdf_free",
-    "svsdf_front_init", "svsdf_front_get_kernels", "svsdf_front_cspace", "svsdf_front_check_kernel_value",
+    "svsdf_front_init", "svsdf_front_get_kernels", "svsdf_front_cspace", "svsdf_front_check_kernel_value", "svsdf_front_expand",
 ]
 
 
@@ -116,6 +116,7 @@ def lib():
     L.svsdf_front_get_kernels.argtypes = [vp, dp, vp, vp]
     L.svsdf_front_cspace.argtypes = [vp, vp, C.POINTER(C.c_float), C.POINTER(vp)]
     L.svsdf_front_check_kernel_value.argtypes = [vp, C.c_int64, dp, vp, vp, dp]
+    L.svsdf_front_expand.argtypes = [vp, C.c_int64, vp, dp, vp, dp, vp]
     L.svsdf_set_points.argtypes = [vp, dp, C.c_int64, C.c_int]
     L.svsdf_set_points_device.argtypes = [vp, vp, C.c_int64]
     L.svsdf_set_traj.argtypes = [vp, C.c_int, dp, dp]
@@ -459,6 +460,19 @@ class Context:
         self._ck(lib().svsdf_front_check_kernel_value(self.h, fy.size, _p(fy), ind.ctypes.data_as(C.c_void_p), ok.ctypes.data_as(C.c_void_p), _p(cy)),
                  "svsdf_front_check_kernel_value")
         return ok.astype(bool), cy
+
+    def front_expand(self, node_ij, node_yaw):
+        """The neighbour loop of the A* `process` step (front_end_Astar.hpp:192-240) for n nodes:
+        (ok [n, 9] bool, child_yaw [n, 9], parts [n, 9])."""
+        ij = np.ascontiguousarray(node_ij, dtype=np.int32).reshape(-1, 2)
+        fy = _f64(node_yaw).reshape(-1)
+        n = fy.size
+        ok = np.zeros((n, 9), dtype=np.uint8)
+        cy = np.zeros((n, 9))
+        parts = np.zeros((n, 9), dtype=np.uint8)
+        self._ck(lib().svsdf_front_expand(self.h, n, ij.ctypes.data_as(C.c_void_p), _p(fy), ok.ctypes.data_as(C.c_void_p), _p(cy),
+                                          parts.ctypes.data_as(C.c_void_p)), "svsdf_front_expand")
+        return ok.astype(bool), cy, parts
 
     def sincos(self, x):
         x = _f64(x).reshape(-1)

@@ -142,6 +142,121 @@ __global__ void __launch_bounds__(128) k_check_kernel_value(FrontParams F, const
     child_yaw_out[q] = ok ? (2 * pi * (ret) / count - pi) : fy;
 }
 
+__device__ __forceinline__ bool map_occupied(const FrontParams &F, const unsigned char *map, int i, int j) {
+    const int c = j + F.h;
+    return (__ldg(map + (int64_t)(i + F.h) * F.row_bytes + (c >> 3)) & (0x80u >> (c & 7))) != 0;
+}
+
+// GridMap3D::getGridIndex after projInMap (Gridmap3D.cpp:137-172, PCSmap_manager.h:126-133), one axis
+__device__ __forceinline__ int grid_index_1d(double p, double lo, double hi, double res, int size) {
+    if (p < lo) p = lo;
+    if (p > hi) p = hi;
+    int i = (int)floor((p - lo) / res);
+    if (i < 0) i = 0;
+    if (i >= size) i = size - 1;
+    return i;
+}
+
+// The neighbour loop of AstarPathSearcher::process (front_end_Astar.hpp:192-240), one warp per (node, neighbour cell):
+//   cond = isIndexValid(vi) && !isIndexOccupiedFlate(vi, 0) && checkKernelValue(fy, cy, vi) && checkSubSWCollision(state1, state2, aabb)
+// The kernel test is the literal byte-wise one (all lanes in lockstep); the sub-swept-volume test (sw_manager.hpp:1171-1210)
+// spreads the occupied cells of the box around the child (getPointsInAABB2D, PCSmap_manager.h:137-158) over the lanes,
+// each lane walking the kt samples of its cell.
+template <int SHAPE, bool XFORM>
+__global__ void __launch_bounds__(256) k_expand_nodes(const __grid_constant__ ShapeParams S, const __grid_constant__ FrontParams F,
+                                                      const __grid_constant__ SubSwParams P, const unsigned char *map,
+                                                      const unsigned char *kbytes, int64_t n, const int *node_ij, const double *node_yaw,
+                                                      unsigned char *ok_out, double *child_yaw_out, unsigned char *parts_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= 9 * n) return;
+    const int64_t q = w / 9;
+    const int nb = (int)(w % 9);
+    const int ix = node_ij[2 * q], iy = node_ij[2 * q + 1];
+    const int vx = ix + (nb / 3 - 1), vy = iy + (nb % 3 - 1);
+    const double fy = node_yaw[q];
+    double cy = fy;
+    unsigned parts = 0;
+    const bool valid = vx >= 0 && vx < F.X && vy >= 0 && vy < F.Y;
+    if (valid) {
+        if (!map_occupied(F, map, vx, vy)) parts |= 1u;
+        // checkKernelValue (sw_manager.hpp:1158-1169) -> visit_kernels_by_distance (:1099-1156)
+        {
+            const double pi = 3.1415926536;
+            const int count = F.kernel_count;
+            int father_i = int(count * ((fy + pi) / (2 * pi)));
+            father_i = father_i < 0 ? 0 : (father_i >= count ? count - 1 : father_i);
+            unsigned long long visited = 1ull << father_i;
+            int queue[24];
+            int head = 0, tail = 0, deep = 0;
+            queue[tail++] = father_i;
+            while (head < tail) {
+                deep++;
+                const int x = queue[head++];
+                if (kernel_conv_byte(F, map, kbytes, x, vx, vy)) {
+                    cy = 2 * pi * (x) / count - pi;
+                    parts |= 2u;
+                    break;
+                }
+#pragma unroll
+                for (int d = 0; d < 2; ++d) {
+                    int nx = x + (d == 0 ? -1 : 1);
+                    if (nx < 0) nx = count - 1;
+                    if (nx >= count) nx = 0;
+                    if ((visited >> nx) & 1ull) continue;
+                    visited |= 1ull << nx;
+                    if (tail < 24) queue[tail++] = nx;
+                }
+                if (deep > 10) break;
+            }
+        }
+        // checkSubSWCollision(state1 = (father centre, fy), state2 = (child centre, cy), points in the box around the child)
+        const double f0 = (ix + 0.5) * F.map_res + F.ox, f1 = (iy + 0.5) * F.map_res + F.oy;
+        const double c0 = (vx + 0.5) * F.map_res + F.ox, c1 = (vy + 0.5) * F.map_res + F.oy;
+        const double xmax = F.ox + F.X * F.map_res, ymax = F.oy + F.Y * F.map_res;
+        const int i1 = grid_index_1d(c0 - P.half_box, F.ox, xmax, F.map_res, F.X), i2 = grid_index_1d(c0 + P.half_box, F.ox, xmax, F.map_res, F.X);
+        const int j1 = grid_index_1d(c1 - P.half_box, F.oy, ymax, F.map_res, F.Y), j2 = grid_index_1d(c1 + P.half_box, F.oy, ymax, F.map_res, F.Y);
+        const int nj = j2 - j1 + 1, cells = (i2 - i1 + 1) * nj;
+        bool hit = false;
+        for (int base = 0; base < cells && !hit; base += 32) {
+            const int c = base + lane;
+            bool mine = false;
+            if (c < cells) {
+                const int i = i1 + c / nj, j = j1 + c % nj;
+                if (map_occupied(F, map, i, j)) {
+                    const double px = (i + 0.5) * F.map_res + F.ox, py = (j + 0.5) * F.map_res + F.oy;
+                    for (int t = 0; t < P.nkt && !mine; ++t) {
+                        const double kt = P.kt[t], om = 1 - kt;
+                        const double lx = kt * c0 + om * f0, ly = kt * c1 + om * f1, yaw = kt * cy + om * fy;
+                        double sn, cs;
+                        dev::sincos_portable(yaw, sn, cs);
+                        const double d0 = px - lx, d1 = py - ly;
+                        const double rx = cs * d0 + sn * d1, ry = -sn * d0 + cs * d1;
+                        mine = dev::shape_sdf<SHAPE, XFORM>(S, rx, ry) < 0;
+                    }
+                }
+            }
+            hit = __any_sync(0xffffffffu, mine);
+        }
+        if (!hit) parts |= 4u;
+    }
+    if (lane == 0) {
+        ok_out[w] = (parts == 7u) ? 1 : 0;
+        child_yaw_out[w] = cy;
+        if (parts_out) parts_out[w] = (unsigned char)parts;
+    }
+}
+
+template <int SHAPE, bool XFORM>
+cudaError_t launch_expand_t(const ShapeParams &S, const FrontParams &F, const SubSwParams &P, const unsigned char *map, const unsigned char *kbytes,
+                            int64_t n, const int *node_ij, const double *node_yaw, unsigned char *ok_out, double *child_yaw_out,
+                            unsigned char *parts_out, cudaStream_t st) {
+    const int64_t threads = 9 * n * 32;
+    k_expand_nodes<SHAPE, XFORM><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(S, F, P, map, kbytes, n, node_ij, node_yaw, ok_out,
+                                                                                     child_yaw_out, parts_out);
+    return cudaGetLastError();
+}
+
 template <int SHAPE, bool XFORM>
 cudaError_t launch_cells_t(const ShapeParams &S, const FrontParams &F, const double *yaws, unsigned char *cells, cudaStream_t st) {
     const int n = F.kernel_count * F.kernel_size * F.kernel_size;
@@ -174,6 +289,37 @@ cudaError_t launch_front_cells(const ShapeParams &S, const FrontParams &F, const
         SVSDF_CASE(SH_CIRCLE)
 #undef SVSDF_CASE
         default: return cudaErrorInvalidValue;  // Polygon / mesh: the reference defines no rotated kernels for them
+    }
+}
+
+cudaError_t launch_front_expand(const ShapeParams &S, const FrontParams &F, const SubSwParams &P, const unsigned char *map,
+                                const unsigned char *kbytes, int64_t n, const int *node_ij, const double *node_yaw, unsigned char *ok_out,
+                                double *child_yaw_out, unsigned char *parts_out, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    switch (S.id) {
+#define SVSDF_CASE(ID)                                                                                                              \
+    case ID:                                                                                                                        \
+        return S.has_xform ? launch_expand_t<ID, true>(S, F, P, map, kbytes, n, node_ij, node_yaw, ok_out, child_yaw_out, parts_out, st) \
+                           : launch_expand_t<ID, false>(S, F, P, map, kbytes, n, node_ij, node_yaw, ok_out, child_yaw_out, parts_out, st);
+        SVSDF_CASE(SH_STAR)
+        SVSDF_CASE(SH_HORSESHOE)
+        SVSDF_CASE(SH_PIE)
+        SVSDF_CASE(SH_PIE2)
+        SVSDF_CASE(SH_ARC)
+        SVSDF_CASE(SH_TUNNEL)
+        SVSDF_CASE(SH_CUTDISK)
+        SVSDF_CASE(SH_TRAPEZOID)
+        SVSDF_CASE(SH_RHOMBUS)
+        SVSDF_CASE(SH_HEART)
+        SVSDF_CASE(SH_ROUNDEDX)
+        SVSDF_CASE(SH_BIGX)
+        SVSDF_CASE(SH_ROUNDEDCROSS)
+        SVSDF_CASE(SH_VESICA)
+        SVSDF_CASE(SH_MOON)
+        SVSDF_CASE(SH_UNEVENCAPSULE)
+        SVSDF_CASE(SH_CIRCLE)
+#undef SVSDF_CASE
+        default: return cudaErrorInvalidValue;
     }
 }
 

@@ -621,6 +621,7 @@ static int front_params_with_map(svsdf_ctx *ctx, FrontParams &F, const char *who
     F = ctx->front;
     F.X = ctx->map_X; F.Y = ctx->map_Y; F.h = ctx->map_h; F.row_bytes = ctx->map_row_bytes;
     F.out_words = (ctx->map_Y + 31) / 32;
+    F.ox = ctx->map_ox; F.oy = ctx->map_oy; F.map_res = ctx->map_res;
     if (F.h != (F.kernel_size - 1) / 2) {
         ctx->err = std::string(who) + ": the map was packed for another kernel_size (its inflation must be (kernel_size - 1) / 2)";
         return SVSDF_ERR_INVALID;
@@ -650,6 +651,43 @@ int svsdf_front_cspace(svsdf_ctx *ctx, uint32_t *words_out, float *ms_out, const
     CK(cudaStreamSynchronize(ctx->stream));
     if (ms_out) CK(cudaEventElapsedTime(ms_out, ctx->ev0, ctx->ev1));
     if (dev_words_out) *dev_words_out = ctx->d_cspace;
+    return SVSDF_OK;
+}
+
+int svsdf_front_expand(svsdf_ctx *ctx, int64_t n, const int32_t *node_ij, const double *node_yaw, unsigned char *ok_out, double *child_yaw_out,
+                       unsigned char *parts_out) {
+    if (!ctx || n < 0 || (n > 0 && (!node_ij || !node_yaw || !ok_out || !child_yaw_out))) return SVSDF_ERR_INVALID;
+    FrontParams F;
+    int rc = front_params_with_map(ctx, F, "svsdf_front_expand");
+    if (rc != SVSDF_OK) return rc;
+    if (n == 0) return SVSDF_OK;
+    for (int64_t i = 0; i < n; ++i)
+        if (node_ij[2 * i] < 0 || node_ij[2 * i] >= F.X || node_ij[2 * i + 1] < 0 || node_ij[2 * i + 1] >= F.Y) {
+            ctx->err = "svsdf_front_expand: node index outside the map";
+            return SVSDF_ERR_INVALID;
+        }
+    SubSwParams P{};
+    P.half_box = (double)(F.kernel_size / 2 + 1);
+    for (double kt = 0.0; kt <= 1.0 && P.nkt < 64; kt += 0.02) P.kt[P.nkt++] = kt;  // sw_manager.hpp:1190
+    CK(cudaSetDevice(ctx->device));
+    int *d_ij = nullptr;
+    double *d_fy = nullptr, *d_cy = nullptr;
+    unsigned char *d_ok = nullptr, *d_parts = nullptr;
+    cudaError_t e = cudaMalloc(&d_ij, 2 * n * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&d_fy, n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_cy, 9 * n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&d_ok, 9 * n);
+    if (e == cudaSuccess) e = cudaMalloc(&d_parts, 9 * n);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_ij, node_ij, 2 * n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_fy, node_yaw, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = launch_front_expand(ctx->shape, F, P, ctx->d_map, ctx->d_front_bytes, n, d_ij, d_fy, d_ok, d_cy, d_parts, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ok_out, d_ok, 9 * n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(child_yaw_out, d_cy, 9 * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && parts_out) e = cudaMemcpyAsync(parts_out, d_parts, 9 * n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_ij); cudaFree(d_fy); cudaFree(d_cy); cudaFree(d_ok); cudaFree(d_parts);
+    if (e != cudaSuccess) { ctx->err = std::string("svsdf_front_expand: ") + cudaGetErrorString(e); return SVSDF_ERR_CUDA; }
+    ctx->launches += 1;
     return SVSDF_OK;
 }
 

@@ -147,6 +147,13 @@ struct FrontParams {
     double res, safemargin;      // kernelresu (occupancy_resolution), max(front_end_safeh, res / 2)
     int X, Y, h, row_bytes;      // map (svsdf_set_map)
     int out_words;               // 32-cell words per output row: ceil(Y / 32)
+    double ox, oy, map_res;      // boundary_xyzmin (x, y) and grid resolution of the map
+};
+// k_expand_nodes: sample parameters of checkSubSWCollision (kt = 0, 0.02, ... accumulated on the host, <= 1)
+struct SubSwParams {
+    int nkt;
+    double half_box;             // kernel_size / 2 + 1 (integer division), world units (front_end_Astar.hpp:224)
+    double kt[64];
 };
 
 }  // namespace svsdf

@@ -14,6 +14,7 @@
 // The Polygon fallback is not covered: its rotated overload takes a Matrix2d and does not override the virtual the
 // reference's initShape calls (Shape.hpp:1477 vs :267), i.e. the reference itself has no defined kernels for it.
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <queue>
 #include <vector>
@@ -198,6 +199,88 @@ inline bool check_kernel_value(const ShapeKernels &K, const FrontMap &M, double 
         return true;
     }
     return false;
+}
+
+// ---- the second half of the A* node test: the sub-swept-volume between father and child ----
+// PCSmapManager::getPointsInAABB2D (map_manager/include/map_manager/PCSmap_manager.h:137-158) with projInMap (:126-133),
+// GridMap3D::getGridIndex / getGridCubeCenter (map_manager/src/Gridmap3D.cpp:137-195): occupied cell centres in the box
+struct MapGeom {
+    double ox = 0, oy = 0, res = 1;  // boundary_xyzmin (x, y), grid_resolution; boundary_xyzmax = min + size * res
+};
+inline int grid_index_1d(double p, double lo, double res, int size) {
+    int i = (int)std::floor((p - lo) / res);
+    if (i < 0) i = 0;
+    if (i >= size) i = size - 1;
+    return i;
+}
+inline void points_in_aabb2d(const FrontMap &M, const MapGeom &G, double cx, double cy, double hbx, double hby, std::vector<double> &xy) {
+    const double xmax = G.ox + M.X * G.res, ymax = G.oy + M.Y * G.res;
+    double x1 = cx - hbx, y1 = cy - hby, x2 = cx + hbx, y2 = cy + hby;
+    auto proj = [](double v, double lo, double hi) { if (v < lo) v = lo; if (v > hi) v = hi; return v; };
+    x1 = proj(x1, G.ox, xmax); x2 = proj(x2, G.ox, xmax);
+    y1 = proj(y1, G.oy, ymax); y2 = proj(y2, G.oy, ymax);
+    const int i1 = grid_index_1d(x1, G.ox, G.res, M.X), i2 = grid_index_1d(x2, G.ox, G.res, M.X);
+    const int j1 = grid_index_1d(y1, G.oy, G.res, M.Y), j2 = grid_index_1d(y2, G.oy, G.res, M.Y);
+    for (int i = i1; i <= i2; i++)
+        for (int j = j1; j <= j2; j++)
+            if (M.occ[(size_t)i * M.Y + j]) {
+                xy.push_back((i + 0.5) * G.res + G.ox);
+                xy.push_back((j + 0.5) * G.res + G.oy);
+            }
+}
+
+// SweptVolumeManager::checkSubSWCollision (sw_manager.hpp:1171-1210): every obstacle point must stay outside the shape
+// while the pose moves linearly (yaw included) from father to child, sampled at kt = 0, 0.02, ... (accumulated) <= 1
+inline bool check_sub_sw_collision(const Shape &S, const double father[3], const double child[3], const std::vector<double> &xy) {
+    const double dt = 0.02;
+    for (size_t i = 0; i + 1 < xy.size(); i += 2) {
+        const double px = xy[i], py = xy[i + 1];
+        double min_sdf = 1e9;
+        for (double kt = 0.0; kt <= 1.0; kt += dt) {
+            const double om = 1 - kt;
+            const double lx = kt * child[0] + om * father[0];
+            const double ly = kt * child[1] + om * father[1];
+            const double yaw = kt * child[2] + om * father[2];
+            double s, c;
+            psc::sincos(yaw, s, c);
+            const double d0 = px - lx, d1 = py - ly;
+            const double rx = c * d0 + s * d1, ry = -s * d0 + c * d1;  // posEva2Rel (:521-526)
+            const double f = shape_sdf(S, rx, ry, 0.0);
+            if (f < min_sdf) min_sdf = f;
+            if (min_sdf < 0) return false;
+        }
+    }
+    return true;
+}
+
+// The neighbour loop of AstarPathSearcher::process (planner_algorithm/include/planner_algorithm/front_end_Astar.hpp:192-240)
+// for one node (cell index, yaw): for each of the 9 cells (i, j) in -1..1:
+//   cond = isIndexValid(vi) && !isIndexOccupiedFlate(vi, 0) && checkKernelValue(fy, cy, vi) && checkSubSWCollision(state1, state2, aabb)
+// parts[n]: bit 0 valid and free, bit 1 kernel test, bit 2 sub-swept-volume test (each evaluated on its own, for tests);
+// ok = all three; child_yaw = the yaw checkKernelValue chose (father's yaw when it failed).
+inline void expand_node(const Shape &S, const ShapeKernels &K, const FrontMap &M, const MapGeom &G, int ix, int iy, double fy,
+                        int kernel_size_world, uint8_t ok[9], double child_yaw[9], uint8_t parts[9]) {
+    const double state1[3] = {(ix + 0.5) * G.res + G.ox, (iy + 0.5) * G.res + G.oy, fy};
+    const double hb = (double)(kernel_size_world / 2 + 1);  // `kernel_size/2+1`, integer division (front_end_Astar.hpp:224)
+    int n = 0;
+    for (int i = -1; i < 2; i++)
+        for (int j = -1; j < 2; j++, n++) {
+            const int vx = ix + i, vy = iy + j;
+            uint8_t p = 0;
+            double cy = fy;
+            const bool valid = M.valid(vx, vy);
+            if (valid && !M.occ[(size_t)vx * M.Y + vy]) p |= 1;
+            if (valid && check_kernel_value(K, M, fy, cy, vx, vy)) p |= 2;
+            if (valid) {
+                const double state2[3] = {(vx + 0.5) * G.res + G.ox, (vy + 0.5) * G.res + G.oy, cy};
+                std::vector<double> pts;
+                points_in_aabb2d(M, G, state2[0], state2[1], hb, hb, pts);
+                if (check_sub_sw_collision(S, state1, state2, pts)) p |= 4;
+            }
+            parts[n] = p;
+            ok[n] = (p == 7);
+            child_yaw[n] = cy;
+        }
 }
 
 }  // namespace oracle

@@ -117,6 +117,21 @@ void orc_check_kernel_value(const char *name, const double *poly_params, int ks,
     }
 }
 
+// A* neighbour loop for n nodes (front_end_Astar.hpp:192-240): ok / child_yaw / parts are [n][9]
+void orc_expand_nodes(const char *name, const double *poly_params, int ks, int K, double res_kernel, double safeh, const uint8_t *occ, int X,
+                      int Y, double ox, double oy, double map_res, int64_t n, const int *node_ij, const double *node_yaw, uint8_t *ok_out,
+                      double *child_yaw_out, uint8_t *parts_out) {
+    Shape S = make_shape(name, poly_params, nullptr, 0);
+    ShapeKernels SK = init_shape_kernels(S, ks, K, res_kernel, safeh);
+    FrontMap M;
+    M.build(occ, X, Y, ks);
+    MapGeom G;
+    G.ox = ox; G.oy = oy; G.res = map_res;
+#pragma omp parallel for schedule(dynamic)
+    for (int64_t q = 0; q < n; ++q)
+        expand_node(S, SK, M, G, node_ij[2 * q], node_ij[2 * q + 1], node_yaw[q], ks, ok_out + 9 * q, child_yaw_out + 9 * q, parts_out + 9 * q);
+}
+
 void *orc_create(const char *name, const double *poly_params, const double *poly_xy, int poly_n, double weight_p,
                  double safety_hor, double rho, int threads) {
     TrajOptimizerOracle *o = new TrajOptimizerOracle();

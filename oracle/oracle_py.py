@@ -84,6 +84,8 @@ def lib(variant: str = "default"):
         L.orc_cspace.argtypes = [C.c_char_p, dp, C.c_int, C.c_int, C.c_double, C.c_double, u8, C.c_int, C.c_int, C.c_int, u8]
         L.orc_check_kernel_value.argtypes = [C.c_char_p, dp, C.c_int, C.c_int, C.c_double, C.c_double, u8, C.c_int, C.c_int, C.c_int64, dp,
                                              C.POINTER(C.c_int), u8, dp]
+        L.orc_expand_nodes.argtypes = [C.c_char_p, dp, C.c_int, C.c_int, C.c_double, C.c_double, u8, C.c_int, C.c_int, C.c_double, C.c_double,
+                                       C.c_double, C.c_int64, C.POINTER(C.c_int), dp, u8, dp, u8]
         L.orc_max_threads.restype = C.c_int
         L.orc_num_procs.restype = C.c_int
         _libs[variant] = L
@@ -170,6 +172,24 @@ def check_kernel_value(name, occ, father_yaw, ind_xy, kernel_size=17, kernel_cou
     lib().orc_check_kernel_value(name.encode(), _p(pp), kernel_size, kernel_count, res, safeh, _u8p(occ), X, Y, fy.shape[0], _p(fy),
                                  ind.ctypes.data_as(C.POINTER(C.c_int)), _u8p(ok), _p(cy))
     return ok.astype(bool), cy
+
+
+def expand_nodes(name, occ, node_ij, node_yaw, origin=(0.0, 0.0), map_res=1.0, kernel_size=17, kernel_count=18, safeh=0.0,
+                 poly_params=(0.0, 0.0, 0.0)):
+    """The neighbour loop of the A* `process` step for n nodes: (ok [n, 9] bool, child_yaw [n, 9], parts [n, 9] bit mask:
+    1 valid and free, 2 kernel test, 4 sub-swept-volume test).  The shape kernels use the map resolution as cell size."""
+    occ = np.ascontiguousarray(occ, dtype=np.uint8)
+    X, Y = occ.shape
+    pp = _f64(poly_params)
+    ij = np.ascontiguousarray(node_ij, dtype=np.int32).reshape(-1, 2)
+    fy = _f64(node_yaw).reshape(-1)
+    n = fy.size
+    ok = np.zeros((n, 9), dtype=np.uint8)
+    cy = np.zeros((n, 9))
+    parts = np.zeros((n, 9), dtype=np.uint8)
+    lib().orc_expand_nodes(name.encode(), _p(pp), kernel_size, kernel_count, float(map_res), safeh, _u8p(occ), X, Y, float(origin[0]),
+                           float(origin[1]), float(map_res), n, ij.ctypes.data_as(C.POINTER(C.c_int)), _p(fy), _u8p(ok), _p(cy), _u8p(parts))
+    return ok.astype(bool), cy, parts
 
 
 def minco_forward(init_s, final_s, q, T):

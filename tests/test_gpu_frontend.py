@@ -112,3 +112,27 @@ def test_full_size_map_properties(oracle_mod):
     first = order[np.arange(m), hits.argmax(axis=1)]
     assert np.array_equal(cy[ok], (2 * pi * first / K - pi)[ok])
     ctx.close()
+
+
+@pytest.mark.parametrize("shape,pp", [("star", (0.0, 0.0, 0.0)), ("sdHorseshoe", (0.0, 0.0, 0.0)), ("sdTunnel", (0.3, -0.2, 20.0))])
+def test_expand_nodes_is_bitwise_the_oracles(oracle_mod, shape, pp):
+    """AstarPathSearcher::process neighbour loop (kernel test + sub-swept-volume test) for a batch of nodes."""
+    X, Y, ks, K, res = 70, 55, 17, 18, 1.0
+    occ = random_occ(X, Y, 0.012, 99)
+    origin = (-12.5, 3.25)
+    rng = np.random.default_rng(4)
+    n = 400
+    ij = np.stack([rng.integers(0, X, n), rng.integers(0, Y, n)], axis=1)
+    ij[:6] = [[0, 0], [X - 1, Y - 1], [0, Y - 1], [X - 1, 0], [X // 2, 0], [0, Y // 2]]  # map corners and edges
+    fy = rng.uniform(-3.14, 3.14, n)
+    ctx = api.Context(shape, poly_params=pp)
+    ctx.front_init(ks, K, res, 0.0)
+    ctx.set_map(batch.pack_map_kernel(occ, ks), X, Y, ks, origin, res)
+    ok, cy, parts = ctx.front_expand(ij, fy)
+    ok_o, cy_o, parts_o = oracle_mod.expand_nodes(shape, occ, ij, fy, origin=origin, map_res=res, kernel_size=ks, kernel_count=K, safeh=0.0,
+                                                  poly_params=pp)
+    assert np.array_equal(parts, parts_o), int((parts != parts_o).sum())
+    assert np.array_equal(ok, ok_o) and np.array_equal(cy, cy_o)
+    assert 0.05 < ok.mean() < 0.99  # the scene exercises both outcomes
+    assert len(np.unique(parts)) >= 4
+    ctx.close()

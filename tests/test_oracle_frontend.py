@@ -84,3 +84,25 @@ def test_check_kernel_value_search_order(oracle_mod):
         assert ok[q] == bool(hit)
         if hit:
             assert cy[q] == 2 * pi * hit[0] / K - pi
+
+
+def test_expand_nodes_semantics(oracle_mod):
+    # empty map: every in-map neighbour passes, the child keeps the father's yaw bin; out-of-map neighbours fail
+    occ = np.zeros((20, 20), bool)
+    ij = np.array([[0, 0], [10, 10], [19, 5]])
+    fy = np.array([0.3, -2.0, 3.0])
+    ok, cy, parts = oracle_mod.expand_nodes("star", occ, ij, fy, origin=(-5.0, 1.0), map_res=1.0)
+    assert ok[1].all() and (parts[1] == 7).all()
+    assert ok[0].reshape(3, 3)[1:, 1:].all() and not ok[0].reshape(3, 3)[0, :].any() and not ok[0].reshape(3, 3)[:, 0].any()
+    pi, K = 3.1415926536, 18
+    for q in range(3):
+        fi = int(K * ((fy[q] + pi) / (2 * pi)))
+        assert np.all(cy[q][ok[q]] == 2 * pi * fi / K - pi)
+    # a fully occupied map: nothing passes (cell occupied, kernel hits, obstacle points inside the shape)
+    ok, cy, parts = oracle_mod.expand_nodes("star", np.ones((20, 20), bool), ij, fy, map_res=1.0)
+    assert not ok.any() and (parts[1] == 0).all()
+    # one obstacle right next to the node: the sub-swept-volume test sees it even where the cell itself is free
+    occ = np.zeros((30, 30), bool)
+    occ[15, 17] = True
+    ok, cy, parts = oracle_mod.expand_nodes("star", occ, np.array([[15, 15]]), np.array([0.0]), map_res=1.0)
+    assert (parts[0] & 1).all() and not ok[0].all()
