@@ -37,4 +37,21 @@ rec = {"kernel": "k_cspace", "map_cells": [X, Y], "yaw_kernels": K, "kernel_size
                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"},
        "cpu": {"kernel_conv_per_s": K * n * n / t_cpu, "threads": O.num_procs(), "sample": f"{n} x {n} crop, {K} kernels, oracle kernelConv<true> restatement"},
        "speedup": (cells / (ms_med * 1e-3)) / (K * n * n / t_cpu)}
+# node expansion (AstarPathSearcher::process neighbour loop) for 4096 nodes at once — one node per problem of the batch mode —
+# on a front-end grid like the reference's (occupancy_resolution 1.0, 60 x 60 cells)
+rng = np.random.default_rng(7)
+occ2 = rng.random((60, 60)) < 0.03
+ctx2 = api.Context("star")
+ctx2.front_init(17, 18, 1.0, 0.0)
+ctx2.set_map(batch.pack_map_kernel(occ2, 17), 60, 60, 17, (0.0, 0.0), 1.0)
+ij = np.stack([rng.integers(0, 60, 4096), rng.integers(0, 60, 4096)], axis=1)
+fy = rng.uniform(-3.14, 3.14, 4096)
+ctx2.front_expand(ij, fy)
+t0 = time.perf_counter()
+for _ in range(10):
+    ok, cy, parts = ctx2.front_expand(ij, fy)
+t_gpu = (time.perf_counter() - t0) / 10
+t0 = time.perf_counter(); O.expand_nodes("star", occ2, ij, fy, map_res=1.0); t_cpu2 = time.perf_counter() - t0
+rec["expand"] = {"nodes": 4096, "gpu_ms_e2e": 1e3 * t_gpu, "cpu_ms": 1e3 * t_cpu2, "cpu_threads": O.num_procs(), "speedup": t_cpu2 / t_gpu,
+                 "pass_rate": float(ok.mean()), "note": "host buffers in and out (svsdf_front_expand), 9 neighbours per node"}
 print(json.dumps(rec))
