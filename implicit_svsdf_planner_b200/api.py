@@ -88,7 +88,7 @@ EXPORTED_SYMBOLS = [
     "svsdf_shape_sdf", "svsdf_shape_grad1", "svsdf_cost_grad_device", "svsdf_kernel_launches",
     "svsdf_executed_evals", "svsdf_fp64_peak", "svsdf_device_ptr_points", "svsdf_lbfgs_minimize", "svsdf_last_kernel_ms", "svsdf_sincos", "svsdf_set_map", "svsdf_set_map_device",
     "svsdf_extract_points", "svsdf_get_points", "svsdf_read_obj", "svsdf_free",
-    "svsdf_front_init", "svsdf_front_get_kernels", "svsdf_front_cspace", "svsdf_front_check_kernel_value", "svsdf_front_expand",
+    "svsdf_front_init", "svsdf_front_get_kernels", "svsdf_front_cspace", "svsdf_front_check_kernel_value", "svsdf_front_expand", "svsdf_front_astar",
 ]
 
 
@@ -117,6 +117,7 @@ def lib():
     L.svsdf_front_cspace.argtypes = [vp, vp, C.POINTER(C.c_float), C.POINTER(vp)]
     L.svsdf_front_check_kernel_value.argtypes = [vp, C.c_int64, dp, vp, vp, dp]
     L.svsdf_front_expand.argtypes = [vp, C.c_int64, vp, dp, vp, dp, vp]
+    L.svsdf_front_astar.argtypes = [vp, C.c_int, dp, dp, C.c_int, dp, vp, vp, C.POINTER(C.c_int64)]
     L.svsdf_set_points.argtypes = [vp, dp, C.c_int64, C.c_int]
     L.svsdf_set_points_device.argtypes = [vp, vp, C.c_int64]
     L.svsdf_set_traj.argtypes = [vp, C.c_int, dp, dp]
@@ -473,6 +474,20 @@ class Context:
         self._ck(lib().svsdf_front_expand(self.h, n, ij.ctypes.data_as(C.c_void_p), _p(fy), ok.ctypes.data_as(C.c_void_p), _p(cy),
                                           parts.ctypes.data_as(C.c_void_p)), "svsdf_front_expand")
         return ok.astype(bool), cy, parts
+
+    def front_astar(self, start_xy, goal_xy, max_path=1024):
+        """AstarPathSearch + getPath for n start/goal pairs in lock-step (one expand launch per iteration):
+        (paths: list of [len, 3] arrays or None, expansions [n], rounds)."""
+        st = _f64(start_xy).reshape(-1, 2)
+        go = _f64(goal_xy).reshape(-1, 2)
+        n = st.shape[0]
+        path = np.zeros((n, max_path, 3))
+        ln = np.zeros(n, dtype=np.int32)
+        ex = np.zeros(n, dtype=np.int32)
+        rounds = C.c_int64()
+        self._ck(lib().svsdf_front_astar(self.h, n, _p(st), _p(go), int(max_path), _p(path), ln.ctypes.data_as(C.c_void_p),
+                                         ex.ctypes.data_as(C.c_void_p), C.byref(rounds)), "svsdf_front_astar")
+        return [path[q, : ln[q]].copy() if ln[q] else None for q in range(n)], ex, rounds.value
 
     def sincos(self, x):
         x = _f64(x).reshape(-1)

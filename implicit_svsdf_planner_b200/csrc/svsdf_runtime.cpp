@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/svsdf.h"
+#include "host/astar.hpp"
 #include "host/lbfgs.hpp"
 #include "host/minco.hpp"
 #include "svsdf_launch.h"
@@ -51,6 +52,8 @@ struct svsdf_ctx {
     unsigned *d_front_rowmask = nullptr;
     unsigned *d_cspace = nullptr;
     size_t cap_cspace = 0;
+    unsigned char *d_front_scratch = nullptr;  // grow-only device scratch of the batched front-end calls
+    size_t cap_front_scratch = 0;
     double *d_points = nullptr;  // packed xy
     bool own_points = true;
     int64_t P = 0;
@@ -615,6 +618,17 @@ int svsdf_front_get_kernels(svsdf_ctx *ctx, double *yaw_out, unsigned char *cell
     return SVSDF_OK;
 }
 
+static int front_scratch(svsdf_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->cap_front_scratch) return SVSDF_OK;
+    cudaFree(ctx->d_front_scratch);
+    ctx->d_front_scratch = nullptr;
+    ctx->cap_front_scratch = 0;
+    const size_t cap = bytes + bytes / 2 + 4096;
+    CK(cudaMalloc(&ctx->d_front_scratch, cap));
+    ctx->cap_front_scratch = cap;
+    return SVSDF_OK;
+}
+
 static int front_params_with_map(svsdf_ctx *ctx, FrontParams &F, const char *who) {
     if (!ctx->front_ready) { ctx->err = std::string(who) + ": call svsdf_front_init first"; return SVSDF_ERR_NOT_READY; }
     if (!ctx->d_map) { ctx->err = std::string(who) + ": map not set (svsdf_set_map)"; return SVSDF_ERR_NOT_READY; }
@@ -670,25 +684,42 @@ int svsdf_front_expand(svsdf_ctx *ctx, int64_t n, const int32_t *node_ij, const 
     P.half_box = (double)(F.kernel_size / 2 + 1);
     for (double kt = 0.0; kt <= 1.0 && P.nkt < 64; kt += 0.02) P.kt[P.nkt++] = kt;  // sw_manager.hpp:1190
     CK(cudaSetDevice(ctx->device));
-    int *d_ij = nullptr;
-    double *d_fy = nullptr, *d_cy = nullptr;
-    unsigned char *d_ok = nullptr, *d_parts = nullptr;
-    cudaError_t e = cudaMalloc(&d_ij, 2 * n * sizeof(int));
-    if (e == cudaSuccess) e = cudaMalloc(&d_fy, n * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&d_cy, 9 * n * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&d_ok, 9 * n);
-    if (e == cudaSuccess) e = cudaMalloc(&d_parts, 9 * n);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_ij, node_ij, 2 * n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+    // one scratch allocation, carved: child yaws [9n] f64 | father yaws [n] f64 | node indices [2n] i32 | ok [9n] | parts [9n]
+    const size_t un = (size_t)n;
+    rc = front_scratch(ctx, 9 * un * 8 + un * 8 + 2 * un * 4 + 18 * un + 64);
+    if (rc != SVSDF_OK) return rc;
+    double *d_cy = reinterpret_cast<double *>(ctx->d_front_scratch);
+    double *d_fy = d_cy + 9 * un;
+    int *d_ij = reinterpret_cast<int *>(d_fy + un);
+    unsigned char *d_ok = reinterpret_cast<unsigned char *>(d_ij + 2 * un);
+    unsigned char *d_parts = d_ok + 9 * un;
+    cudaError_t e = cudaMemcpyAsync(d_ij, node_ij, 2 * n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_fy, node_yaw, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = launch_front_expand(ctx->shape, F, P, ctx->d_map, ctx->d_front_bytes, n, d_ij, d_fy, d_ok, d_cy, d_parts, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(ok_out, d_ok, 9 * n, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(child_yaw_out, d_cy, 9 * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess && parts_out) e = cudaMemcpyAsync(parts_out, d_parts, 9 * n, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_ij); cudaFree(d_fy); cudaFree(d_cy); cudaFree(d_ok); cudaFree(d_parts);
     if (e != cudaSuccess) { ctx->err = std::string("svsdf_front_expand: ") + cudaGetErrorString(e); return SVSDF_ERR_CUDA; }
     ctx->launches += 1;
     return SVSDF_OK;
+}
+
+int svsdf_front_astar(svsdf_ctx *ctx, int n, const double *start_xy, const double *goal_xy, int max_path, double *paths_out, int32_t *len_out,
+                      int32_t *expansions_out, int64_t *rounds_out) {
+    if (!ctx || n < 0 || max_path < 1 || (n > 0 && (!start_xy || !goal_xy || !paths_out || !len_out))) return SVSDF_ERR_INVALID;
+    FrontParams F;
+    int rc = front_params_with_map(ctx, F, "svsdf_front_astar");
+    if (rc != SVSDF_OK) return rc;
+    host::AstarGrid G;
+    G.X = F.X; G.Y = F.Y; G.ox = F.ox; G.oy = F.oy; G.res = F.map_res;
+    host::AstarStats stats;
+    auto expand = [&](int m, const int32_t *ij, const double *yaw, unsigned char *ok, double *cyaw) {
+        return svsdf_front_expand(ctx, m, ij, yaw, ok, cyaw, nullptr);
+    };
+    rc = host::astar_batch(G, n, start_xy, goal_xy, max_path, paths_out, len_out, expansions_out, (int64_t)1 << 40, expand, &stats);
+    if (rounds_out) *rounds_out = stats.rounds;
+    return rc;
 }
 
 int svsdf_front_check_kernel_value(svsdf_ctx *ctx, int64_t n, const double *father_yaw, const int32_t *ind_xy, unsigned char *ok_out,
@@ -704,20 +735,19 @@ int svsdf_front_check_kernel_value(svsdf_ctx *ctx, int64_t n, const double *fath
             return SVSDF_ERR_INVALID;
         }
     CK(cudaSetDevice(ctx->device));
-    double *d_fy = nullptr, *d_cy = nullptr;
-    int *d_ind = nullptr;
-    unsigned char *d_ok = nullptr;
-    cudaError_t e = cudaMalloc(&d_fy, n * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&d_cy, n * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&d_ind, 2 * n * sizeof(int));
-    if (e == cudaSuccess) e = cudaMalloc(&d_ok, n);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_fy, father_yaw, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    const size_t un = (size_t)n;
+    rc = front_scratch(ctx, un * 8 + un * 8 + 2 * un * 4 + un + 64);
+    if (rc != SVSDF_OK) return rc;
+    double *d_fy = reinterpret_cast<double *>(ctx->d_front_scratch);
+    double *d_cy = d_fy + un;
+    int *d_ind = reinterpret_cast<int *>(d_cy + un);
+    unsigned char *d_ok = reinterpret_cast<unsigned char *>(d_ind + 2 * un);
+    cudaError_t e = cudaMemcpyAsync(d_fy, father_yaw, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_ind, ind_xy, 2 * n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = launch_front_check(F, ctx->d_map, ctx->d_front_bytes, n, d_fy, d_ind, d_ok, d_cy, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(ok_out, d_ok, n, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(child_yaw_out, d_cy, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_fy); cudaFree(d_cy); cudaFree(d_ind); cudaFree(d_ok);
     if (e != cudaSuccess) { ctx->err = std::string("svsdf_front_check_kernel_value: ") + cudaGetErrorString(e); return SVSDF_ERR_CUDA; }
     ctx->launches += 1;
     return SVSDF_OK;
@@ -810,7 +840,7 @@ void svsdf_destroy(svsdf_ctx *ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->own_points) cudaFree(ctx->d_points);
     cudaFree(ctx->d_mesh_tri);
-    cudaFree(ctx->d_front_bytes); cudaFree(ctx->d_front_rowmask); cudaFree(ctx->d_cspace);
+    cudaFree(ctx->d_front_bytes); cudaFree(ctx->d_front_rowmask); cudaFree(ctx->d_cspace); cudaFree(ctx->d_front_scratch);
     cudaFree(ctx->d_flag); cudaFree(ctx->d_inside_tstar); cudaFree(ctx->d_inside_list);
     cudaFree(ctx->d_gsip_contrib); cudaFree(ctx->d_gsip_piece); cudaFree(ctx->d_n_inside);
     cudaFree(ctx->d_eval_counter); cudaFree(ctx->d_tot); cudaFree(ctx->d_ticket); cudaFree(ctx->d_blob); cudaFree(ctx->d_partials); cudaFree(ctx->d_out);

@@ -16,6 +16,8 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
+#include <map>
 #include <queue>
 #include <vector>
 
@@ -281,6 +283,93 @@ inline void expand_node(const Shape &S, const ShapeKernels &K, const FrontMap &M
             ok[n] = (p == 7);
             child_yaw[n] = cy;
         }
+}
+
+// ---- AstarPathSearcher::AstarPathSearch / getPath (front_end_Astar.hpp:243-390), z = 0 layer ----
+// Literal single-problem restatement: GridNode bookkeeping (id 0 unseen / 1 open / -1 closed, yaw fixed when a node is first
+// seen), std::multimap open list (equal keys pop in insertion order), stale keys when an open node improves (the
+// reference does not re-key it), closed nodes re-opened when improved, separate start-node object.
+struct AstarResult {
+    bool success = false;
+    int expansions = 0;
+    std::vector<double> path;  // x, y, yaw per node, start first
+};
+inline double astar_heuristic(int ax, int ay, int bx, int by) {  // getHeu (:165-183), dz = 0
+    const double p = 1.0 / 1000;
+    const int dx = std::abs(ax - bx), dy = std::abs(ay - by), dz = 0;
+    const int dmin = std::min(dx, std::min(dy, dz));
+    const int dmax = std::max(dx, std::max(dy, dz));
+    const int dmid = dx + dy + dz - dmin - dmax;
+    const double h = std::sqrt(3) * dmin + std::sqrt(2) * (dmid - dmin) + (dmax - dmid);
+    return h * (1 + p);
+}
+inline AstarResult astar_search(const Shape &S, const ShapeKernels &K, const FrontMap &M, const MapGeom &G, const double start[2],
+                                const double goal[2], int max_expansions = 1 << 30) {
+    AstarResult R;
+    const double xmax = G.ox + M.X * G.res, ymax = G.oy + M.Y * G.res;
+    auto in_map = [&](const double p[2]) { return !(p[0] < G.ox || p[1] < G.oy || p[0] > xmax || p[1] > ymax); };
+    if (!in_map(start) || !in_map(goal)) return R;
+    const int sx = grid_index_1d(start[0], G.ox, G.res, M.X), sy = grid_index_1d(start[1], G.oy, G.res, M.Y);
+    const int gx = grid_index_1d(goal[0], G.ox, G.res, M.X), gy = grid_index_1d(goal[1], G.oy, G.res, M.Y);
+    struct Node { int id = 0; double g = 0, f = 0, yaw = 0; int father = -1; };  // father: node slot, -1 none
+    const int NS = M.X * M.Y;                    // slot NS = the separate start-node object
+    std::vector<Node> nodes((size_t)NS + 1);
+    auto slot_xy = [&](int s, int &x, int &y) { if (s == NS) { x = sx; y = sy; } else { x = s / M.Y; y = s % M.Y; } };
+    std::multimap<double, int> open;
+    Node &st = nodes[NS];
+    st.g = 0; st.f = astar_heuristic(sx, sy, gx, gy); st.id = 1; st.yaw = 0.0;
+    open.insert({st.f, NS});
+    nodes[(size_t)sx * M.Y + sy].id = 1; nodes[(size_t)sx * M.Y + sy].g = st.g; nodes[(size_t)sx * M.Y + sy].f = st.f;
+    while (!open.empty()) {
+        auto it = open.begin();
+        const int cur = it->second;
+        open.erase(it);
+        nodes[cur].id = -1;
+        int cx, cy_;
+        slot_xy(cur, cx, cy_);
+        if (cx == gx && cy_ == gy) {
+            R.success = true;
+            std::vector<int> chain;
+            int p = cur;
+            while (nodes[p].father != -1) { chain.push_back(p); p = nodes[p].father; }
+            chain.push_back(p);
+            for (auto q = chain.rbegin(); q != chain.rend(); ++q) {
+                int x, y;
+                slot_xy(*q, x, y);
+                R.path.push_back((x + 0.5) * G.res + G.ox);
+                R.path.push_back((y + 0.5) * G.res + G.oy);
+                R.path.push_back(nodes[*q].yaw);
+            }
+            return R;
+        }
+        if (R.expansions >= max_expansions) return R;
+        R.expansions++;
+        uint8_t ok[9], parts[9];
+        double cyaw[9];
+        expand_node(S, K, M, G, cx, cy_, nodes[cur].yaw, K.kernel_size, ok, cyaw, parts);
+        int n = 0;
+        for (int i = -1; i < 2; i++)
+            for (int j = -1; j < 2; j++, n++) {
+                if (!ok[n]) continue;
+                const int nx = cx + i, ny = cy_ + j, ns = nx * M.Y + ny;
+                Node &nb = nodes[ns];
+                if (nb.id == 0) nb.yaw = cyaw[n];  // AstarGetSucc :229-233
+                const double ec = std::sqrt((double)(i * i + j * j));
+                const double tg = ec + nodes[cur].g;
+                if (nb.id == 0) {
+                    nb.father = cur; nb.g = tg; nb.f = tg + astar_heuristic(nx, ny, gx, gy) + 0.0; nb.id = 1;
+                    open.insert({nb.f, ns});
+                } else if (nb.id == 1) {
+                    if (tg < nb.g) { nb.father = cur; nb.g = tg; nb.f = tg + astar_heuristic(nx, ny, gx, gy) + 0.0; }  // key not updated
+                } else {
+                    if (tg < nb.g) {
+                        nb.father = cur; nb.g = tg; nb.f = tg + astar_heuristic(nx, ny, gx, gy) + 0.0; nb.id = 1;
+                        open.insert({nb.f, ns});
+                    }
+                }
+            }
+    }
+    return R;
 }
 
 }  // namespace oracle

@@ -132,6 +132,25 @@ void orc_expand_nodes(const char *name, const double *poly_params, int ks, int K
         expand_node(S, SK, M, G, node_ij[2 * q], node_ij[2 * q + 1], node_yaw[q], ks, ok_out + 9 * q, child_yaw_out + 9 * q, parts_out + 9 * q);
 }
 
+// AstarPathSearch for n start/goal pairs; path_out [n][max_path][3], len_out [n] (0 = no path), exp_out [n] expansions
+void orc_astar(const char *name, const double *poly_params, int ks, int K, double safeh, const uint8_t *occ, int X, int Y, double ox, double oy,
+               double map_res, int n, const double *start_xy, const double *goal_xy, int max_path, double *path_out, int *len_out, int *exp_out) {
+    Shape S = make_shape(name, poly_params, nullptr, 0);
+    ShapeKernels SK = init_shape_kernels(S, ks, K, map_res, safeh);
+    FrontMap M;
+    M.build(occ, X, Y, ks);
+    MapGeom G;
+    G.ox = ox; G.oy = oy; G.res = map_res;
+#pragma omp parallel for schedule(dynamic)
+    for (int q = 0; q < n; ++q) {
+        AstarResult R = astar_search(S, SK, M, G, start_xy + 2 * q, goal_xy + 2 * q);
+        const int len = (int)(R.path.size() / 3);
+        len_out[q] = (R.success && len <= max_path) ? len : 0;
+        exp_out[q] = R.expansions;
+        if (len_out[q]) std::memcpy(path_out + (size_t)q * max_path * 3, R.path.data(), R.path.size() * sizeof(double));
+    }
+}
+
 void *orc_create(const char *name, const double *poly_params, const double *poly_xy, int poly_n, double weight_p,
                  double safety_hor, double rho, int threads) {
     TrajOptimizerOracle *o = new TrajOptimizerOracle();

@@ -86,6 +86,8 @@ def lib(variant: str = "default"):
                                              C.POINTER(C.c_int), u8, dp]
         L.orc_expand_nodes.argtypes = [C.c_char_p, dp, C.c_int, C.c_int, C.c_double, C.c_double, u8, C.c_int, C.c_int, C.c_double, C.c_double,
                                        C.c_double, C.c_int64, C.POINTER(C.c_int), dp, u8, dp, u8]
+        L.orc_astar.argtypes = [C.c_char_p, dp, C.c_int, C.c_int, C.c_double, u8, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, dp,
+                                dp, C.c_int, dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.orc_max_threads.restype = C.c_int
         L.orc_num_procs.restype = C.c_int
         _libs[variant] = L
@@ -190,6 +192,23 @@ def expand_nodes(name, occ, node_ij, node_yaw, origin=(0.0, 0.0), map_res=1.0, k
     lib().orc_expand_nodes(name.encode(), _p(pp), kernel_size, kernel_count, float(map_res), safeh, _u8p(occ), X, Y, float(origin[0]),
                            float(origin[1]), float(map_res), n, ij.ctypes.data_as(C.POINTER(C.c_int)), _p(fy), _u8p(ok), _p(cy), _u8p(parts))
     return ok.astype(bool), cy, parts
+
+
+def astar(name, occ, start_xy, goal_xy, origin=(0.0, 0.0), map_res=1.0, kernel_size=17, kernel_count=18, safeh=0.0, max_path=1024,
+          poly_params=(0.0, 0.0, 0.0)):
+    """AstarPathSearcher::AstarPathSearch + getPath for n start/goal pairs: (list of paths [len, 3] (x, y, yaw) or None, expansions [n])."""
+    occ = np.ascontiguousarray(occ, dtype=np.uint8)
+    X, Y = occ.shape
+    pp = _f64(poly_params)
+    st = _f64(start_xy).reshape(-1, 2)
+    go = _f64(goal_xy).reshape(-1, 2)
+    n = st.shape[0]
+    path = np.zeros((n, max_path, 3))
+    ln = np.zeros(n, dtype=np.int32)
+    ex = np.zeros(n, dtype=np.int32)
+    lib().orc_astar(name.encode(), _p(pp), kernel_size, kernel_count, safeh, _u8p(occ), X, Y, float(origin[0]), float(origin[1]), float(map_res), n,
+                    _p(st), _p(go), max_path, _p(path), ln.ctypes.data_as(C.POINTER(C.c_int)), ex.ctypes.data_as(C.POINTER(C.c_int)))
+    return [path[q, : ln[q]].copy() if ln[q] else None for q in range(n)], ex
 
 
 def minco_forward(init_s, final_s, q, T):

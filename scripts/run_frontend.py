@@ -54,4 +54,18 @@ t_gpu = (time.perf_counter() - t0) / 10
 t0 = time.perf_counter(); O.expand_nodes("star", occ2, ij, fy, map_res=1.0); t_cpu2 = time.perf_counter() - t0
 rec["expand"] = {"nodes": 4096, "gpu_ms_e2e": 1e3 * t_gpu, "cpu_ms": 1e3 * t_cpu2, "cpu_threads": O.num_procs(), "speedup": t_cpu2 / t_gpu,
                  "pass_rate": float(ok.mean()), "note": "host buffers in and out (svsdf_front_expand), 9 neighbours per node"}
+# batch A*: 1024 start/goal problems in lock-step (svsdf_front_astar) vs the oracle's AstarPathSearch per problem (OpenMP over problems)
+occ3 = rng.random((60, 60)) < 0.005
+ctx3 = api.Context("star")
+ctx3.front_init(17, 18, 1.0, 0.0)
+ctx3.set_map(batch.pack_map_kernel(occ3, 17), 60, 60, 17, (0.0, 0.0), 1.0)
+npb = int(os.environ.get("SVSDF_ASTAR_PROBLEMS", "1024"))
+st = rng.uniform(1.0, 59.0, size=(npb, 2)); go = rng.uniform(1.0, 59.0, size=(npb, 2))
+ctx3.front_astar(st[:8], go[:8])
+t0 = time.perf_counter(); paths, ex, rounds = ctx3.front_astar(st, go); t_gpu = time.perf_counter() - t0
+t0 = time.perf_counter(); paths_o, ex_o = O.astar("star", occ3, st, go, map_res=1.0); t_cpu3 = time.perf_counter() - t0
+same = bool(np.array_equal(ex, ex_o) and all((a is None) == (b is None) and (a is None or np.array_equal(a, b)) for a, b in zip(paths, paths_o)))
+rec["astar"] = {"problems": npb, "found": int(sum(p is not None for p in paths)), "expansions": int(ex.sum()), "lockstep_rounds": int(rounds),
+                "gpu_s": t_gpu, "cpu_s": t_cpu3, "cpu_threads": O.num_procs(), "speedup": t_cpu3 / t_gpu, "identical_to_oracle": same,
+                "problems_per_s_gpu": npb / t_gpu}
 print(json.dumps(rec))

@@ -136,3 +136,30 @@ def test_expand_nodes_is_bitwise_the_oracles(oracle_mod, shape, pp):
     assert 0.05 < ok.mean() < 0.99  # the scene exercises both outcomes
     assert len(np.unique(parts)) >= 4
     ctx.close()
+
+
+def test_batch_astar_equals_the_oracles_search(oracle_mod):
+    """svsdf_front_astar: n searches in lock-step on the GPU node test vs the oracle's literal AstarPathSearch per problem."""
+    rng = np.random.default_rng(33)
+    X, Y, ks, K, res = 60, 52, 17, 18, 1.0
+    occ = rng.random((X, Y)) < 0.005
+    origin = (2.0, -9.5)
+    n = 64
+    st = np.c_[rng.uniform(origin[0], origin[0] + X, n), rng.uniform(origin[1], origin[1] + Y, n)]
+    go = np.c_[rng.uniform(origin[0], origin[0] + X, n), rng.uniform(origin[1], origin[1] + Y, n)]
+    st[3] = [origin[0] - 2.0, origin[1] + 1.0]  # outside the map
+    ctx = api.Context("star")
+    ctx.front_init(ks, K, res, 0.0)
+    ctx.set_map(batch.pack_map_kernel(occ, ks), X, Y, ks, origin, res)
+    paths, ex, rounds = ctx.front_astar(st, go)
+    paths_o, ex_o = oracle_mod.astar("star", occ, st, go, origin=origin, map_res=res, kernel_size=ks, kernel_count=K)
+    assert np.array_equal(ex, ex_o)
+    found = 0
+    for p, po in zip(paths, paths_o):
+        assert (p is None) == (po is None)
+        if p is not None:
+            assert np.array_equal(p, po)
+            found += 1
+    assert found >= n // 2 and paths[3] is None
+    assert rounds == ex.max() + 0 or rounds >= ex.max()  # lock-step: as many rounds as the longest search needs (+ its goal pop)
+    ctx.close()

@@ -106,3 +106,49 @@ def test_expand_nodes_semantics(oracle_mod):
     occ[15, 17] = True
     ok, cy, parts = oracle_mod.expand_nodes("star", occ, np.array([[15, 15]]), np.array([0.0]), map_res=1.0)
     assert (parts[0] & 1).all() and not ok[0].all()
+
+
+def test_astar_paths_are_valid_and_near_optimal(oracle_mod):
+    rng = np.random.default_rng(21)
+    X, Y = 50, 44
+    occ = rng.random((X, Y)) < 0.005
+    origin = (-3.0, 7.5)
+    st = np.c_[rng.uniform(origin[0] + 1, origin[0] + X - 1, 12), rng.uniform(origin[1] + 1, origin[1] + Y - 1, 12)]
+    go = np.c_[rng.uniform(origin[0] + 1, origin[0] + X - 1, 12), rng.uniform(origin[1] + 1, origin[1] + Y - 1, 12)]
+    st[0] = [origin[0] - 5.0, origin[1]]  # outside the map: no search
+    paths, ex = oracle_mod.astar("star", occ, st, go, origin=origin, map_res=1.0)
+    assert paths[0] is None and ex[0] == 0
+    found = [p for p in paths if p is not None]
+    assert len(found) >= 6
+    for q, p in enumerate(paths):
+        if p is None:
+            continue
+        ij = np.floor((p[:, :2] - np.array(origin)) / 1.0).astype(int)
+        assert np.array_equal(ij[0], np.floor((st[q] - np.array(origin))).astype(int))
+        assert np.array_equal(ij[-1], np.floor((go[q] - np.array(origin))).astype(int))
+        step = np.abs(np.diff(ij, axis=0))
+        assert step.max() <= 1 and (step.sum(axis=1) >= 1).all()   # 8-connected moves, no repeated cell
+        assert not occ[ij[:, 0], ij[:, 1]].any()
+        # every edge of the path passes the node test it was generated by
+        ok, cy, _ = oracle_mod.expand_nodes("star", occ, ij[:-1], p[:-1, 2], origin=origin, map_res=1.0)
+        k = (ij[1:, 0] - ij[:-1, 0] + 1) * 3 + (ij[1:, 1] - ij[:-1, 1] + 1)
+        assert ok[np.arange(len(k)), k].all()
+        # cost within 0.1 % + of the octile lower bound when the straight route is free, never below it
+        d = np.abs(ij[-1] - ij[0])
+        lower = np.sqrt(2) * d.min() + (d.max() - d.min())
+        cost = np.sqrt((np.diff(ij, axis=0) ** 2).sum(axis=1)).sum()
+        assert cost >= lower - 1e-9
+
+
+def test_product_batch_astar_host_logic_equals_the_oracle(tmp_path):
+    """csrc/host/astar.hpp (the lock-step batch search the library runs on top of svsdf_front_expand) compiled for the host with
+    the oracle's node test plugged in: paths and expansion counts must equal the oracle's literal AstarPathSearch."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "astar_host")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fopenmp", "-mfma", "-ffp-contract=off",
+                           os.path.join(root, "tests", "cpp", "astar_host_main.cpp"), "-o", exe])
+    out = subprocess.run([exe, "40"], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("OK"), out.stdout + out.stderr
