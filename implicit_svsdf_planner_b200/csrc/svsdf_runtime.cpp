@@ -880,11 +880,17 @@ int svsdf_set_points(svsdf_ctx *ctx, const double *pts, int64_t P, int stride) {
     int rc = ensure_stage(ctx, (size_t)P * 2 * sizeof(double));
     if (rc) return rc;
     double *h = ctx->h_stage;
-    for (int64_t i = 0; i < P; ++i) {  // pos_eva(2) = 0 (back_end_optimizer.hpp:791): only x, y are kept
-        h[2 * i] = pts[i * stride];
-        h[2 * i + 1] = pts[i * stride + 1];
+    // pos_eva(2) = 0 (back_end_optimizer.hpp:791): only x, y are kept.  Packed into the pinned stage chunk by chunk, each
+    // chunk's copy overlapping the packing of the next one.
+    const int64_t chunk = 32768;
+    for (int64_t b = 0; b < P; b += chunk) {
+        const int64_t e = std::min(P, b + chunk);
+        for (int64_t i = b; i < e; ++i) {
+            h[2 * i] = pts[i * stride];
+            h[2 * i + 1] = pts[i * stride + 1];
+        }
+        CK(cudaMemcpyAsync(ctx->d_points + 2 * b, h + 2 * b, (size_t)(e - b) * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     }
-    CK(cudaMemcpyAsync(ctx->d_points, h, (size_t)P * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->P = P;
     ctx->last_n_inside = -1;
@@ -927,8 +933,6 @@ int svsdf_query(svsdf_ctx *ctx, int N, const double *T, const double *coeffs, in
     if (P > ctx->cap_q) {
         cudaFree(ctx->d_q_points); cudaFree(ctx->d_q_sdf); cudaFree(ctx->d_q_ts); cudaFree(ctx->d_q_grad);
         cudaFree(ctx->d_q_rounds);
-    if (ctx->own_map) cudaFree(ctx->d_map);
-    cudaFree(ctx->d_block_counts); cudaFree(ctx->d_n_total);
         ctx->d_q_points = ctx->d_q_sdf = ctx->d_q_ts = ctx->d_q_grad = nullptr;
         ctx->d_q_rounds = nullptr;
         ctx->cap_q = 0;

@@ -81,3 +81,20 @@ def test_extract_errors():
         ctx.extract_points(np.zeros((1, 2)), 1.0)
     with pytest.raises(api.SvsdfError):  # even kernel size
         ctx.set_map(np.zeros((10, 2), dtype=np.uint8), 4, 4, 6, (0, 0), 1.0)
+
+
+def test_map_survives_growing_queries(scene2k):
+    """Regression: growing the per-point query buffers (svsdf_query with more points than before) must not touch the map."""
+    rng = np.random.default_rng(5)
+    occ = rng.random((60, 60)) < 0.3
+    gm = batch.GridMap(occ=occ, origin=np.zeros(2), res=1.0)
+    ctx, ref = _check(gm, np.array([[20.5, 20.5], [30.0, 31.0]]), 4.0)
+    sc = scene2k
+    co = sc.coeffs_colmajor()
+    p = np.c_[sc.points[:, :2], np.zeros(sc.P)]
+    ctx.query(sc.T, co, p[:10])
+    ctx.query(sc.T, co, p)              # larger than any query before: buffers are re-allocated
+    ctx.query(sc.T, co, np.r_[p, p, p])  # and again
+    n = ctx.extract_points(np.array([[20.5, 20.5], [30.0, 31.0]]), 4.0)
+    assert n == ref.shape[0] and np.array_equal(ctx.get_points(), ref)
+    ctx.close()
