@@ -21,7 +21,7 @@ ncu --set full --clock-control none -k regex:k_gsip -s 2 -c 1 -f -o gpurun_out/p
     python scripts/prof_step.py >> gpurun_out/prof_r1.log 2>&1
 fi
 if [[ $PART == *a* ]]; then
-python scripts/run_configs.py 1 2 3 4 4m > gpurun_out/configs_r1.jsonl 2> gpurun_out/configs_r1.err
+python tests/tools/run_configs.py 1 2 3 4 4m > gpurun_out/configs_r1.jsonl 2> gpurun_out/configs_r1.err
 python scripts/run_batch.py --problems 16 --max-iter 20 > gpurun_out/batch_1gpu_r1.json 2> gpurun_out/batch_r1.err
 tail -3 gpurun_out/pytest_gpu_r1.log
 fi

@@ -16,7 +16,7 @@ LMBM = os.path.join(ROOT, "oracle", "_ref", "lmbm.so")
 
 
 def run(args):
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "run_lmbm_gpu.py")] + args, capture_output=True, text=True, timeout=600)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "run_lmbm_gpu.py")] + args, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     return json.loads(out.stdout.strip().split("\n")[-1])
 

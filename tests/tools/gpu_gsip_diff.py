@@ -1,6 +1,6 @@
 """How far are the interior-branch (GSIP) per-point results of the strict build from the oracle's?"""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from implicit_svsdf_planner_b200 import api, scenes
 from oracle import oracle_py as O

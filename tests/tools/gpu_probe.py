@@ -1,6 +1,6 @@
 """Ad-hoc GPU probe (development aid): parity vs oracle on small scenes + raw kernel timing."""
 import sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from implicit_svsdf_planner_b200 import api, scenes
 from oracle import oracle_py as O

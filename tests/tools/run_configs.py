@@ -9,7 +9,7 @@
             release of the reference uses for non-analytic shapes; the libigl path is unreachable there), N=16, 500k
 """
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from implicit_svsdf_planner_b200 import api, scenes
 from oracle import oracle_py as O
@@ -19,8 +19,8 @@ def nrel(a, b): return float(np.linalg.norm(np.asarray(a) - b) / max(np.linalg.n
 def star_obj_polygon():
     """2-D outline of the reference's shapes/star.obj (tests/golden/obj_outlines.json), ordered by angle: the mesh shape of
     config 4 handed to the Polygon fallback functor (what this release of the reference uses for non-analytic shapes)."""
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    xy = np.array(json.load(open(os.path.join(root, "tests", "golden", "obj_outlines.json")))["star"]["outline_xy"])
+    tests_dir = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    xy = np.array(json.load(open(os.path.join(tests_dir, "golden", "obj_outlines.json")))["star"]["outline_xy"])
     return xy[np.argsort(np.arctan2(xy[:, 1], xy[:, 0]))].reshape(-1)
 
 
@@ -74,7 +74,7 @@ if __name__ == "__main__":
     if "2" in which: run("2", "star", 8, 200_000, 2.75, 50_000)
     if "3" in which: run("3", "sdHorseshoe", 16, 500_000, 2.15, 50_000)
     if "4m" in which:  # the same mesh through the triangle-mesh functor (getonlySDF_igl restated exactly)
-        g = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "fwn_ref.npz"))
+        g = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "golden", "fwn_ref.npz"))
         P4 = int(os.environ.get("SVSDF_MESH_P", "500000"))
         run("4m", "star_obj_mesh_sdf", 16, P4, 2.75, 3000, lbfgs_iters=int(os.environ.get("SVSDF_MESH_LBFGS", "4")), scene_shape="sdHorseshoe",
             mesh=(g["star_V"], g["star_F"]))

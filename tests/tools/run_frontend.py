@@ -2,7 +2,7 @@
 (60 m at 0.025 m = 2400 x 2400 cells, 18 yaw kernels of 17 x 17) on one GPU, next to the oracle's restatement of the
 reference's kernelConv<true> on the host cores (a crop, scaled).  Prints one JSON line."""
 import json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from implicit_svsdf_planner_b200 import api, batch
 from oracle import oracle_py as O
@@ -21,7 +21,7 @@ W = (Y + 31) // 32
 out_bytes = K * X * W * 4
 in_bytes = (X + ks - 1) * ((Y + ks - 1 + 7) // 8)
 peaks = {}
-pp = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+pp = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "MEASURED_PEAKS.json")
 if os.path.exists(pp):
     peaks = json.load(open(pp))
 hbm = peaks.get("hbm_gbs", 6650.0)

@@ -2,7 +2,7 @@
 back_end_optimizer.cpp:29) driving THIS library's cost callback on the GPU: `svsdf_evaluate` has the lmbm_evaluate_t
 signature (lmbm.h:206-209), so its address is handed to lmbm_optimize as is — no Python in the loop.
 
-    python scripts/run_lmbm_gpu.py [--points 400 --pieces 8 --clearance 2.6 --seed-map 777 --max-evals 400] [--trace out.npz]
+    python tests/tools/run_lmbm_gpu.py [--points 400 --pieces 8 --clearance 2.6 --seed-map 777 --max-evals 400] [--trace out.npz]
 
 Needs oracle/_ref/lmbm.so (copied there from /root/reference by __graft_entry__.build(); git-ignored, travels to the GPU
 box) and a libgfortran.so.5 (scipy bundles one; symlinked into oracle/_ref/).  The script re-executes itself with
@@ -16,7 +16,7 @@ import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 REFDIR = os.path.join(ROOT, "oracle", "_ref")
 LMBM = os.path.join(REFDIR, "lmbm.so")
 SYM = "_ZN4lmbm13lmbm_optimizeEiPdS0_PFdPvPKdS0_iES1_PFiS1_S3_iEPNS_16lmbm_parameter_tE"  # lmbm::lmbm_optimize (lmbm.h:214-221)
