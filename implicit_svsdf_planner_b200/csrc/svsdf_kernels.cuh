@@ -664,6 +664,9 @@ __global__ void k_pose_table(double *blob) {
 #ifndef SVSDF_OUTER_MIN_CTAS
 #define SVSDF_OUTER_MIN_CTAS 3
 #endif
+#ifndef SVSDF_GSIP_MIN_CTAS
+#define SVSDF_GSIP_MIN_CTAS 3
+#endif
 template <int SHAPE, bool XFORM>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, (SHAPE == SH_MESH) ? 2 : SVSDF_OUTER_MIN_CTAS)
     k_outer(const __grid_constant__ KernelArgs A, const __grid_constant__ ShapeParams S) {
@@ -831,7 +834,7 @@ __global__ void __launch_bounds__(1024) k_compact(const unsigned char *flag, int
 // dynamic smem: [ blob ]
 // ------------------------------------------------------------------------------------------------
 template <int SHAPE, bool XFORM, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 1)
+__global__ void __launch_bounds__(WARPS * 32, (WARPS == kWarpsPerBlock && SHAPE != SH_MESH) ? SVSDF_GSIP_MIN_CTAS : 1)
     k_gsip(const __grid_constant__ KernelArgs A, const __grid_constant__ ShapeParams S) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t bar;
