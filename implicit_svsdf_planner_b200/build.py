@@ -29,7 +29,7 @@ UNITS = [
     ("svsdf_kernels_strict.cu", "svsdf_kernels_strict.o", ["-fmad=false"]),
     ("svsdf_extract.cu", "svsdf_extract.o", ["-fmad=false"]),  # cell centres must round like the host formula
     ("svsdf_frontend.cu", "svsdf_frontend.o", ["-fmad=false"]),  # shape kernels: same rounding as the strict functors
-    ("svsdf_runtime.cpp", "svsdf_runtime.o", []),
+    ("svsdf_runtime.cpp", "svsdf_runtime.o", ["-Xcompiler", "-fopenmp"]),  # host threads for the batch A* bookkeeping
 ]
 HEADERS = [
     "svsdf_kernels.cuh",
@@ -84,7 +84,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                     print(out)
     objs = [os.path.join(OBJDIR, u[1]) for u in UNITS]
     if todo or not os.path.exists(SO) or _mtime(SO) < max(_mtime(o) for o in objs):
-        cmd = [NVCC, *ARCH, "-shared", "-ccbin", "/usr/bin/g++", "-o", SO, *objs]
+        cmd = [NVCC, *ARCH, "-shared", "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fopenmp", "-o", SO, *objs, "-lgomp"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

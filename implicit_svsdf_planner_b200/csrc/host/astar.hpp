@@ -17,6 +17,9 @@
 #include <map>
 #include <unordered_map>
 #include <vector>
+#if defined(_OPENMP)
+#include <omp.h>
+#endif
 
 namespace svsdf {
 namespace host {
@@ -85,10 +88,21 @@ int astar_batch(const AstarGrid &G, int n, const double *start_xy, const double 
     std::vector<int32_t> ij;
     std::vector<double> yaw, cyaw;
     std::vector<unsigned char> ok;
+    std::vector<unsigned char> wants(n, 0);   // problem q hands a node to this round's expand call
+    std::vector<int32_t> cur_xy(2 * (size_t)n);
+    std::vector<double> cur_yaw(n);
+    // The searches are independent: the per-problem bookkeeping of a round (pop + goal test, then the neighbour updates)
+    // runs on a few host threads when the batch is large; the order inside each problem is untouched.
+#if defined(_OPENMP)
+    const int host_threads = std::min(16, omp_get_max_threads());
+#endif
     for (;;) {
-        batch.clear(); ij.clear(); yaw.clear();
+#if defined(_OPENMP)
+#pragma omp parallel for schedule(static) num_threads(host_threads) if (n >= 256)
+#endif
         for (int q = 0; q < n; ++q) {
             Problem &p = P[q];
+            wants[q] = 0;
             if (p.done) continue;
             if (p.open.empty()) { p.done = true; continue; }   // search failed
             auto it = p.open.begin();
@@ -121,10 +135,17 @@ int astar_batch(const AstarGrid &G, int n, const double *start_xy, const double 
             if (p.expansions >= max_expansions_per_problem) { p.done = true; continue; }
             p.expansions++;
             p.cur = cur;
-            batch.push_back(q);
-            ij.push_back(cx); ij.push_back(cy);
-            yaw.push_back(c.yaw);
+            wants[q] = 1;
+            cur_xy[2 * (size_t)q] = cx; cur_xy[2 * (size_t)q + 1] = cy;
+            cur_yaw[q] = c.yaw;
         }
+        batch.clear(); ij.clear(); yaw.clear();
+        for (int q = 0; q < n; ++q)
+            if (wants[q]) {
+                batch.push_back(q);
+                ij.push_back(cur_xy[2 * (size_t)q]); ij.push_back(cur_xy[2 * (size_t)q + 1]);
+                yaw.push_back(cur_yaw[q]);
+            }
         if (batch.empty()) break;
         const int m = (int)batch.size();
         ok.assign((size_t)9 * m, 0);
@@ -132,6 +153,9 @@ int astar_batch(const AstarGrid &G, int n, const double *start_xy, const double 
         const int rc = expand(m, ij.data(), yaw.data(), ok.data(), cyaw.data());
         if (rc != 0) return rc;
         if (stats) { stats->rounds++; stats->expansions += m; }
+#if defined(_OPENMP)
+#pragma omp parallel for schedule(static) num_threads(host_threads) if (m >= 256)
+#endif
         for (int b = 0; b < m; ++b) {
             Problem &p = P[batch[b]];
             const int cur = p.cur;

@@ -217,26 +217,33 @@ __global__ void __launch_bounds__(256) k_expand_nodes(const __grid_constant__ Sh
         const int i1 = grid_index_1d(c0 - P.half_box, F.ox, xmax, F.map_res, F.X), i2 = grid_index_1d(c0 + P.half_box, F.ox, xmax, F.map_res, F.X);
         const int j1 = grid_index_1d(c1 - P.half_box, F.oy, ymax, F.map_res, F.Y), j2 = grid_index_1d(c1 + P.half_box, F.oy, ymax, F.map_res, F.Y);
         const int nj = j2 - j1 + 1, cells = (i2 - i1 + 1) * nj;
+        // occupied cells are found 32 at a time (ballot); for each one the kt samples are spread over the lanes (2 per lane at
+        // 51 samples), so the latency of an edge is ~2 evaluations per obstacle cell instead of 51 per lane.  The test is
+        // a plain "any sample inside the shape", so the order does not matter.
         bool hit = false;
         for (int base = 0; base < cells && !hit; base += 32) {
             const int c = base + lane;
-            bool mine = false;
-            if (c < cells) {
-                const int i = i1 + c / nj, j = j1 + c % nj;
-                if (map_occupied(F, map, i, j)) {
-                    const double px = (i + 0.5) * F.map_res + F.ox, py = (j + 0.5) * F.map_res + F.oy;
-                    for (int t = 0; t < P.nkt && !mine; ++t) {
-                        const double kt = P.kt[t], om = 1 - kt;
-                        const double lx = kt * c0 + om * f0, ly = kt * c1 + om * f1, yaw = kt * cy + om * fy;
-                        double sn, cs;
-                        dev::sincos_portable(yaw, sn, cs);
-                        const double d0 = px - lx, d1 = py - ly;
-                        const double rx = cs * d0 + sn * d1, ry = -sn * d0 + cs * d1;
-                        mine = dev::shape_sdf<SHAPE, XFORM>(S, rx, ry) < 0;
-                    }
+            bool occ = false;
+            if (c < cells) occ = map_occupied(F, map, i1 + c / nj, j1 + c % nj);
+            unsigned m = __ballot_sync(0xffffffffu, occ);
+            while (m && !hit) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                const int cc = base + b;
+                const int i = i1 + cc / nj, j = j1 + cc % nj;
+                const double px = (i + 0.5) * F.map_res + F.ox, py = (j + 0.5) * F.map_res + F.oy;
+                bool mine = false;
+                for (int t = lane; t < P.nkt && !mine; t += 32) {
+                    const double kt = P.kt[t], om = 1 - kt;
+                    const double lx = kt * c0 + om * f0, ly = kt * c1 + om * f1, yaw = kt * cy + om * fy;
+                    double sn, cs;
+                    dev::sincos_portable(yaw, sn, cs);
+                    const double d0 = px - lx, d1 = py - ly;
+                    const double rx = cs * d0 + sn * d1, ry = -sn * d0 + cs * d1;
+                    mine = dev::shape_sdf<SHAPE, XFORM>(S, rx, ry) < 0;
                 }
+                hit = __any_sync(0xffffffffu, mine);
             }
-            hit = __any_sync(0xffffffffu, mine);
         }
         if (!hit) parts |= 4u;
     }

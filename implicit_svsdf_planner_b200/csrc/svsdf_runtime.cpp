@@ -684,22 +684,30 @@ int svsdf_front_expand(svsdf_ctx *ctx, int64_t n, const int32_t *node_ij, const 
     P.half_box = (double)(F.kernel_size / 2 + 1);
     for (double kt = 0.0; kt <= 1.0 && P.nkt < 64; kt += 0.02) P.kt[P.nkt++] = kt;  // sw_manager.hpp:1190
     CK(cudaSetDevice(ctx->device));
-    // one scratch allocation, carved: child yaws [9n] f64 | father yaws [n] f64 | node indices [2n] i32 | ok [9n] | parts [9n]
+    // One device scratch block and a pinned mirror of it: outputs first (child yaws [9n] f64 | ok [9n] | parts [9n], padded to
+    // 8 bytes), then inputs (father yaws [n] f64 | node indices [2n] i32) — one copy in, one launch, one copy out.
     const size_t un = (size_t)n;
-    rc = front_scratch(ctx, 9 * un * 8 + un * 8 + 2 * un * 4 + 18 * un + 64);
+    const size_t out_bytes = (9 * un * 8 + 18 * un + 7) & ~(size_t)7, in_bytes = un * 8 + 2 * un * 4;
+    rc = front_scratch(ctx, out_bytes + in_bytes + 64);
     if (rc != SVSDF_OK) return rc;
-    double *d_cy = reinterpret_cast<double *>(ctx->d_front_scratch);
-    double *d_fy = d_cy + 9 * un;
-    int *d_ij = reinterpret_cast<int *>(d_fy + un);
-    unsigned char *d_ok = reinterpret_cast<unsigned char *>(d_ij + 2 * un);
-    unsigned char *d_parts = d_ok + 9 * un;
-    cudaError_t e = cudaMemcpyAsync(d_ij, node_ij, 2 * n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(d_fy, node_yaw, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+    rc = ensure_stage(ctx, out_bytes + in_bytes + 64);
+    if (rc != SVSDF_OK) return rc;
+    unsigned char *hb = reinterpret_cast<unsigned char *>(ctx->h_stage), *db = ctx->d_front_scratch;
+    double *d_cy = reinterpret_cast<double *>(db);
+    unsigned char *d_ok = db + 9 * un * 8, *d_parts = d_ok + 9 * un;
+    double *d_fy = reinterpret_cast<double *>(db + out_bytes);
+    int *d_ij = reinterpret_cast<int *>(db + out_bytes + un * 8);
+    std::memcpy(hb + out_bytes, node_yaw, un * 8);
+    std::memcpy(hb + out_bytes + un * 8, node_ij, 2 * un * 4);
+    cudaError_t e = cudaMemcpyAsync(db + out_bytes, hb + out_bytes, in_bytes, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = launch_front_expand(ctx->shape, F, P, ctx->d_map, ctx->d_front_bytes, n, d_ij, d_fy, d_ok, d_cy, d_parts, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(ok_out, d_ok, 9 * n, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(child_yaw_out, d_cy, 9 * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess && parts_out) e = cudaMemcpyAsync(parts_out, d_parts, 9 * n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hb, db, out_bytes, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) {
+        std::memcpy(child_yaw_out, hb, 9 * un * 8);
+        std::memcpy(ok_out, hb + 9 * un * 8, 9 * un);
+        if (parts_out) std::memcpy(parts_out, hb + 9 * un * 8 + 9 * un, 9 * un);
+    }
     if (e != cudaSuccess) { ctx->err = std::string("svsdf_front_expand: ") + cudaGetErrorString(e); return SVSDF_ERR_CUDA; }
     ctx->launches += 1;
     return SVSDF_OK;
