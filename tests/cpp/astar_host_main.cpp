@@ -26,6 +26,7 @@ int main(int argc, char **argv) {
     std::vector<double> st(2 * n), go(2 * n);
     std::uniform_real_distribution<double> ux(ox - 1.0, ox + X * res + 1.0), uy(oy - 1.0, oy + Y * res + 1.0);  // some outside the map
     for (int q = 0; q < n; ++q) { st[2 * q] = ux(rng); st[2 * q + 1] = uy(rng); go[2 * q] = ux(rng); go[2 * q + 1] = uy(rng); }
+    st[0] = ox + 20.5; st[1] = oy + 20.5; go[0] = ox + 20.75; go[1] = oy + 20.25;  // start and goal in the same cell: a one-node path
     const int max_path = 256;
     std::vector<double> paths((size_t)n * max_path * 3, 0.0);
     std::vector<int32_t> len(n), ex(n);
@@ -49,6 +50,7 @@ int main(int argc, char **argv) {
         if (want_len && std::memcmp(R.path.data(), &paths[(size_t)q * max_path * 3], R.path.size() * sizeof(double)) != 0) { bad++; std::printf("problem %d: path differs\n", q); }
         found += want_len > 0;
     }
+    if (len[0] != 1) { bad++; std::printf("same-cell problem: len %d\n", len[0]); }
     std::printf("%s problems %d found %d rounds %lld expansions %lld\n", bad ? "FAIL" : "OK", n, found, (long long)stats.rounds, (long long)stats.expansions);
     return bad ? 1 : 0;
 }
