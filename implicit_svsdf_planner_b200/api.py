@@ -424,7 +424,7 @@ class Context:
         return out
 
     # ---- A* front-end collision kernels ----
-    def front_init(self, kernel_size=17, kernel_yaw_num=18, occupancy_resolution=1.0, front_end_safeh=0.0):
+    def front_init(self, kernel_size, kernel_yaw_num, occupancy_resolution, front_end_safeh=0.0):
         """BasicShape::initShape on the device (Shape.hpp:386-430)."""
         self._front = (int(kernel_size), int(kernel_yaw_num))
         self._ck(lib().svsdf_front_init(self.h, int(kernel_size), int(kernel_yaw_num), float(occupancy_resolution), float(front_end_safeh)),

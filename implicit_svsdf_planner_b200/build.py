@@ -39,6 +39,7 @@ HEADERS = [
     "svsdf_launch.h",
     "host/minco.hpp",
     "host/lbfgs.hpp",
+    "host/astar.hpp",
     "../../include/svsdf.h",
 ]
 

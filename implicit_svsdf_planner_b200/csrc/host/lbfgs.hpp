@@ -77,6 +77,11 @@ class Lbfgs {
 
         double fx = eval(inst, x, g.data(), n);
         R.evaluations = 1;
+        if (!std::isfinite(fx)) {  // a failed first evaluation (NaN cost, g left at zero) must not read as convergence
+            R.status = LBFGSERR_INVALID_FUNCVAL;
+            R.f = fx;
+            return R;
+        }
         pf[0] = fx;
         for (int i = 0; i < n; ++i) d[i] = -g[i];
         int k = 0;

@@ -434,6 +434,10 @@ __device__ __forceinline__ void grad_prel(const TrajView &tv, const ShapeParams 
         gx = vx; gy = vy;
         return;
     }
+    if (SHAPE == SH_CIRCLE) {
+        dev::circle_grad1<XFORM>(S, rx, ry, gx, gy);
+        return;
+    }
     const double dx = 0.000001;
     double qx = rx, qy = ry;
     if (lane == 0) { qx -= dx; }
@@ -590,6 +594,10 @@ __device__ __forceinline__ void thread_grad_prel(const TrajView &tv, const Shape
         }
         if (H.rs % 2 != 0) { vx = -vx; vy = -vy; }
         gx = vx; gy = vy;
+        return;
+    }
+    if (SHAPE == SH_CIRCLE) {
+        dev::circle_grad1<XFORM>(S, rx, ry, gx, gy);
         return;
     }
     const double dx = 0.000001;
@@ -1037,6 +1045,8 @@ __global__ void k_shape_grad(const __grid_constant__ ShapeParams S, const double
         if (z > 0.0) { double nn = sqrt(z); vx /= nn; vy /= nn; }
         if (H.rs % 2 != 0) { vx = -vx; vy = -vy; }
         gx = vx; gy = vy;
+    } else if (SHAPE == SH_CIRCLE) {
+        dev::circle_grad1<XFORM>(S, rx, ry, gx, gy);
     } else {
         const double dx = 0.000001;
         double t0 = rx, t1 = ry;
@@ -1089,7 +1099,11 @@ struct LaunchCfg {
 template <int SHAPE, bool XFORM>
 static cudaError_t launch_shape(const KernelArgs &A, const ShapeParams &S, const LaunchCfg &cfg, int N) {
     cudaError_t e;
-    static bool attr_set = false;
+    // the attribute is per device (a process may hold contexts on several GPUs): one flag per device ordinal
+    static bool attr_set_dev[64] = {};
+    int dev_ord = 0;
+    cudaGetDevice(&dev_ord);
+    bool &attr_set = attr_set_dev[dev_ord & 63];
     if (!attr_set) {
         e = cudaFuncSetAttribute(k_outer<SHAPE, XFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;

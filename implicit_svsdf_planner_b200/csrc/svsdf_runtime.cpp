@@ -113,6 +113,10 @@ struct svsdf_ctx {
     double gpu_ms_total = 0.0;
     bool time_kernels = false;
     int last_status = 0;
+    // test hooks, read ONCE at svsdf_create (SVSDF_FORCE_GRID_OUTER / SVSDF_FORCE_BATCHED): exercise the batched schedule
+    // on small inputs; -1 = not set
+    int force_grid_outer = -1;
+    int force_batched = -1;
 };
 
 namespace {
@@ -340,10 +344,7 @@ int run_kernels(svsdf_ctx *ctx, const double *d_points, int64_t P, bool reduce, 
     rc = refresh_occupancy(ctx);
     if (rc) return rc;
     int grid = grid_for(ctx, P);
-    if (const char *fg = std::getenv("SVSDF_FORCE_GRID_OUTER")) {  // test hook: exercise the batched path on small inputs
-        const int g = std::atoi(fg);
-        if (g > 0) grid = g;
-    }
+    if (ctx->force_grid_outer > 0) grid = ctx->force_grid_outer;  // test hook
     const int nacc = 19 * N + 1;
     if (reduce) {
         int64_t need = (int64_t)grid * nacc;
@@ -379,7 +380,7 @@ int run_kernels(svsdf_ctx *ctx, const double *d_points, int64_t P, bool reduce, 
     A.want_gsip = gsip ? 1 : 0;
     // batched path pays off once every warp owns a couple of dozen points; small problems keep one point per warp
     A.batched = (P >= (int64_t)16 * grid * kWarpsPerBlock) ? 1 : 0;
-    if (const char *fb = std::getenv("SVSDF_FORCE_BATCHED")) A.batched = std::atoi(fb);
+    if (ctx->force_batched >= 0) A.batched = ctx->force_batched;  // test hook
     A.inside_flag = ctx->d_flag;
     A.inside_tstar = ctx->d_inside_tstar;
     A.inside_list = ctx->d_inside_list;
@@ -640,6 +641,10 @@ static int front_params_with_map(svsdf_ctx *ctx, FrontParams &F, const char *who
         ctx->err = std::string(who) + ": the map was packed for another kernel_size (its inflation must be (kernel_size - 1) / 2)";
         return SVSDF_ERR_INVALID;
     }
+    if (F.res != F.map_res) {  // the reference has ONE conf.occupancy_resolution for the map and the shape kernels
+        ctx->err = std::string(who) + ": svsdf_front_init's occupancy_resolution differs from the map resolution";
+        return SVSDF_ERR_INVALID;
+    }
     return SVSDF_OK;
 }
 
@@ -784,6 +789,8 @@ int svsdf_create(const svsdf_config *cfg, svsdf_ctx **out) {
     ctx->rho = cfg->rho;
     ctx->device = cfg->device;
     ctx->strict = cfg->strict_fp != 0;
+    if (const char *fg = std::getenv("SVSDF_FORCE_GRID_OUTER")) ctx->force_grid_outer = std::atoi(fg);
+    if (const char *fb = std::getenv("SVSDF_FORCE_BATCHED")) ctx->force_batched = std::atoi(fb);
     auto fail = [&](cudaError_t e) {
         std::fprintf(stderr, "svsdf_create: %s\n", cudaGetErrorString(e));
         svsdf_destroy(ctx);
@@ -1121,6 +1128,9 @@ int svsdf_optimize(svsdf_ctx *ctx, const double *initS, const double *finalS, do
         stats->seconds = std::chrono::duration<double>(t1 - t0).count();
         stats->gpu_seconds = ctx->gpu_ms_total * 1e-3;
     }
+    // an evaluation that failed (points not set, CUDA error, duration >= 300 s) is an error of the run, whatever the
+    // solver made of the NaN it was handed
+    if (ctx->last_status != SVSDF_OK) return ctx->last_status;
     int ret = R.status;
     if (ret == 0) ret = 1;  // back_end_optimizer.cpp:66-69
     return ret;

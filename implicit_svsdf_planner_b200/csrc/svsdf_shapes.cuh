@@ -472,5 +472,21 @@ __device__ __forceinline__ double shape_sdf(const ShapeParams &S, double rx, dou
     return ShapeFn<SHAPE>::sdf(S, rx, ry);
 }
 
+// Circle overrides getonlyGrad1 (Shape.hpp:487-497): the normalised ((p - trans) * Rotate).head(2), no finite difference
+template <bool XFORM>
+__device__ __forceinline__ void circle_grad1(const ShapeParams &S, double rx, double ry, double &gx, double &gy) {
+    if (XFORM) {
+        double v0 = rx - S.trans[0], v1 = ry - S.trans[1];
+        rx = v0 * S.rot[0] + v1 * S.rot[2];
+        ry = v0 * S.rot[1] + v1 * S.rot[3];
+    }
+    double z = rx * rx + ry * ry;
+    if (z > 0.0) {  // Eigen normalize(): divides by sqrt(squaredNorm)
+        double n = sqrt(z);
+        rx /= n; ry /= n;
+    }
+    gx = rx; gy = ry;
+}
+
 }  // namespace dev
 }  // namespace svsdf

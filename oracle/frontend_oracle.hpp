@@ -8,7 +8,9 @@
 //   SweptVolumeManager::kernelConv        swept_volume/include/swept_volume/sw_manager.hpp:1033-1096 (bool and byte variants)
 //   visit_kernels_by_distance             sw_manager.hpp:1099-1156
 //   checkKernelValue                      sw_manager.hpp:1158-1169   (`#define pi 3.1415926536`, :20)
-// PARITY UNPINNED (no reference tests / golden vectors for this path; the reference cannot be compiled here).  Pins:
+// initShape (the yaw-indexed byte kernels) is PINNED to the reference's own BasicShape::initShape compiled from Shape.hpp
+// (oracle/_ref/libref_path_*.so; tests/test_oracle_ref_pin.py::test_init_shape_kernels_match_reference_code, all 16 registry
+// shapes, identical bytes).  kernelConv / checkKernelValue / the A* bookkeeping remain restatements (parity unpinned).  Pins:
 // the two kernelConv variants of the reference must agree with each other, closed-form kernels of the Circle, and the
 // byte-level layout shared with generateMapKernel2D (tests/test_oracle_frontend.py).
 // The Polygon fallback is not covered: its rotated overload takes a Matrix2d and does not override the virtual the

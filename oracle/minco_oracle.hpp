@@ -1,4 +1,7 @@
-// oracle/minco_oracle.hpp — TEST INFRASTRUCTURE ONLY (see svsdf_oracle.hpp header; parity unpinned).
+// oracle/minco_oracle.hpp — TEST INFRASTRUCTURE ONLY (see svsdf_oracle.hpp header).
+// MINCO_S3NU, the tau<->T maps and the cost callback are pinned to the reference's own minco.hpp / back_end_optimizer.hpp
+// code (oracle/_ref/libref_path_*.so, tests/test_oracle_ref_pin.py: b, energy, gradients, adjoint to 1e-13 relative —
+// Eigen's reduction order inside getEnergy/propogateGrad is the only freedom); the L-BFGS is a restatement of lbfgs_ref.hpp..
 //
 // Restatement of  utils/include/utils/minco.hpp (BandedSystem :43-198, MINCO_S3NU :397-655),
 // the tau<->T maps and cost wrapper of planner_algorithm/include/planner_algorithm/back_end_optimizer.hpp

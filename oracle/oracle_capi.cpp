@@ -288,6 +288,14 @@ void orc_minco_propagate(const double *initS, const double *finalS, int N, const
     m.setParameters(q, T);
     m.propogateGrad(gdC, gdT, gradQ, gradT);
 }
+// smoothedL1 (back_end_optimizer.hpp:316-340) over n samples; ret[i] = its boolean return
+void orc_smoothed_l1(int64_t n, const double *x, double mu, double *f, double *df, uint8_t *ret) {
+    for (int64_t i = 0; i < n; ++i) {
+        double ff = 0, dd = 0;
+        ret[i] = smoothedL1(x[i], mu, ff, dd) ? 1 : 0;
+        f[i] = ff; df[i] = dd;
+    }
+}
 void orc_forward_T(int n, const double *tau, double *T) { for (int i = 0; i < n; ++i) T[i] = forwardT1(tau[i]); }
 void orc_backward_T(int n, const double *T, double *tau) { for (int i = 0; i < n; ++i) tau[i] = backwardT1(T[i]); }
 

@@ -3,11 +3,12 @@
 // Plain-C++ (no Eigen) restatement of the reference's 2-D robot-shape SDF functors
 //   /root/reference/src/utils/include/utils/Shape.hpp
 // one function per shape class, same operation order as the reference source, double precision.
-// PARITY UNPINNED for the analytic functors: the reference ships no golden vectors / known-answer tests for these
-// functions and Shape.hpp cannot be compiled in this environment (needs Eigen/ROS/PCL); see DESIGN.md §4.  The mesh
-// functor's winding number IS pinned against the reference's own compiled code (oracle/_ref, tests/golden/fwn_ref.npz).
-// The pins we do have are in tests/: closed-form known answers, the Eikonal property, and the
-// reference's own shapes/*.obj outlines (tests/golden/obj_outlines.json).
+// PINNED to the reference's own classes: oracle/_ref/libref_path_*.so compiles the 16 registry classes + Circle + Polygon
+// verbatim from Shape.hpp (oracle/ref_extract.py, oracle/ref_path_shim.cpp); tests/test_oracle_ref_pin.py requires
+// getonlySDF / getonlyGrad1 of this file to equal them BIT FOR BIT (1e5 random points per shape live, 2 000 in the
+// committed fixture tests/golden/ref_pin_shapes.npz, two body-frame pre-transforms).  The mesh functor's winding number is
+// pinned against the reference's own compiled FWN code (oracle/_ref/libref_fwn.so, tests/golden/fwn_ref.npz).
+// Further sanity pins in tests/: closed-form known answers, the Eikonal property, the reference's shapes/*.obj outlines.
 #pragma once
 #include <algorithm>
 #include <cmath>
@@ -520,6 +521,17 @@ inline void shape_grad1(const Shape &S, double rx, double ry, double rz, double 
         }
         if (H.rs % 2 != 0) { vx = -vx; vy = -vy; vz = -vz; }
         g[0] = vx; g[1] = vy; g[2] = vz;
+        return;
+    }
+    if (S.id == SH_CIRCLE) {  // Circle overrides getonlyGrad1 (Shape.hpp:487-497): normalised ((p - trans) * Rotate).head(2)
+        double px, py;
+        pretransform(S, rx, ry, rz, px, py);
+        double z = px * px + py * py;
+        if (z > 0.0) {  // Eigen normalize()
+            double n = std::sqrt(z);
+            px /= n; py /= n;
+        }
+        g[0] = px; g[1] = py; g[2] = 0.0;
         return;
     }
     double dx = 0.000001;

@@ -4,12 +4,16 @@
 // It is the checker for the CUDA product path and the timed "cpu_baseline"/"--impl reference" leg of
 // bench.py.  Nothing under implicit_svsdf_planner_b200/ may include, link or call this file.
 //
-// PARITY UNPINNED: the reference (ZJU-FAST-Lab/Implicit-SVSDF-Planner @ f18fd91) ships no golden
-// vectors or tests for this path and cannot be compiled here (hot-path headers need Eigen, ROS, PCL,
-// libigl — none present), so this restatement is pinned only by its own known-answer
-// and finite-difference tests (tests/test_oracle_*.py), by the reference's shape meshes, by a trace of the reference's
-// own LMBM binary driving it (tests/golden/lmbm_trace_star_400.npz) and — mesh functor only — by the reference's own
-// fast-winding-number code compiled into oracle/_ref (tests/golden/fwn_ref.npz).
+// PARITY PINNED TO THE REFERENCE'S OWN SOURCE (round 2): the reference (ZJU-FAST-Lab/Implicit-SVSDF-Planner @ f18fd91)
+// ships no golden vectors for this path and its headers need Eigen/ROS/PCL (absent here), but the arithmetic itself
+// compiles: `make -C oracle ref_path` builds oracle/_ref/libref_path_*.so from the reference tree where it lies
+// (trajectory.hpp, minco.hpp whole; the Shape.hpp classes, the SweptVolumeManager query methods and the TrajOptimizer
+// penalty loop cut verbatim by oracle/ref_extract.py; Eigen = the stand-in in oracle/ref_shim).  tests/test_oracle_ref_pin.py
+// holds this restatement to it: every per-point output (Piece<5> samples, sdf, t*, gradient, outside and GSIP points,
+// smoothedL1, tau<->T) BIT FOR BIT, sums (cost, gradC, gradT, f, g, MINCO) to summation-order rounding; fixtures of the
+// reference's outputs are committed as tests/golden/ref_pin_*.npz.  Also: a trace of the reference's own LMBM binary driving
+// this code (tests/golden/lmbm_trace_star_400.npz) and, for the mesh functor, the reference's fast-winding-number code
+// compiled into oracle/_ref (tests/golden/fwn_ref.npz).
 //
 // Every function cites the reference file:line it follows (paths relative to /root/reference/src).
 #pragma once
