@@ -81,7 +81,7 @@ EVAL_T = C.CFUNCTYPE(C.c_double, C.c_void_p, dp, dp, C.c_int)
 
 # every symbol include/svsdf.h declares (tests check the library exports all of them)
 EXPORTED_SYMBOLS = [
-    "svsdf_default_config", "svsdf_create", "svsdf_destroy", "svsdf_last_error", "svsdf_shape_id",
+    "svsdf_default_config", "svsdf_create", "svsdf_destroy", "svsdf_last_error", "svsdf_shape_id", "svsdf_shape_bound_radius",
     "svsdf_set_points", "svsdf_set_points_device", "svsdf_set_traj", "svsdf_query", "svsdf_cost_grad",
     "svsdf_set_boundary", "svsdf_evaluate", "svsdf_last_costs", "svsdf_get_traj", "svsdf_default_lbfgs_params",
     "svsdf_optimize", "svsdf_minco_forward", "svsdf_minco_propagate", "svsdf_forward_T", "svsdf_backward_T",
@@ -229,6 +229,26 @@ def backward_T(T):
     tau = np.empty_like(T)
     lib().svsdf_backward_T(T.shape[0], _p(T), _p(tau))
     return tau
+
+
+def shape_bound_radius(shape="star", poly_params=(0.0, 0.0, 0.0), polygon=None) -> float:
+    """svsdf_shape_bound_radius: R with sdf(q) >= |q| - R for the configured shape functor (host-only, no GPU needed)."""
+    L = lib()
+    cfg = _Config()
+    L.svsdf_default_config(C.byref(cfg))
+    name = (shape or "").encode()
+    cfg.shape = name
+    cfg.poly_params = (C.c_double * 3)(*[float(v) for v in poly_params])
+    poly = None
+    if polygon is not None:
+        poly = _f64(polygon).reshape(-1)
+        cfg.polygon_xy = _p(poly)
+        cfg.polygon_n = poly.size // 2
+    out = C.c_double()
+    rc = L.svsdf_shape_bound_radius(C.byref(cfg), C.byref(out))
+    if rc != 0:
+        raise SvsdfError(f"svsdf_shape_bound_radius failed with status {rc}")
+    return out.value
 
 
 def read_obj(path: str):

@@ -538,25 +538,64 @@ __device__ __forceinline__ Contribution point_contribution(const TrajView &tv, c
 // per-point work that have no intra-point parallelism worth a warp are run one point per LANE, literally as the
 // reference's loops, and only gradientDescent (29-way speculative) stays one point per WARP.
 // ------------------------------------------------------------------------------------------------
-// choiceTInit<false>(p, 0.15) (sw_manager.hpp:538-581); layer 1 reads the shared pose table
+// choiceTInit<false>(p, 0.15) (sw_manager.hpp:538-581); layer 1 reads the shared pose table.
+//
+// Layer 1 (the 0.15 s lattice over the whole trajectory, K1 = 134 samples at D = 20 s) is an arg-min with the rule
+// "first strict minimum wins, nothing >= 1e9 wins".  That result is the lexicographic minimum of (f_k, k) over the samples
+// with f_k < 1e9, whatever the order of evaluation — so samples that PROVABLY cannot attain the minimum need not be
+// evaluated.  The shape functors are distances outside the shape: f_k = sdf(R_k^T (p - x_k)) >= |p - x_k| - rout
+// (S.rout: circumradius + margin, checked against the oracle for every shape).  Pass 1 finds the lattice pose nearest to p
+// (5 flops per sample) and evaluates it: m; pass 2 walks k upwards and evaluates only samples with
+// |p - x_k| <= m + rout, tightening m as it goes.  A skipped sample has f_k > m >= the final minimum.  Typically ~15 of
+// the 134 samples survive; bits identical to the full scan (GPU parity tests, strict build).
 template <int SHAPE, bool XFORM>
 __device__ __forceinline__ void thread_choice_t_init(const TrajView &tv, const ShapeParams &S, double px, double py,
                                                      double &seed, double &min_dis, int &evals) {
-    min_dis = 1e9;
-    seed = 0.0;
-    uint32_t ps = tv.spose;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
     const uint32_t row = 8u * (uint32_t)tv.K1pad;
+    const int K1 = tv.K1;
+    // pass 1: nearest lattice pose (rows are 16-byte aligned and K1pad is even: two samples per load)
+    double bd2 = INF;
+    int k0 = 0;
+    {
+        uint32_t ps = tv.spose;
 #pragma unroll 1
-    for (int k = 0; k < tv.K1; ++k, ps += 8) {
-        double rx, ry;
-        rel_from_pose(px, py, lds_f64(ps), lds_f64(ps + row), lds_f64(ps + 2 * row), lds_f64(ps + 3 * row), rx, ry);
-        const double f = dev::shape_sdf<SHAPE, XFORM>(S, rx, ry);
-        if (f < min_dis) {
-            min_dis = f;
-            seed = lds_f64(tv.slat + 8u * (uint32_t)k);
+        for (int k = 0; k < K1; k += 2, ps += 16) {
+            double x0, x1, y0, y1;
+            lds_v2(ps, x0, x1);
+            lds_v2(ps + row, y0, y1);
+            const double ax = px - x0, ay = py - y0, bx = px - x1, by = py - y1;
+            const double d0 = ax * ax + ay * ay, d1 = bx * bx + by * by;
+            if (d0 < bd2) { bd2 = d0; k0 = k; }
+            if (k + 1 < K1 && d1 < bd2) { bd2 = d1; k0 = k + 1; }
         }
     }
-    evals += tv.K1;
+    // pass 2: the nearest pose first (it = -1), then every sample that can still reach the minimum, k ascending; ties are
+    // resolved towards the smaller k, so the visiting order does not matter.  One functor call site.
+    min_dis = 1e9;
+    int kb = -1, ne = 0;
+    double thr2 = INF;  // squared pruning radius: |p - x_k| > min_dis + rout  =>  f_k > min_dis
+#pragma unroll 1
+    for (int it = -1; it < K1; ++it) {
+        const int k = (it < 0) ? k0 : it;
+        const uint32_t ps = tv.spose + 8u * (uint32_t)k;
+        const double xk = lds_f64(ps), yk = lds_f64(ps + row);
+        const double ax = px - xk, ay = py - yk;
+        const double d2 = ax * ax + ay * ay;
+        if (it >= 0 && (!(d2 <= thr2) || k == k0)) continue;
+        double rx, ry;
+        rel_from_pose(px, py, xk, yk, lds_f64(ps + 2 * row), lds_f64(ps + 3 * row), rx, ry);
+        const double f = dev::shape_sdf<SHAPE, XFORM>(S, rx, ry);
+        ++ne;
+        if (f < min_dis || (f == min_dis && k < kb)) {
+            min_dis = f;
+            kb = k;
+            const double thr = f + S.rout;               // < 0 cannot happen for a distance function; then no pruning
+            thr2 = (thr >= 0.0) ? thr * thr : INF;
+        }
+    }
+    seed = (kb >= 0) ? lds_f64(tv.slat + 8u * (uint32_t)kb) : 0.0;
+    evals += ne;
     double dt = 0.15;
     int hint = 0;  // piece of the previous sample (the windows are <= 0.3 s wide)
 #pragma unroll 1
@@ -611,6 +650,125 @@ __device__ __forceinline__ void thread_grad_prel(const TrajView &tv, const Shape
     }
     gx = (f[1] - f[0]) / (2 * dx);
     gy = (f[3] - f[2]) / (2 * dx);
+}
+
+// ------------------------------------------------------------------------------------------------
+// gradientDescent (sw_manager.hpp:1249-1325) for a BATCH of points, a quarter warp (8 lanes) per point, four points in
+// flight per warp — the batched path of k_outer and the interior-branch kernel.
+//
+// The reference's loop, per descent step: slope sign from the finite difference at x (2 evaluations, recomputed for every
+// halving in the reference but always at the same x, hence the same bits), then candidates x - sign * 0.01 * 2^-j for
+// j = 0, 1, ... until the first one that decreases f (29 failures end the descent).  Measured on configs 1-3 (oracle,
+// orc_descent_stats): ~8 steps per point, accepted j spread evenly over 7..20 (never 1..6), so a full warp per step
+// (29 candidates + slope, the round-1 design) spends most of its lanes on candidates beyond the accepted one, and one lane per
+// point (sequential, 155 +- 65 evaluations) leaves the warp waiting for its slowest lane.  Eight lanes per point in
+// rounds of one evaluation per lane:
+//   R1   lanes 0/1 of the quarter: the two finite-difference samples; lanes 2..7: candidates j = 0..5 in the PREDICTED
+//        direction (the slope flips after every non-full step because the accepted step is the largest decreasing one)
+//   RN   candidates j = jbase .. jbase + 7 in the known direction (jbase = 6, 14, 22 after R1; 0, 8, 16, 24 after a
+//        misprediction)
+//   F0   f(x0) when choiceTInit found nothing below 1e9 (degenerate input; the reference evaluates it at iter == 0)
+// => ~21 lane-evaluations per step instead of 31.  A quarter that finishes its point stores (sdf, t*) and takes the next
+// point of the batch (warp-uniform cursor), so the four quarters stay busy until the batch runs dry.  Every decision is
+// the sequential loop's decision given the same SDF values: the accepted halving is the FIRST j whose candidate
+// decreases f, the sign comes from the finite difference — bit-identical results (GPU parity tests, strict build).
+// In: lane i (< nb) holds point i of the batch (px, py, choiceTInit seed and minimum).  Out: res[2 i] = sdf, res[2 i + 1] = t*.
+// ------------------------------------------------------------------------------------------------
+template <int SHAPE, bool XFORM>
+__device__ __forceinline__ void descent_engine(const TrajView &tv, const ShapeParams &S, int nb, double mpx, double mpy,
+                                               double mseed, double mmin, double *res, unsigned &evals) {
+    enum { E_F0 = 0, E_R1 = 1, E_RN = 2 };
+    const int lane = threadIdx.x & 31, q = lane & 7, qbase = lane & 24;
+    const double D = tv.D;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    const int hi001 = __double2hiint(0.01), lo001 = __double2loint(0.01);
+    // state of this lane's quarter (identical in its 8 lanes)
+    int pt = -1, mode = E_R1, iter = 0, pred = 1, sgn = 1, jbase = 0, hint = 0;
+    double px = 0.0, py = 0.0, x = 0.0, fx = 0.0, prev_x = 0.0, t_min = 0.0, t_max = 0.0;
+    bool need = true;   // the quarter wants a point
+    int next_i = 0;     // warp-uniform cursor into the batch
+#pragma unroll 1
+    for (;;) {
+        // ---- hand the next points of the batch to the quarters that are free ----
+        const unsigned want = __ballot_sync(FULL, need && q == 0);
+        if (want) {
+            const int cand = next_i + __popc(want & ((1u << qbase) - 1u));
+            next_i += __popc(want);
+            const bool take = need && cand < nb;
+            const int src = take ? cand : lane;
+            const double npx = __shfl_sync(FULL, mpx, src), npy = __shfl_sync(FULL, mpy, src);
+            const double nsd = __shfl_sync(FULL, mseed, src), nmn = __shfl_sync(FULL, mmin, src);
+            if (need) {
+                need = false;
+                pt = -1;
+                if (take) {
+                    pt = cand;
+                    px = npx; py = npy;
+                    x = nsd; fx = nmn; prev_x = nsd;   // `prev_x = x` after the (true) first loop test
+                    t_min = smaxd(0.0, nsd - 3.4);      // :856-857
+                    t_max = smind(nsd + 3.4, D);
+                    iter = 0; pred = 1; sgn = 1; jbase = 0; hint = 0;
+                    mode = (nmn >= 1e9) ? E_F0 : E_R1;
+                }
+            }
+        }
+        if (!__any_sync(FULL, pt >= 0)) break;
+
+        // ---- this lane's sample (straight-line code: the four quarters are in different modes) ----
+        const bool isR1 = mode == E_R1, isF0 = mode == E_F0;
+        const bool slope = isR1 && q < 2;
+        const int j = isR1 ? q - 2 : jbase + q;
+        const bool cand = !isF0 && !slope && j <= 28;
+        evals += (pt >= 0 && (cand || slope || (isF0 && q == 0))) ? 1u : 0u;
+        // candidate: tau = 0.01 halved j times (exact: subtract j from the exponent field); change = -tau * sign
+        const int dir = isR1 ? pred : sgn;
+        const int tau_hi = (hi001 - ((j & 31) << 20)) ^ ((dir > 0) ? (int)0x80000000 : 0);
+        // slope samples: t1 = max(0, x - 1e-6), t2 = min(D, x + 1e-6)   (:798-806)
+        const double off = slope ? ((q == 0) ? -0.000001 : 0.000001) : __hiloint2double(tau_hi, lo001);
+        const double lo_l = slope ? ((q == 0) ? 0.0 : -INF) : t_min;
+        const double hi_l = slope ? ((q == 0) ? INF : D) : t_max;
+        const double tc = smaxd(smind(x + off, hi_l), lo_l);
+        const double tq = (cand || slope) ? tc : x;
+        const double fq = eval_sdf<SHAPE, XFORM>(tv, S, px, py, tq, hint);
+
+        // ---- collectives (all lanes), then each quarter's decision, again without branches ----
+        const unsigned m8 = (__ballot_sync(FULL, (fq - fx) < 0) >> qbase) & 0xffu;
+        const double f0 = __shfl_sync(FULL, fq, qbase), f1 = __shfl_sync(FULL, fq, qbase + 1);
+        const double g = (f1 - f0) * 500000;
+        const int s_new = (int)(g > 0) - (int)(g < 0);
+        sgn = isR1 ? s_new : sgn;
+        const bool zero = isR1 && sgn == 0;              // all 29 candidates equal x: none decreases f
+        const bool mispred = isR1 && sgn != 0 && sgn != pred;
+        const int nvalid = max(0, min(8, 29 - jbase));   // (idle quarters keep counting jbase up)
+        const unsigned mc = isR1 ? (m8 >> 2) : (m8 & ((1u << nvalid) - 1u));
+        const bool hit = (pt >= 0) && !isF0 && !zero && !mispred && mc != 0u;   // first decreasing candidate found
+        const int k = __ffs(mc) - 1;
+        const int jacc = isR1 ? k : jbase + k;
+        const int src = hit ? qbase + (isR1 ? k + 2 : k) : lane;
+        const double xacc = __shfl_sync(FULL, tq, src), facc = __shfl_sync(FULL, fq, src);
+        // no decreasing candidate in this round: next chunk of halvings (R1: j = 6.., or j = 0.. after a misprediction)
+        const int jb_next = isR1 ? (mispred ? 0 : 6) : jbase + 8;
+        const bool failed = (pt >= 0) && !isF0 && (zero || (!hit && !mispred && jb_next > 28));
+        // a full, unclamped stride means we are still walking downhill: same slope sign next; otherwise the step overshot
+        // the minimiser (tau_j is the largest decreasing step) and the slope flips
+        const bool walking = (jacc == 0) && (xacc == x + (-0.01 * (double)sgn));
+        pred = hit ? (walking ? sgn : -sgn) : pred;
+        iter += hit ? jacc + 1 : (failed ? 29 : 0);
+        x = hit ? xacc : x;
+        fx = hit ? facc : (isF0 ? f0 : fx);
+        const bool step_end = hit || failed;
+        // while (iter < max_iter && !stop && abs(x - prev_x) > tol)   (:1288)
+        const bool running = (iter < 1000) && !failed && (fabs(x - prev_x) > 1e-16);
+        prev_x = step_end ? x : prev_x;
+        mode = (step_end || isF0) ? E_R1 : E_RN;
+        jbase = jb_next;
+        if (step_end && !running) {
+            if (q == 0) { res[2 * pt] = fx; res[2 * pt + 1] = x; }
+            pt = -1;
+            need = true;
+        }
+    }
+    __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -675,7 +833,8 @@ __global__ void k_pose_table(double *blob) {
 #ifndef SVSDF_GSIP_MIN_CTAS
 #define SVSDF_GSIP_MIN_CTAS 3
 #endif
-template <int SHAPE, bool XFORM>
+// BATCHED selects the schedule at compile time (two kernels: each carries only its own evaluation sites)
+template <int SHAPE, bool XFORM, bool BATCHED>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, (SHAPE == SH_MESH) ? 2 : SVSDF_OUTER_MIN_CTAS)
     k_outer(const __grid_constant__ KernelArgs A, const __grid_constant__ ShapeParams S) {
     extern __shared__ __align__(16) double smem[];
@@ -693,39 +852,52 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (SHAPE == SH_MESH) ? 2 : 
     const int64_t wstride = (int64_t)gridDim.x * kWarpsPerBlock;
     const int64_t first = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
     unsigned long long my_evals = 0;
-    // The warp owns points first, first + wstride, ...; it walks them in batches of 32 (lane i <-> i-th point of the
-    // batch).  Batched path (many points per warp): choiceTInit and the FD gradient / penalty / chain rule run one point
-    // per lane; gradientDescent runs one point per warp, one batch member after the other.  Sparse path (few points per
-    // warp, i.e. small problems): everything one point per warp, as solve_outer / grad_prel do.
-    for (int64_t bfirst = first; bfirst < A.P; bfirst += 32 * wstride) {
-        const int64_t my_pt = bfirst + (int64_t)lane * wstride;
-        const bool my_valid = my_pt < A.P;
-        const int nb = (int)min((int64_t)32, (A.P - bfirst + wstride - 1) / wstride);  // batch size (warp-uniform)
+    double *res = smem + A.blob_doubles + kWarpsPerBlock * nacc + warp * 64;  // descent_engine results: [32] x (sdf, t*)
+    // The warp walks its points in batches of up to 32 (lane i <-> i-th point of the batch).
+    //  * Batched schedule (large P): the points are cut into nB = W * ceil(P / 32 W) CONTIGUOUS batches of equal size
+    //    (+-1; neighbouring map cells: the lanes of a warp then prune the same layer-1 samples and run descents of similar
+    //    length), warp w owns batches w, w + W, ... (strided: a warp's batches come from different regions of the map, so
+    //    hard regions are spread over the warps; static, hence deterministic).  choiceTInit and the FD gradient /
+    //    penalty / chain rule run one point per lane, gradientDescent one point per quarter warp (descent_engine).
+    //  * Sparse schedule (few points per warp, i.e. small problems): the warp owns points w, w + W, ...; everything one
+    //    point per warp, as solve_outer / grad_prel do (lowest latency).
+    constexpr bool chunked = BATCHED;
+    const int64_t lstride = chunked ? 1 : wstride;  // distance between the points of neighbouring lanes
+    const int64_t nB = wstride * ((A.P + 32 * wstride - 1) / (32 * wstride));   // batches (batched schedule)
+    for (int64_t bi = first; chunked ? (bi < nB) : (bi < A.P); bi += chunked ? wstride : 32 * wstride) {
+        // batched: batch bi covers [bi P / nB, (bi + 1) P / nB); sparse: points bi, bi + W, ...
+        const int64_t bfirst = chunked ? (bi * A.P) / nB : bi;
+        const int64_t bend = chunked ? ((bi + 1) * A.P) / nB : A.P;
+        const int64_t my_pt = bfirst + (int64_t)lane * lstride;
+        const int nb = (int)min((int64_t)32, (bend - bfirst + lstride - 1) / lstride);  // batch size (warp-uniform)
+        const bool my_valid = lane < nb;
         const int64_t ld_pt = my_valid ? my_pt : bfirst;
         const double mpx = __ldg(A.points_xy + 2 * ld_pt), mpy = __ldg(A.points_xy + 2 * ld_pt + 1);
-        const bool batched = A.batched && nb >= 12;
+        const bool batched = chunked && nb >= 8;
         double m_seed = 0.0, m_min = 1e9, m_sdf = 0.0, m_ts = 0.0, m_gx = 0.0, m_gy = 0.0;
-        if (batched) {
+        if (BATCHED && batched) {
             int ev = 0;
             if (my_valid) thread_choice_t_init<SHAPE, XFORM>(tv, S, mpx, mpy, m_seed, m_min, ev);
-            my_evals += (unsigned long long)__reduce_add_sync(FULL, ev);
             __syncwarp();
-        }
+            unsigned ev2 = 0;
+            descent_engine<SHAPE, XFORM>(tv, S, nb, mpx, mpy, m_seed, m_min, res, ev2);
+            my_evals += (unsigned long long)__reduce_add_sync(FULL, (unsigned)ev + ev2);
+            if (my_valid) { m_sdf = res[2 * lane]; m_ts = res[2 * lane + 1]; }
+            __syncwarp();
+        } else {
 #pragma unroll 1
-        for (int i = 0; i < nb; ++i) {
-            const double px = __shfl_sync(FULL, mpx, i), py = __shfl_sync(FULL, mpy, i);
-            const double sd = __shfl_sync(FULL, m_seed, i), mn = __shfl_sync(FULL, m_min, i);
-            const OuterResult R = solve_outer<SHAPE, XFORM>(tv, S, px, py, batched, sd, mn);
-            my_evals += (unsigned long long)R.evals;
-            if (lane == i) { m_sdf = R.sdf; m_ts = R.tstar; }
-            if (!batched) {
+            for (int i = 0; i < nb; ++i) {
+                const double px = __shfl_sync(FULL, mpx, i), py = __shfl_sync(FULL, mpy, i);
+                const OuterResult R = solve_outer<SHAPE, XFORM>(tv, S, px, py);
+                my_evals += (unsigned long long)R.evals;
+                if (lane == i) { m_sdf = R.sdf; m_ts = R.tstar; }
                 double gx, gy;
                 grad_prel<SHAPE, XFORM>(tv, S, px, py, R.tstar, gx, gy);
                 if (lane == i) { m_gx = gx; m_gy = gy; }
             }
         }
         my_evals += 4ull * (unsigned long long)nb;
-        if (batched && my_valid) thread_grad_prel<SHAPE, XFORM>(tv, S, mpx, mpy, m_ts, m_gx, m_gy);
+        if (BATCHED && batched && my_valid) thread_grad_prel<SHAPE, XFORM>(tv, S, mpx, mpy, m_ts, m_gx, m_gy);
         // ---- per-lane epilogue: outputs, interior flag, penalty + chain rule (one point per lane) ----
         const bool inside = my_valid && A.want_gsip && !(m_sdf > 0);  // getTrueSDFofSweptVolume: `if (argmin_dis > 0) return`
         if (my_valid) {
@@ -1105,7 +1277,9 @@ static cudaError_t launch_shape(const KernelArgs &A, const ShapeParams &S, const
     cudaGetDevice(&dev_ord);
     bool &attr_set = attr_set_dev[dev_ord & 63];
     if (!attr_set) {
-        e = cudaFuncSetAttribute(k_outer<SHAPE, XFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        e = cudaFuncSetAttribute(k_outer<SHAPE, XFORM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_outer<SHAPE, XFORM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(k_gsip<SHAPE, XFORM, kWarpsPerBlock>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
@@ -1113,7 +1287,8 @@ static cudaError_t launch_shape(const KernelArgs &A, const ShapeParams &S, const
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    k_outer<SHAPE, XFORM><<<cfg.grid_outer, kWarpsPerBlock * 32, cfg.smem_outer, cfg.stream>>>(A, S);
+    if (A.batched) k_outer<SHAPE, XFORM, true><<<cfg.grid_outer, kWarpsPerBlock * 32, cfg.smem_outer, cfg.stream>>>(A, S);
+    else k_outer<SHAPE, XFORM, false><<<cfg.grid_outer, kWarpsPerBlock * 32, cfg.smem_outer, cfg.stream>>>(A, S);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (cfg.after_outer) cudaEventRecord(cfg.after_outer, cfg.stream);
@@ -1160,11 +1335,14 @@ static cudaError_t dispatch(const KernelArgs &A, const ShapeParams &S, const Lau
 
 template <int SHAPE, bool XFORM>
 static cudaError_t occ_shape(size_t smem_outer, size_t smem_gsip, int *occ_outer, int *occ_gsip) {
-    cudaError_t e = cudaFuncSetAttribute(k_outer<SHAPE, XFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_outer<SHAPE, XFORM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_outer<SHAPE, XFORM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_gsip<SHAPE, XFORM, kWarpsPerBlock>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_outer, k_outer<SHAPE, XFORM>, kWarpsPerBlock * 32, smem_outer);
+    // the two schedules are compiled to the same register cap (launch bounds); the batched kernel sizes the full wave
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_outer, k_outer<SHAPE, XFORM, true>, kWarpsPerBlock * 32, smem_outer);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_gsip, k_gsip<SHAPE, XFORM, kWarpsPerBlock>, kWarpsPerBlock * 32, smem_gsip);
 }
@@ -1172,7 +1350,7 @@ static cudaError_t occ_shape(size_t smem_outer, size_t smem_gsip, int *occ_outer
 // Resident CTAs per SM of k_outer / k_gsip for this shape and trajectory size: the host sizes the grids as
 // SMs x occupancy so that the warp-stride loops run as exactly one full wave (no partial second wave).
 cudaError_t query_occupancy(const ShapeParams &S, int N, int blob_doubles, int *occ_outer, int *occ_gsip) {
-    const size_t so = (size_t)(blob_doubles + kWarpsPerBlock * (19 * N + 1)) * sizeof(double);
+    const size_t so = outer_smem_doubles(blob_doubles, N) * sizeof(double);
     const size_t sg = (size_t)blob_doubles * sizeof(double);
     const bool xf = S.has_xform != 0;
     switch (S.id) {
@@ -1214,7 +1392,7 @@ cudaError_t launch_cost_kernels(const KernelArgs &A, const ShapeParams &S, int N
     cfg.gsip_wide = gsip_wide != 0;
     cfg.grid_outer = grid_outer;
     cfg.grid_gsip = grid_gsip;
-    cfg.smem_outer = (size_t)(A.blob_doubles + kWarpsPerBlock * (19 * N + 1)) * sizeof(double);
+    cfg.smem_outer = outer_smem_doubles(A.blob_doubles, N) * sizeof(double);
     cfg.smem_gsip = (size_t)A.blob_doubles * sizeof(double);
     cfg.stream = stream;
     return S.has_xform ? dispatch<true>(A, S, cfg, N) : dispatch<false>(A, S, cfg, N);

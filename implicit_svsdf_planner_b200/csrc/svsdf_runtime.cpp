@@ -159,9 +159,18 @@ void build_shape(const svsdf_config &cfg, ShapeParams &S) {
     S.has_xform = !(S.trans[0] == 0.0 && S.trans[1] == 0.0 && S.rot[0] == 1.0 && S.rot[1] == 0.0 && S.rot[2] == 0.0 &&
                     S.rot[3] == 1.0);
     S.radius = 1.0;
+    S.rout = 1e300;
     if (cfg.mesh_faces && cfg.mesh_nf > 0) {  // triangle-mesh functor requested: overrides the registry name
         S.id = SH_MESH;
         return;
+    }
+    {
+        // Circumradius of each analytic shape about its own origin, rounded up with a 0.05 margin (measured: the largest
+        // |q| with sdf(q) <= 0; the functors are exact distances outside the shape, so sdf(q) >= |q| - R everywhere —
+        // tests/test_oracle_shapes.py::test_circumradius_bound checks every entry against the oracle, the GPU parity
+        // tests check the pruned scan bit for bit).  The body-frame pre-transform shifts the origin by |trans|.
+        static const double kRout[17] = {2.85, 2.36, 3.05, 3.05, 2.88, 2.97, 5.05, 3.65, 4.55, 4.63, 2.42, 3.84, 2.05, 4.52, 3.05, 6.05, 1.05};
+        if (S.id >= 0 && S.id <= SH_CIRCLE) S.rout = kRout[S.id] + std::sqrt(S.trans[0] * S.trans[0] + S.trans[1] * S.trans[1]);
     }
     switch (S.id) {
         case SH_HORSESHOE: S.cst[0] = std::cos(20.5); S.cst[1] = std::sin(20.5); break;  // Shape.hpp:855
@@ -210,6 +219,9 @@ void build_shape(const svsdf_config &cfg, ShapeParams &S) {
                 S.poly_ey[i] = xy[2 * j + 1];
             }
             S.has_xform = 0;
+            S.rout = 0.0;  // Polygon ignores trans/Rotate: the farthest vertex bounds it
+            for (int i = 0; i < n; ++i) S.rout = std::max(S.rout, std::sqrt(xy[2 * i] * xy[2 * i] + xy[2 * i + 1] * xy[2 * i + 1]));
+            S.rout += 0.05;
             break;
         }
         default: break;
@@ -392,7 +404,7 @@ int run_kernels(svsdf_ctx *ctx, const double *d_points, int64_t P, bool reduce, 
     const int gsip_wide = (reduce && ctx->last_n_inside >= 0 && ctx->last_n_inside <= ctx->sm_count) ? 1 : 0;
     const int grid_gsip = gsip_wide ? ctx->sm_count : ctx->sm_count * ctx->occ_gsip;
     if (!gsip) CK(cudaMemsetAsync(ctx->d_n_inside, 0, sizeof(int), ctx->stream));
-    size_t smem = (size_t)(A.blob_doubles + kWarpsPerBlock * nacc) * sizeof(double);
+    size_t smem = outer_smem_doubles(A.blob_doubles, N) * sizeof(double);
     if (smem > 200 * 1024) {
         ctx->err = "svsdf: trajectory blob does not fit in shared memory";
         return SVSDF_ERR_INVALID;
@@ -494,6 +506,13 @@ void svsdf_default_config(svsdf_config *cfg) {
 }
 
 int svsdf_shape_id(const char *name) { return shape_id_from_name(name); }
+int svsdf_shape_bound_radius(const svsdf_config *cfg, double *radius_out) {
+    if (!cfg || !radius_out) return SVSDF_ERR_INVALID;
+    ShapeParams S;
+    build_shape(*cfg, S);
+    *radius_out = S.rout;
+    return SVSDF_OK;
+}
 
 // Wavefront .obj -> (V, F): `v x y z` and `f i[/..] j[/..] k[/..] ...` records (1-based or negative indices), polygons
 // fan-triangulated — what igl::read_triangle_mesh yields for the reference's shapes/*.obj (Shape.hpp:285).

@@ -54,6 +54,9 @@ struct ShapeParams {
     double rot[4];      // Rotate(0,0),(0,1),(1,0),(1,1)  (Shape.hpp:288-294)
     double cst[4];      // per-shape host-computed constants (see shape_registry.cpp)
     double radius;      // Circle
+    double rout;        // conservative circumradius about the body origin (incl. |trans|): sdf(q) >= |q| - rout for every q.
+                        // Lets choiceTInit's layer-1 scan skip lattice samples that provably cannot be the minimum
+                        // (thread_choice_t_init).  >= 1e30 disables the pruning (mesh functor).
     int poly_n;         // Polygon edge count
     int pad_;
     double poly_sx[kMaxPolyEdges], poly_sy[kMaxPolyEdges], poly_ex[kMaxPolyEdges], poly_ey[kMaxPolyEdges];
@@ -89,6 +92,11 @@ SVSDF_HD inline BlobLayout blob_layout(int N, int K1) {
     L.total = L.off_pose + 4 * K1pad;
     L.total = (L.total + 1) & ~1;
     return L;
+}
+
+// dynamic shared memory of k_outer in doubles: [ blob | 8 warps x (19N + 1) accumulators | 8 warps x 32 x (sdf, t*) ]
+SVSDF_HD inline size_t outer_smem_doubles(int blob_doubles, int N) {
+    return (size_t)blob_doubles + (size_t)kWarpsPerBlock * (19 * N + 1) + (size_t)kWarpsPerBlock * 64;
 }
 
 // Penalty parameters (star.yaml: weight_p 60, safety_hor 0.7; smoothedL1 mu = 0.01 is a literal in the

@@ -80,6 +80,11 @@ void svsdf_destroy(svsdf_ctx *ctx);
 const char *svsdf_last_error(const svsdf_ctx *ctx);
 /* Shape registry lookup: returns the internal id (>= 0); unknown names map to the Polygon fallback id. */
 int svsdf_shape_id(const char *name);
+/* Radius R (about the body origin, pre-transform included) such that the configured shape functor satisfies
+   sdf(q) >= |q| - R for every body-frame point q.  The kernels use it to skip lattice samples of choiceTInit's first layer
+   (sw_manager.hpp:538-581) that provably cannot be the minimum; exposed so that the bound can be tested against the oracle
+   without a GPU.  Writes a value >= 1e300 when no bound is used (mesh functor).  Host-only, no context needed. */
+int svsdf_shape_bound_radius(const svsdf_config *cfg, double *radius_out);
 /* Read a Wavefront .obj (what igl::read_triangle_mesh does for yaml `inputdata`, utils/Shape.hpp:284-285): vertices
    (nv x 3 doubles) and fan-triangulated faces (nf x 3, 0-based), malloc'ed; release both with svsdf_free. */
 int svsdf_read_obj(const char *path, double **vertices_out, int *nv_out, int32_t **faces_out, int *nf_out);

@@ -193,6 +193,42 @@ double orc_choice_t_init(void *h, const double *p3, double dt) {
 void orc_gradient_descent(void *h, const double *p3, double tmin, double tmax, double x0, double *fx, double *x) {
     ((TrajOptimizerOracle *)h)->sv.gradientDescent(tmin, tmax, x0, *fx, *x, p3);
 }
+// Descent statistics per point (analysis tool for the kernel design, not a parity function): runs choiceTInit + the
+// reference's gradientDescent control flow and records the number of outer steps, the total number of halvings
+// (candidate evaluations) and a histogram of the accepted halving index (bin 29 = a step in which all 29 failed).
+void orc_descent_stats(void *h, int64_t P, const double *pts, int *steps, int *halvings, int64_t *jacc_hist30) {
+    TrajOptimizerOracle *o = (TrajOptimizerOracle *)h;
+    const SweptVolume &sv = o->sv;
+    for (int b = 0; b < 30; ++b) jacc_hist30[b] = 0;
+    for (int64_t i = 0; i < P; ++i) {
+        double p[3] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+        double ts = sv.choiceTInit(p, 0.15);
+        double t_min = std::max(0.0, ts - 3.4), t_max = std::min(ts + 3.4, sv.traj_duration);
+        double x = ts, prev_x = 10000000.0, fx = 0, tau;
+        int iter = 0, ns = 0, nh = 0;
+        bool stop = false;
+        while (iter < 1000 && !stop && std::abs(x - prev_x) > 1e-16) {
+            if (iter == 0) fx = sv.sdfAt(p, x);
+            double g = sv.sdfDotAt(p, x);
+            tau = 0.01;
+            prev_x = x;
+            ns++;
+            int acc = 29;
+            for (int div = 1; div < 30; div++) {
+                iter++;
+                nh++;
+                double xc = std::max(std::min(x + (-tau * ((int)(g > 0) - (g < 0))), t_max), t_min);
+                double fc = sv.sdfAt(p, xc);
+                if ((fc - fx) < 0) { x = xc; fx = fc; acc = div - 1; break; }
+                tau = 0.5 * tau;
+                if (div == 29) stop = true;
+            }
+            jacc_hist30[acc]++;
+        }
+        steps[i] = ns;
+        halvings[i] = nh;
+    }
+}
 void orc_count_evals(void *h, int on) {
     TrajOptimizerOracle *o = (TrajOptimizerOracle *)h;
     o->sv.count_evals = on != 0;

@@ -184,6 +184,29 @@ def test_batched_path_is_bit_identical_to_sparse_path(oracle_mod, scene2k, scene
     monkeypatch.delenv("SVSDF_FORCE_BATCHED", raising=False)
 
 
+@pytest.mark.parametrize("shape", ALL_SHAPES)
+def test_every_shape_through_the_batched_schedule_is_bitwise(oracle_mod, shape, monkeypatch):
+    """The batched schedule (layer 1 with exact pruning, quarter-warp descent engine) for every functor, with and without a
+    body-frame pre-transform: same bits as the oracle's plain loops."""
+    monkeypatch.setenv("SVSDF_FORCE_GRID_OUTER", "2")  # 16 warps -> batches of 25..32 points per warp
+    monkeypatch.setenv("SVSDF_FORCE_BATCHED", "1")
+    sc = scenes.make_scene("star", 8, 900, clearance=1.6, seed_map=777)
+    co = sc.coeffs_colmajor()
+    p = pts0(sc)
+    for pp in ((0.0, 0.0, 0.0), (0.4, -0.25, 33.0)):
+        ctx = api.Context(shape, poly_params=pp)
+        orc = oracle_mod.Oracle(shape, poly_params=pp, threads=oracle_mod.num_procs())
+        orc.set_traj(sc.T, co)
+        s_c, t_c, g_c, r_c = orc.query(p)
+        s_g, t_g, g_g, r_g = ctx.query(sc.T, co, p)
+        out = r_c == 0
+        assert np.array_equal(r_g, r_c), (shape, pp)
+        assert np.array_equal(s_g[out], s_c[out]) and np.array_equal(t_g[out], t_c[out]) and np.array_equal(g_g[out], g_c[out]), (shape, pp)
+        ctx.close()
+    monkeypatch.delenv("SVSDF_FORCE_GRID_OUTER", raising=False)
+    monkeypatch.delenv("SVSDF_FORCE_BATCHED", raising=False)
+
+
 def test_query_matches_committed_golden():
     for name in ("config1_star_2k.npz", "config_inside_400.npz"):
         G = np.load(os.path.join(HERE, "golden", name))

@@ -20,8 +20,11 @@ GOLD = os.path.join(HERE, "golden")
 
 
 def bits_differ(a, b):
-    a = np.ascontiguousarray(a, dtype=np.float64).ravel()
-    b = np.ascontiguousarray(b, dtype=np.float64).ravel()
+    """Number of elements whose bit patterns differ; -0.0 and +0.0 count as equal (the kernels skip the body-frame
+    pre-transform when it is the identity, the reference multiplies by it: x * 1 + y * 0 + z * 0 turns a -0.0 input into
+    +0.0 — the only observable difference, and only for inputs that are exactly -0.0)."""
+    a = np.ascontiguousarray(a, dtype=np.float64).ravel() + 0.0
+    b = np.ascontiguousarray(b, dtype=np.float64).ravel() + 0.0
     assert a.shape == b.shape
     return int((a.view(np.int64) != b.view(np.int64)).sum())
 

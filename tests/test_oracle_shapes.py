@@ -166,3 +166,29 @@ def test_polygon_fallback(oracle_mod):
     tri = [0, 0, 4, 0, 0, 3]
     s = oracle_mod.shape_sdf("custom", _rel([[1, 1], [5, 0], [-1, -1]]), polygon=tri)
     assert s[0] < 0 and abs(s[1] - 1.0) < 1e-12 and abs(s[2] - math.sqrt(2)) < 1e-12
+
+
+def test_circumradius_bound(oracle_mod):
+    """The kernels skip lattice samples of choiceTInit's first layer whose pose is farther from the query point than
+    (current minimum + R): that is exact iff sdf(q) >= |q| - R for every q.  Check the library's R (svsdf_shape_bound_radius,
+    host code) against the oracle's functors: far field, near field, with and without a body-frame pre-transform, and the
+    Polygon fallback with a custom outline.  Also: R is not loose (a point of the shape lies within 0.12 of the circle)."""
+    from implicit_svsdf_planner_b200 import api
+
+    rng = np.random.default_rng(12)
+    far = np.c_[rng.uniform(-80, 80, (200_000, 2)), np.zeros(200_000)]
+    rr, th = rng.uniform(0, 14, 200_000), rng.uniform(0, 2 * np.pi, 200_000)
+    near = np.c_[rr * np.cos(th), rr * np.sin(th), np.zeros(200_000)]
+    pts = np.r_[far, near]
+    d = np.linalg.norm(pts[:, :2], axis=1)
+    cases = [(n, (0.0, 0.0, 0.0), None) for n in ANALYTIC + ["Circle", "no_such_shape"]]
+    cases += [("star", (0.6, -0.3, 25.0), None), ("sdHorseshoe", (-1.0, 2.0, -70.0), None),
+              ("custom", (0.0, 0.0, 0.0), [3.0, -1.0, 3.0, 1.0, 0.0, 2.5, -3.0, 1.0, -3.0, -1.0])]
+    for name, pp, poly in cases:
+        R = api.shape_bound_radius(name, pp, poly)
+        f = oracle_mod.shape_sdf(name, pts, poly_params=pp, polygon=poly)
+        slack = f - (d - R)
+        assert slack.min() >= 0.03, (name, pp, R, slack.min())
+        ring = np.c_[(R - 0.12) * np.cos(np.linspace(0, 2 * np.pi, 20001)), (R - 0.12) * np.sin(np.linspace(0, 2 * np.pi, 20001)), np.zeros(20001)]
+        if pp == (0.0, 0.0, 0.0):
+            assert oracle_mod.shape_sdf(name, ring, poly_params=pp, polygon=poly).min() <= 0.0, (name, R)
