@@ -771,6 +771,113 @@ __device__ __forceinline__ void descent_engine(const TrajView &tv, const ShapePa
     __syncwarp();
 }
 
+// descent_engine with TWO samples per lane: a group of 4 lanes per point (8 points in flight per warp), each lane evaluates
+// samples s = q and s = q + 4 of its group's round (same rounds as above: R1 = 2 slope samples + candidates j = 0..5,
+// RN = candidates jbase..jbase + 7).  The two evaluations are independent instruction streams (latency hiding inside the
+// thread, on top of the resident warps) and the per-round bookkeeping is paid once per two evaluations.
+// wk: per-warp shared work area, 4 doubles per point in (px, py, seed, min), 2 doubles per point out (sdf, t*) at wk[4 i].
+// The queue of prepared points is shared by the CTA's 8 warps (wk: 8 x 32 entries of 4 doubles, entry (w, i) at
+// wk[4 (32 w + i)], valid for i < nbw[w]; served in the order i-major, w-minor through the shared cursor): a group that
+// finishes its point takes the next one of the whole CTA, so the warps of a CTA finish together whatever the lengths of
+// their own descents.  Which group solves a point does not change its result; the reductions stay per warp, fixed order.
+template <int SHAPE, bool XFORM>
+__device__ __forceinline__ void descent_engine2(const TrajView &tv, const ShapeParams &S, double *wk, const int *nbw, int *cursor,
+                                                int limit, unsigned &evals) {
+    enum { E_F0 = 0, E_R1 = 1, E_RN = 2 };
+    const int lane = threadIdx.x & 31, q = lane & 3, gbase = lane & 28;
+    const double D = tv.D;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    const int hi001 = __double2hiint(0.01), lo001 = __double2loint(0.01);
+    int pt = -1, mode = E_R1, iter = 0, pred = 1, sgn = 1, jbase = 0, hintA = 0, hintB = 0;
+    double px = 0.0, py = 0.0, x = 0.0, fx = 0.0, prev_x = 0.0, t_min = 0.0, t_max = 0.0;
+    bool need = true;
+#pragma unroll 1
+    for (;;) {
+        const unsigned want = __ballot_sync(FULL, need && q == 0);
+        if (want) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(cursor, __popc(want));
+            base = __shfl_sync(FULL, base, 0);
+            const int c = base + __popc(want & ((1u << gbase) - 1u));
+            if (need) {
+                pt = -1;
+                const int cw = c & (kWarpsPerBlock - 1), ci = c >> 3;     // entry (warp cw, point ci)
+                need = c < limit;                                          // a hole (ci >= nbw[cw]): ask again
+                if (c < limit && ci < nbw[cw]) {
+                    need = false;
+                    pt = 32 * cw + ci;
+                    const double *w = wk + 4 * pt;
+                    px = w[0]; py = w[1];
+                    const double nsd = w[2], nmn = w[3];
+                    x = nsd; fx = nmn; prev_x = nsd;
+                    t_min = smaxd(0.0, nsd - 3.4);
+                    t_max = smind(nsd + 3.4, D);
+                    iter = 0; pred = 1; sgn = 1; jbase = 0; hintA = 0; hintB = 0;
+                    mode = (nmn >= 1e9) ? E_F0 : E_R1;
+                }
+            }
+        }
+        if (!__any_sync(FULL, pt >= 0)) {
+            if (__any_sync(FULL, need)) continue;   // drew only holes: ask again (the queue is not exhausted yet)
+            break;
+        }
+
+        const bool isR1 = mode == E_R1, isF0 = mode == E_F0;
+        const int dir = isR1 ? pred : sgn;
+        const int sbit = (dir > 0) ? (int)0x80000000 : 0;
+        // slot A: sample s = q (R1: s = 0, 1 are the slope samples, s = 2, 3 candidates j = 0, 1); slot B: s = q + 4
+        const bool slopeA = isR1 && q < 2;
+        const int jA = isR1 ? q - 2 : jbase + q;
+        const int jB = isR1 ? q + 2 : jbase + q + 4;
+        const bool candA = !isF0 && !slopeA && jA <= 28, candB = !isF0 && jB <= 28;
+        evals += (pt >= 0) ? ((candA || slopeA || (isF0 && q == 0)) ? 1u : 0u) + (candB ? 1u : 0u) : 0u;
+        const double offA = slopeA ? ((q == 0) ? -0.000001 : 0.000001) : __hiloint2double((hi001 - ((jA & 31) << 20)) ^ sbit, lo001);
+        const double offB = __hiloint2double((hi001 - ((jB & 31) << 20)) ^ sbit, lo001);
+        const double loA = slopeA ? ((q == 0) ? 0.0 : -INF) : t_min, hiA = slopeA ? ((q == 0) ? INF : D) : t_max;
+        const double tcA = smaxd(smind(x + offA, hiA), loA), tcB = smaxd(smind(x + offB, t_max), t_min);
+        const double tA = (candA || slopeA) ? tcA : x, tB = candB ? tcB : x;
+        const double fA = eval_sdf<SHAPE, XFORM>(tv, S, px, py, tA, hintA);
+        const double fB = eval_sdf<SHAPE, XFORM>(tv, S, px, py, tB, hintB);
+
+        const unsigned balA = __ballot_sync(FULL, (fA - fx) < 0), balB = __ballot_sync(FULL, (fB - fx) < 0);
+        const unsigned m8 = ((balA >> gbase) & 0xfu) | (((balB >> gbase) & 0xfu) << 4);
+        const double f0 = __shfl_sync(FULL, fA, gbase), f1 = __shfl_sync(FULL, fA, gbase + 1);
+        const double g = (f1 - f0) * 500000;
+        const int s_new = (int)(g > 0) - (int)(g < 0);
+        sgn = isR1 ? s_new : sgn;
+        const bool zero = isR1 && sgn == 0;
+        const bool mispred = isR1 && sgn != 0 && sgn != pred;
+        const int nvalid = max(0, min(8, 29 - jbase));
+        const unsigned mc = isR1 ? (m8 >> 2) : (m8 & ((1u << nvalid) - 1u));
+        const bool hit = (pt >= 0) && !isF0 && !zero && !mispred && mc != 0u;
+        const int k = __ffs(mc) - 1;
+        const int jacc = isR1 ? k : jbase + k;
+        const int sidx = isR1 ? k + 2 : k;                       // accepted sample index within the round
+        const int src = hit ? gbase + (sidx & 3) : lane;
+        const bool fromB = (sidx & 4) != 0;
+        const double tsel = fromB ? tB : tA, fsel = fromB ? fB : fA;
+        const double xacc = __shfl_sync(FULL, tsel, src), facc = __shfl_sync(FULL, fsel, src);
+        const int jb_next = isR1 ? (mispred ? 0 : 6) : jbase + 8;
+        const bool failed = (pt >= 0) && !isF0 && (zero || (!hit && !mispred && jb_next > 28));
+        const bool walking = (jacc == 0) && (xacc == x + (-0.01 * (double)sgn));
+        pred = hit ? (walking ? sgn : -sgn) : pred;
+        iter += hit ? jacc + 1 : (failed ? 29 : 0);
+        x = hit ? xacc : x;
+        fx = hit ? facc : (isF0 ? f0 : fx);
+        const bool step_end = hit || failed;
+        const bool running = (iter < 1000) && !failed && (fabs(x - prev_x) > 1e-16);
+        prev_x = step_end ? x : prev_x;
+        mode = (step_end || isF0) ? E_R1 : E_RN;
+        jbase = jb_next;
+        if (step_end && !running) {
+            if (q == 0) { wk[4 * pt] = fx; wk[4 * pt + 1] = x; }
+            pt = -1;
+            need = true;
+        }
+    }
+    __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------------
 // TMA bulk copy of the trajectory blob into shared memory (cp.async.bulk + mbarrier)
 // ------------------------------------------------------------------------------------------------
@@ -827,6 +934,9 @@ __global__ void k_pose_table(double *blob) {
 // K1: outer solve for every point (+ penalty, chain rule and CTA reduction for outside points)
 // dynamic smem: [ blob | 8 warps x (19N + 1) accumulators ]
 // ------------------------------------------------------------------------------------------------
+#ifndef SVSDF_ENGINE_ILP
+#define SVSDF_ENGINE_ILP 2   // samples per lane and round in the batched descent (1: descent_engine, 2: descent_engine2)
+#endif
 #ifndef SVSDF_OUTER_MIN_CTAS
 #define SVSDF_OUTER_MIN_CTAS 3
 #endif
@@ -839,6 +949,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (SHAPE == SH_MESH) ? 2 : 
     k_outer(const __grid_constant__ KernelArgs A, const __grid_constant__ ShapeParams S) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t bar;
+    __shared__ int s_nb[kWarpsPerBlock];
+    __shared__ int s_cursor;
     double *sblob = smem;
     tma_load_blob(sblob, A.blob, A.blob_doubles, &bar);
     const TrajView tv = make_view(sblob);
@@ -852,7 +964,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (SHAPE == SH_MESH) ? 2 : 
     const int64_t wstride = (int64_t)gridDim.x * kWarpsPerBlock;
     const int64_t first = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
     unsigned long long my_evals = 0;
-    double *res = smem + A.blob_doubles + kWarpsPerBlock * nacc + warp * 64;  // descent_engine results: [32] x (sdf, t*)
+    double *res = smem + A.blob_doubles + kWarpsPerBlock * nacc + warp * 128;  // per-warp work area of the descent engine
     // The warp walks its points in batches of up to 32 (lane i <-> i-th point of the batch).
     //  * Batched schedule (large P): the points are cut into nB = W * ceil(P / 32 W) CONTIGUOUS batches of equal size
     //    (+-1; neighbouring map cells: the lanes of a warp then prune the same layer-1 samples and run descents of similar
@@ -873,16 +985,26 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, (SHAPE == SH_MESH) ? 2 : 
         const bool my_valid = lane < nb;
         const int64_t ld_pt = my_valid ? my_pt : bfirst;
         const double mpx = __ldg(A.points_xy + 2 * ld_pt), mpy = __ldg(A.points_xy + 2 * ld_pt + 1);
-        const bool batched = chunked && nb >= 8;
+        const bool batched = chunked;   // CTA-uniform: the batched schedule synchronises the CTA around its shared queue
         double m_seed = 0.0, m_min = 1e9, m_sdf = 0.0, m_ts = 0.0, m_gx = 0.0, m_gy = 0.0;
         if (BATCHED && batched) {
             int ev = 0;
             if (my_valid) thread_choice_t_init<SHAPE, XFORM>(tv, S, mpx, mpy, m_seed, m_min, ev);
             __syncwarp();
             unsigned ev2 = 0;
+#if SVSDF_ENGINE_ILP == 2
+            if (my_valid) { res[4 * lane] = mpx; res[4 * lane + 1] = mpy; res[4 * lane + 2] = m_seed; res[4 * lane + 3] = m_min; }
+            if (lane == 0) s_nb[warp] = nb;
+            if (threadIdx.x == 0) s_cursor = 0;
+            __syncthreads();   // every warp has the same number of batches (nB is a multiple of the warp count)
+            descent_engine2<SHAPE, XFORM>(tv, S, res - 128 * warp, s_nb, &s_cursor, kWarpsPerBlock * 32, ev2);
+            __syncthreads();
+            if (my_valid) { m_sdf = res[4 * lane]; m_ts = res[4 * lane + 1]; }
+#else
             descent_engine<SHAPE, XFORM>(tv, S, nb, mpx, mpy, m_seed, m_min, res, ev2);
-            my_evals += (unsigned long long)__reduce_add_sync(FULL, (unsigned)ev + ev2);
             if (my_valid) { m_sdf = res[2 * lane]; m_ts = res[2 * lane + 1]; }
+#endif
+            my_evals += (unsigned long long)__reduce_add_sync(FULL, (unsigned)ev + ev2);
             __syncwarp();
         } else {
 #pragma unroll 1
