@@ -17,9 +17,14 @@ Reported on ONE JSON line by rank 0:
                    host->device copy of the points and of the trajectory, device->host copy of cost/gradients inside
                    the timed region)
   lbfgs            full L-BFGS optimisation from x0 through svsdf_optimize (iterations/s, evaluations/s)
-  roofline         FP64 (non-tensor) roofline of the dominant kernel k_outer: achieved = E_executed * F * P / t
-  cpu_baseline     the CPU oracle (restatement of the reference OpenMP path) timed on this box's host cores
-`--impl reference` times that CPU path alone with the same metric/config keys.
+  roofline         FP64 (non-tensor) roofline of the dominant kernel k_outer: achieved = flop_per_launch / t, with
+                   flop_per_launch (DADD + DMUL + 2 DFMA thread instructions) from the committed ncu capture of the same
+                   workload (profiles/r2_k_outer_roofline.json, scripts/roofline_from_ncu.py) and t measured here with
+                   CUDA events; the capture's FP64-pipe-active and issue-active percentages are reported next to it
+  cpu_baseline     the reference's CPU path timed on this box's host cores: the reference's OWN code compiled where it
+                   lies (oracle/_ref/libref_path_glibc.so, kind "reference") when that library travelled with the
+                   snapshot, else the line-for-line restatement under oracle/ (kind "port")
+`--impl reference` times that CPU path alone on the same workload with the same metric / config keys.
 """
 from __future__ import annotations
 
@@ -40,7 +45,7 @@ sys.path.insert(0, ROOT)
 P_POINTS = 200_000
 N_PIECES = 8
 SHAPE = "star"
-F_FLOP_PER_EVAL = 173.0  # FP64 flops (FMA = 2) of one SDF-at-time evaluation for `star`
+ROOFLINE_JSON = os.path.join(ROOT, "profiles", "r2_k_outer_roofline.json")  # ncu-derived, scripts/roofline_from_ncu.py
 METRIC = "svsdf_query_pts_per_sec"
 UNIT = "pts/s"
 
@@ -108,29 +113,15 @@ def build_problem(rank: int):
     return scenes.make_scene(SHAPE, N_PIECES, P_POINTS, seed_traj=scenes.SEED_TRAJ + 17 * rank, seed_map=scenes.SEED_MAP + 17 * rank)
 
 
-def cpu_baseline(sc, sample_points: int, threads: int | None = None, reps: int = 2):
-    """Times the CPU oracle (OpenMP, schedule(dynamic), threads = round(1.5 * nproc) per the reference README tip)
-    on a strided subset of the same workload."""
-    from oracle import oracle_py as O
-
-    nproc = O.num_procs()
-    stride = max(1, sc.P // sample_points)
-    pts = sc.points[::stride]
-    orc = O.Oracle(sc.shape, weight_p=sc.weight_p, safety_hor=sc.safety_hor, rho=sc.rho, threads=1, variant="glibc")
-    orc.set_points(pts)
-    # the reference README recommends threads = 1.5 x logical cores; on many-core hosts (or cgroup-limited
-    # containers) that oversubscribes, so a few counts are tried and the best one is reported
-    tried = {}
-    for th in ([threads] if threads else thread_candidates(nproc)):
-        orc.set_threads(th)
-        sec, _ = orc.time_cost_grad(sc.T, sc.coeffs_colmajor(), warm=1, reps=reps)
-        tried[th] = sec
-    best = min(tried, key=tried.get)
-    return {"value": pts.shape[0] / tried[best], "unit": UNIT, "cores": nproc, "threads": best, "kind": "port", "libm": "glibc sin/cos (the reference's own)",
-            "sample": f"every {stride}th point of the {sc.P}-point config-2 workload ({pts.shape[0]} points), best of {reps} "
-                      f"after 1 warm-up, OpenMP schedule(dynamic); thread counts tried (s/eval): "
-                      + ", ".join(f"{k}: {v:.4f}" for k, v in tried.items()),
-            "seconds_per_eval_of_sample": tried[best]}
+def workload_config(world: int) -> dict:
+    """The `config` object of the JSON line: identical for both arms (the driver compares them)."""
+    return {
+        "workload": "config2: star, 8-piece MINCO, 200k query points, one cost+gradient evaluation per step"
+                    + ("" if world == 1 else f"; {world} independent problems of that size in flight, one per GPU, every rank cycling through all of them"),
+        "shape": SHAPE, "pieces": N_PIECES, "points_per_gpu": P_POINTS, "problems": world,
+        "l2": "GPU arm: flushed between timed iterations (320 MB memset, untimed), inputs are 3.2 MB; CPU arm: n/a",
+        "parallelism": "one problem per GPU, no data-path collective" if world > 1 else "single GPU",
+    }
 
 
 def thread_candidates(nproc: int):
@@ -138,45 +129,110 @@ def thread_candidates(nproc: int):
     return sorted(c, reverse=True)
 
 
+class CpuPath:
+    """The reference's CPU implementation of the path: its own code compiled where it lies (oracle/_ref, "reference") when
+    present, else the restatement under oracle/ ("port").  Both run the OpenMP loop with schedule(dynamic)."""
+
+    def __init__(self, sc):
+        from oracle import oracle_py as O
+        from oracle import ref_py as R
+
+        self.nproc = O.num_procs()
+        self.sc = sc
+        self.co = sc.coeffs_colmajor()
+        if R.available("glibc"):
+            self.kind = "reference"
+            self.what = ("the reference's own source (Shape.hpp classes, trajectory.hpp, minco.hpp, the SweptVolumeManager queries and the "
+                         "addSaftyPenaOnSweptVolumeParallelTrueSDF OpenMP loop, cut verbatim / included whole) compiled -O3 against the Eigen "
+                         "stand-in of oracle/ref_shim into oracle/_ref/libref_path_glibc.so")
+            self.h = R.RefPath(sc.shape, weight_p=sc.weight_p, safety_hor=sc.safety_hor, rho=sc.rho, threads=1, variant="glibc")
+        else:
+            self.kind = "port"
+            self.what = "line-for-line CPU restatement under oracle/ (glibc sin/cos, -O3 -fopenmp), oracle/_ref not present"
+            self.h = O.Oracle(sc.shape, weight_p=sc.weight_p, safety_hor=sc.safety_hor, rho=sc.rho, threads=1, variant="glibc")
+        self.h.set_points(sc.points)
+
+    def eval_once(self):
+        return self.h.cost_grad(self.sc.T, self.co)
+
+    def pick_threads(self, reps: int = 3):
+        """README tip: threads = 1.5 x logical cores; that oversubscribes many-core hosts, so a few counts are tried
+        (best of `reps` each) and the fastest is used."""
+        tried = {}
+        for th in thread_candidates(self.nproc):
+            self.h.set_threads(th)
+            self.eval_once()
+            best = float("inf")
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                self.eval_once()
+                best = min(best, time.perf_counter() - t0)
+            tried[th] = best
+        th = min(tried, key=tried.get)
+        self.h.set_threads(th)
+        return th, tried
+
+    def lbfgs(self, max_iterations: int):
+        """The product's host L-BFGS (same solver, same parameters as the GPU arm) minimising the CPU path's own cost callback
+        (costFunctionLmbmParallel of the reference when kind == "reference")."""
+        from implicit_svsdf_planner_b200 import api
+
+        sc = self.sc
+        self.h.set_conditions(sc.init_s, sc.final_s, sc.N)
+        n_eval = [0]
+
+        def fun(x):
+            n_eval[0] += 1
+            return self.h.evaluate(x)
+
+        params = api.default_lbfgs_params(mem_size=16, past=3, delta=1e-6, g_epsilon=0.0, max_iterations=max_iterations, min_step=1e-32)
+        t0 = time.perf_counter()
+        res = api.lbfgs_minimize(fun, sc.x0, params)
+        dt = time.perf_counter() - t0
+        rc, x, st = res[0], res[1], res[2]
+        return {"iters_per_sec": st["iterations"] / dt, "evals_per_sec": n_eval[0] / dt, "iterations": st["iterations"],
+                "evaluations": n_eval[0], "status": rc, "final_cost": st["final_cost"], "seconds": dt, "max_iterations": max_iterations}
+
+
+def cpu_baseline(sc, reps: int = 3):
+    """cpu_baseline leg of the GPU arm's line (rank 0, N = 1): the CPU path on the FULL config-2 workload."""
+    cp = CpuPath(sc)
+    th, tried = cp.pick_threads(reps)
+    sec = tried[th]
+    return {"value": sc.P / sec, "unit": UNIT, "cores": cp.nproc, "threads": th, "kind": cp.kind, "what": cp.what,
+            "sample": f"the whole {sc.P}-point config-2 workload, one cost+gradient evaluation, best of {reps} after 1 warm-up, OpenMP "
+                      "schedule(dynamic); thread counts tried (s/eval): " + ", ".join(f"{k}: {v:.4f}" for k, v in tried.items()),
+            "seconds_per_eval": sec}
+
+
 def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return 0
     sc = build_problem(0)
-    from oracle import oracle_py as O
-
-    nproc = O.num_procs()
-    stride = 4
-    pts = sc.points[::stride]
-    orc = O.Oracle(sc.shape, weight_p=sc.weight_p, safety_hor=sc.safety_hor, rho=sc.rho, threads=1, variant="glibc")
-    orc.set_points(pts)
-    co = sc.coeffs_colmajor()
-    tried = {}
-    for th in thread_candidates(nproc):  # pick the best thread count (see cpu_baseline)
-        orc.set_threads(th)
-        tried[th], _ = orc.time_cost_grad(sc.T, co, warm=1, reps=1)
-    threads = min(tried, key=tried.get)
-    orc.set_threads(threads)
+    cp = CpuPath(sc)
+    threads, tried = cp.pick_threads(3)
     for _ in range(args.warmup):
-        orc.cost_grad(sc.T, co)
+        cp.eval_once()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        orc.cost_grad(sc.T, co)
+        cp.eval_once()
     dt = time.perf_counter() - t0
-    value = pts.shape[0] * args.steps / dt
+    value = sc.P * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "config2: star, 8-piece MINCO, 200k query points, one cost+gradient evaluation per step",
-                   "shape": SHAPE, "pieces": N_PIECES, "points": sc.P, "l2": "n/a (CPU)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nproc, "threads": threads, "kind": "port",
-                         "sample": f"each step = every {stride}th point of the 200k-point workload ({pts.shape[0]} points); the "
-                                   "reference itself cannot be compiled here (needs Eigen/ROS/PCL), so this is the line-for-line "
-                                   "CPU restatement under oracle/ with the reference's OpenMP settings"},
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cp.nproc, "threads": threads, "kind": cp.kind, "what": cp.what,
+                         "sample": f"each step = one cost+gradient evaluation of the whole {sc.P}-point config-2 workload (rank 0 only; at N > 1 the "
+                                   "GPU arm runs N such problems concurrently, this arm runs one); thread counts tried, best of 3 (s/eval): "
+                                   + ", ".join(f"{k}: {v:.4f}" for k, v in tried.items())},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_lbfgs:
+        line["lbfgs"] = cp.lbfgs(max_iterations=4)  # bounded: a handful of iterations, ~20 evaluations of 200k points
     print(json.dumps(line), flush=True)
     return 0
 
@@ -296,22 +352,27 @@ def main():
         lane_evals = ctx.executed_evals(False)
         peak = ctx.fp64_peak_tflops()
         t_outer = statistics.mean(outer_ms) * 1e-3
-        achieved = lane_evals * F_FLOP_PER_EVAL / t_outer / 1e12
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r1_k_outer_traffic.json")
-        if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        cap = json.load(open(ROOFLINE_JSON)) if os.path.exists(ROOFLINE_JSON) else None
         peaks = {}
         ppath = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(ppath):
             peaks = json.load(open(ppath))
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         alg_bytes = sc.P * 16
+        achieved = (cap["flop_per_launch"] / t_outer / 1e12) if cap else None
         extra["roofline"] = {
-            "bound": "fp64", "kernel": "k_outer", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "bound": "fp64", "kernel": "k_outer", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "frac": (achieved / peak) if achieved else None,
             "peak_source": "DFMA micro-benchmark in this run (svsdf_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
-            "traffic": traffic,
-            "evals_per_point_executed": lane_evals / sc.P, "flop_per_eval": F_FLOP_PER_EVAL, "kernel_ms": t_outer * 1e3,
+            "flop_per_launch": cap["flop_per_launch"] if cap else None,
+            "flop_source": "profiles/r2_k_outer_roofline.json: DADD + DMUL + 2 DFMA thread instructions of one launch (ncu --set full capture of this workload); "
+                           "the strict build issues DMUL + DADD where an FMA build would issue one DFMA, so the DFMA-based peak is reachable "
+                           "only at half rate by this instruction mix - see fp64_pipe_active_pct",
+            "fp64_pipe_active_pct": cap.get("fp64_pipe_active_pct") if cap else None,
+            "issue_active_pct": cap.get("issue_active_pct") if cap else None,
+            "traffic": cap.get("dram_bytes_per_launch") if cap else None,
+            "evals_per_point_executed": lane_evals / sc.P, "kernel_ms": t_outer * 1e3,
+            "flop_per_lane_eval": (cap["flop_per_launch"] / lane_evals) if cap else None,
             "kernel_share_of_step": t_outer * 1e3 / statistics.mean(ms_steps),
             "hbm": {"achieved": alg_bytes / t_outer / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / t_outer / 1e9 / hbm_peak,
                     "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback", "algorithmic_bytes": alg_bytes},
@@ -322,11 +383,17 @@ def main():
         if not args.no_lbfgs:
             params = api.default_lbfgs_params(mem_size=16, past=3, delta=1e-6, g_epsilon=0.0, max_iterations=200, min_step=1e-32)
             rc, x, T, b, st = ctx.optimize(sc.init_s, sc.final_s, sc.x0, sc.N, params)
+            # the same small budget the CPU arm runs (`--impl reference`: max_iterations = 4) for a like-for-like evaluations/s ratio
+            p4 = api.default_lbfgs_params(mem_size=16, past=3, delta=1e-6, g_epsilon=0.0, max_iterations=4, min_step=1e-32)
+            rc4, _, _, _, st4 = ctx.optimize(sc.init_s, sc.final_s, sc.x0, sc.N, p4)
+            extra["lbfgs_same_budget_as_cpu_arm"] = {"iters_per_sec": st4["iterations"] / st4["seconds"], "evals_per_sec": st4["evaluations"] / st4["seconds"],
+                                                     "iterations": st4["iterations"], "evaluations": st4["evaluations"], "status": st4["status"],
+                                                     "final_cost": st4["final_cost"], "seconds": st4["seconds"], "max_iterations": 4}
             extra["lbfgs"] = {"iters_per_sec": st["iterations"] / st["seconds"], "evals_per_sec": st["evaluations"] / st["seconds"],
                               "iterations": st["iterations"], "evaluations": st["evaluations"], "status": st["status"],
                               "final_cost": st["final_cost"], "seconds": st["seconds"], "gpu_seconds": st["gpu_seconds"]}
         if not args.no_cpu_baseline and world == 1:  # rank 0 at N = 1 only
-            extra["cpu_baseline"] = cpu_baseline(sc, sample_points=50_000)
+            extra["cpu_baseline"] = cpu_baseline(sc)
 
     if world > 1:
         dist.barrier()
@@ -335,12 +402,8 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "config2: star, 8-piece MINCO, 200k query points, one cost+gradient evaluation per step"
-                                   + ("" if world == 1 else f"; {world} independent problems of that size in flight, one per GPU, every rank cycling through all of them"),
-                       "shape": SHAPE, "pieces": N_PIECES, "points_per_gpu": sc.P, "fp_mode": "strict (-fmad=false)" if strict else "fma-contracted (opt-in, not bit-exact)",
-                       "l2": "flushed between timed iterations (320 MB memset, untimed); inputs are 3.2 MB",
-                       "parallelism": "one problem per GPU, no data-path collective" if world > 1 else "single GPU",
-                       "map_broadcast_bytes": map_bytes},
+            "config": workload_config(world),
+            "impl_config": {"fp_mode": "strict (-fmad=false)" if strict else "fma-contracted (opt-in, not bit-exact)", "map_broadcast_bytes": map_bytes},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": float(te.item()) / args.steps},
             "gpu_launches": launches, "clocks": clocks, "wall_ms_timed_region": 1e3 * (t_wall1 - t_wall0),

@@ -253,24 +253,60 @@ __device__ __forceinline__ OuterResult solve_outer(const TrajView &tv, const Sha
     int evals = 0;
 
     // ---- choiceTInit layer 1: shared lattice t_k (accumulated 0.15 adds) with the pose table ----
-    // (skipped when the caller already ran choiceTInit thread-per-point: thread_choice_t_init)
+    // Exact pruning as in thread_choice_t_init: the result is the lexicographic minimum of (f_k, k) over the samples with
+    // f_k < 1e9, and f_k >= |p - x_k| - S.rout.  The 32 lattice poses around the one nearest to p are evaluated first (one
+    // round: this already contains the minimum almost always), then every block of 32 is revisited and only samples with
+    // |p - x_k| <= min + rout are evaluated (usually none).  (Skipped when the caller ran choiceTInit thread-per-point.)
     double min_dis = have_seed ? min_in : 1e9, seed = have_seed ? seed_in : 0.0;
-    for (int base = have_seed ? tv.K1 : 0; base < tv.K1; base += 32) {
-        int k = base + lane;
-        double f = INF;
-        if (k < tv.K1) {
-            const uint32_t ps = tv.spose + 8u * (uint32_t)k, row = 8u * (uint32_t)tv.K1pad;
-            double rx, ry;
-            rel_from_pose(px, py, lds_f64(ps), lds_f64(ps + row), lds_f64(ps + 2 * row), lds_f64(ps + 3 * row), rx, ry);
-            f = dev::shape_sdf<SHAPE, XFORM>(S, rx, ry);
-            if (!(f == f)) f = INF;
+    if (!have_seed) {
+        const uint32_t row = 8u * (uint32_t)tv.K1pad;
+        const int K1 = tv.K1;
+        // nearest lattice pose
+        double bd2 = INF;
+        int k0 = 0;
+        for (int k = lane; k < K1; k += 32) {
+            const uint32_t ps = tv.spose + 8u * (uint32_t)k;
+            const double ax = px - lds_f64(ps), ay = py - lds_f64(ps + row);
+            const double d2 = ax * ax + ay * ay;
+            if (d2 < bd2) { bd2 = d2; k0 = k; }
         }
-        evals += min(32, tv.K1 - base);
-        const int kb = base + warp_argmin_lane(f);
-        if (__any_sync(FULL, f < min_dis)) {  // f is warp-uniform; the vote lets the compiler know the branch is too
-            min_dis = f;
-            seed = lds_f64(tv.slat + 8u * (uint32_t)kb);
+        {
+            double v = bd2;
+            const int src = warp_argmin_lane(v);
+            k0 = __shfl_sync(FULL, k0, src);
         }
+        const int w0 = max(0, min(k0 - 16, K1 - 32));   // window [w0, w0 + 32) (whole lattice when K1 <= 32)
+        int kb = -1;
+        double thr2 = INF;
+        // it = -1: the window; it >= 0: block it (samples of the window are not evaluated twice)
+        for (int it = -1; 32 * it < K1; ++it) {
+            const int k = (it < 0) ? w0 + lane : 32 * it + lane;
+            bool need = k >= 0 && k < K1;
+            double rx = 0.0, ry = 0.0;
+            if (need) {
+                const uint32_t ps = tv.spose + 8u * (uint32_t)k;
+                const double xk = lds_f64(ps), yk = lds_f64(ps + row);
+                const double ax = px - xk, ay = py - yk;
+                need = (it < 0) || ((ax * ax + ay * ay <= thr2) && !(k >= w0 && k < w0 + 32));
+                if (need) rel_from_pose(px, py, xk, yk, lds_f64(ps + 2 * row), lds_f64(ps + 3 * row), rx, ry);
+            }
+            const unsigned mneed = __ballot_sync(FULL, need);
+            if (mneed == 0u) continue;
+            double f = INF;
+            if (need) {
+                f = dev::shape_sdf<SHAPE, XFORM>(S, rx, ry);
+                if (!(f == f)) f = INF;
+            }
+            evals += __popc(mneed);
+            const int kl = k - lane + warp_argmin_lane(f);   // first lane holding the block minimum; f := that minimum
+            if (__any_sync(FULL, f < min_dis || (f == min_dis && f < 1e9 && kl < kb))) {
+                min_dis = f;
+                kb = kl;
+                const double thr = f + S.rout;
+                thr2 = (thr >= 0.0) ? thr * thr : INF;
+            }
+        }
+        seed = (kb >= 0) ? lds_f64(tv.slat + 8u * (uint32_t)kb) : 0.0;
     }
 
     // ---- choiceTInit layers 2..4: 21-sample window around the seed, dt *= 0.1 per layer, one sample per lane ----

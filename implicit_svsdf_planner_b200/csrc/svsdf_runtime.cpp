@@ -5,6 +5,9 @@
 // of svsdf_kernels.cuh.  There is deliberately no CPU implementation of the hot path in this library: if CUDA is
 // unavailable svsdf_create fails.
 #include <cuda_runtime.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include <chrono>
 #include <algorithm>
@@ -914,16 +917,45 @@ int svsdf_set_points(svsdf_ctx *ctx, const double *pts, int64_t P, int stride) {
     int rc = ensure_stage(ctx, (size_t)P * 2 * sizeof(double));
     if (rc) return rc;
     double *h = ctx->h_stage;
-    // pos_eva(2) = 0 (back_end_optimizer.hpp:791): only x, y are kept.  Packed into the pinned stage chunk by chunk, each
-    // chunk's copy overlapping the packing of the next one.
-    const int64_t chunk = 32768;
-    for (int64_t b = 0; b < P; b += chunk) {
-        const int64_t e = std::min(P, b + chunk);
-        for (int64_t i = b; i < e; ++i) {
-            h[2 * i] = pts[i * stride];
-            h[2 * i + 1] = pts[i * stride + 1];
+    // pos_eva(2) = 0 (back_end_optimizer.hpp:791): only x, y are kept.  Packed into the pinned stage chunk by chunk by a few
+    // host threads; every chunk is handed to the copy engine as soon as it is packed (packing of the next chunks overlaps the
+    // DMA of the finished ones).  One thread for small inputs.
+    const int64_t chunk = 16384;
+    const int64_t nchunks = (P + chunk - 1) / chunk;
+    int nth = (int)std::min<int64_t>(nchunks, 4);
+#ifdef _OPENMP
+    nth = std::max(1, std::min(nth, omp_get_max_threads()));
+#else
+    nth = 1;
+#endif
+    int first_err = (int)cudaSuccess;
+    const int dev = ctx->device;
+    double *d_points = ctx->d_points;
+    cudaStream_t stream = ctx->stream;
+#pragma omp parallel num_threads(nth) if (nth > 1)
+    {
+        if (nth > 1) cudaSetDevice(dev);  // the worker threads' current device
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t c = 0; c < nchunks; ++c) {
+            const int64_t b = c * chunk, e = std::min(P, b + chunk);
+            if (stride == 2) {
+                std::memcpy(h + 2 * b, pts + 2 * b, (size_t)(e - b) * 2 * sizeof(double));
+            } else {
+                for (int64_t i = b; i < e; ++i) {
+                    h[2 * i] = pts[i * stride];
+                    h[2 * i + 1] = pts[i * stride + 1];
+                }
+            }
+            cudaError_t ce = cudaMemcpyAsync(d_points + 2 * b, h + 2 * b, (size_t)(e - b) * 2 * sizeof(double), cudaMemcpyHostToDevice, stream);
+            if (ce != cudaSuccess) {
+#pragma omp atomic write
+                first_err = (int)ce;
+            }
         }
-        CK(cudaMemcpyAsync(ctx->d_points + 2 * b, h + 2 * b, (size_t)(e - b) * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (first_err != (int)cudaSuccess) {
+        ctx->err = std::string("svsdf_set_points: cudaMemcpyAsync: ") + cudaGetErrorString((cudaError_t)first_err);
+        return SVSDF_ERR_CUDA;
     }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->P = P;

@@ -506,35 +506,55 @@ def test_errors_are_reported_not_thrown(scene2k):
 # ----------------------------------------------------------------------------------------------------------------
 # Full-size (BASELINE config 2: 200k points) size-independent properties
 # ----------------------------------------------------------------------------------------------------------------
-def test_full_size_properties_200k(oracle_mod):
-    sc = scenes.make_scene("star", 8, 200_000)
+def _full_size_check(oracle_mod, shape, N, P, mesh=None, spot=1500, cost_evals=True):
+    """Size-independent properties at a BASELINE config's full size + a spot check of the FULL-SIZE run's per-point outputs
+    (batched schedule) against the oracle."""
+    sc = scenes.make_scene(shape if shape in scenes.START_GOAL else "star", N, P)
     co = sc.coeffs_colmajor()
-    ctx = api.Context("star")
+    ctx = api.Context(shape, mesh=mesh)
     ctx.set_points(sc.points)
     c, gT, gC = ctx.cost_grad(sc.T, co)
     assert np.isfinite(c) and c > 0
-    # additivity over a partition of the query set
-    half = sc.P // 2
-    ctx.set_points(sc.points[:half])
-    ca, gTa, gCa = ctx.cost_grad(sc.T, co)
-    ctx.set_points(sc.points[half:])
-    cb, gTb, gCb = ctx.cost_grad(sc.T, co)
-    assert abs((ca + cb) - c) <= 1e-11 * c and nrel(gCa + gCb, gC) <= 1e-11 and gT_err(gTa + gTb, gT, gC) <= 1e-11
-    # permutation invariance
-    perm = np.random.default_rng(3).permutation(sc.P)
-    ctx.set_points(sc.points[perm])
-    cp, gTp, gCp = ctx.cost_grad(sc.T, co)
-    assert abs(cp - c) <= 1e-11 * c and nrel(gCp, gC) <= 1e-11
-    # spot check of a random subset against the oracle (per-point sdf) and its share of the cost
-    idx = np.sort(np.random.default_rng(5).choice(sc.P, size=1500, replace=False))
+    if cost_evals:
+        # additivity over a partition of the query set
+        half = sc.P // 2
+        ctx.set_points(sc.points[:half])
+        ca, gTa, gCa = ctx.cost_grad(sc.T, co)
+        ctx.set_points(sc.points[half:])
+        cb, gTb, gCb = ctx.cost_grad(sc.T, co)
+        assert abs((ca + cb) - c) <= 1e-11 * c and nrel(gCa + gCb, gC) <= 1e-11 and gT_err(gTa + gTb, gT, gC) <= 1e-11
+        # permutation invariance
+        perm = np.random.default_rng(3).permutation(sc.P)
+        ctx.set_points(sc.points[perm])
+        cp, gTp, gCp = ctx.cost_grad(sc.T, co)
+        assert abs(cp - c) <= 1e-11 * c and nrel(gCp, gC) <= 1e-11
+    # per-point outputs of the full-size run (this is the batched schedule) on a random subset vs the oracle: bitwise outside
+    # the swept volume, round counts equal, interior values to 1e-9
+    p_all = np.c_[sc.points[:, :2], np.zeros(sc.P)]
+    s_g, t_g, g_g, r_g = ctx.query(sc.T, co, p_all)
+    idx = np.sort(np.random.default_rng(5).choice(sc.P, size=spot, replace=False))
+    orc = oracle_mod.Oracle(shape, threads=oracle_mod.num_procs(), mesh=mesh)
+    orc.set_traj(sc.T, co)
+    s_c, t_c, g_c, r_c = orc.query(p_all[idx])
+    out = r_c == 0
+    assert np.array_equal(r_g[idx], r_c)
+    assert np.array_equal(s_g[idx][out], s_c[out]) and np.array_equal(t_g[idx][out], t_c[out]) and np.array_equal(g_g[idx][out], g_c[out])
+    assert np.abs(s_g[idx] - s_c).max() <= 1e-9
+    # and the subset's share of the cost through the reduction
     sub = sc.points[idx]
-    orc = oracle_mod.Oracle("star", threads=oracle_mod.num_procs())
     orc.set_points(sub)
     c0, gT0, gC0, _, _ = orc.cost_grad(sc.T, co)
     ctx.set_points(sub)
     c1, gT1, gC1 = ctx.cost_grad(sc.T, co)
-    assert abs(c1 - c0) <= 1e-12 * abs(c0) and nrel(gC1, gC0) <= 1e-8
-    s_g, t_g, g_g, r_g = ctx.query(sc.T, co, np.c_[sub[:, :2], np.zeros(len(sub))])
-    orc.set_traj(sc.T, co)
-    s_c, t_c, g_c, r_c = orc.query(np.c_[sub[:, :2], np.zeros(len(sub))])
-    assert np.array_equal(r_g, r_c) and np.array_equal(s_g[r_c == 0], s_c[r_c == 0]) and np.abs(s_g - s_c).max() <= 1e-9
+    assert abs(c1 - c0) <= 1e-12 * max(abs(c0), 1.0) and nrel(gC1, gC0) <= 1e-8
+    ctx.close()
+
+
+def test_full_size_properties_200k(oracle_mod):
+    """BASELINE config 2: star, N = 8, 200 000 points."""
+    _full_size_check(oracle_mod, "star", 8, 200_000)
+
+
+def test_full_size_properties_config3_500k(oracle_mod):
+    """BASELINE config 3: sdHorseshoe (concave), N = 16, 500 000 points."""
+    _full_size_check(oracle_mod, "sdHorseshoe", 16, 500_000)
