@@ -62,6 +62,7 @@ class LbfgsParams(C.Structure):
         ("s_curv_coeff", C.c_double),
         ("cautious_factor", C.c_double),
         ("machine_prec", C.c_double),
+        ("nonsmooth_restarts", C.c_int),
     ]
 
 

@@ -24,12 +24,14 @@ struct LbfgsParams {
     double s_curv_coeff = 0.9;
     double cautious_factor = 1.0e-6;
     double machine_prec = 1.0e-16;
+    int nonsmooth_restarts = 0;   // see svsdf_lbfgs_params
 };
 
 enum LbfgsCode {
     LBFGS_CONVERGENCE = 0,
     LBFGS_STOP = 1,
     LBFGS_CANCELED = 2,
+    LBFGS_NOMOREPROGRESS = 3,  // line search failed along -g: no decrease to line-search precision (kink of a non-smooth cost)
     LBFGSERR_UNKNOWNERROR = -1024,
     LBFGSERR_INVALID_N,
     LBFGSERR_INVALID_MEMSIZE,
@@ -89,20 +91,38 @@ class Lbfgs {
             R.status = LBFGS_CONVERGENCE;
         } else {
             double step = 1.0 / std::sqrt(dotp(d.data(), d.data(), n));
-            int head = 0, stored = 0;
+            int head = 0, stored = 0, restarts = 0;
             k = 1;
             for (;;) {
                 std::copy(x, x + n, xp.begin());
                 gp = g;
                 const double step_min = P.min_step, step_max = P.max_step;
                 step = step < step_max ? step : 0.5 * step_max;
+                const double fx_before = fx;
                 int ls = line_search(x, n, fx, step, step_min, step_max, eval, inst, R.evaluations);
                 if (ls < 0) {
                     std::copy(xp.begin(), xp.end(), x);
                     g = gp;
+                    fx = fx_before;
+                    const bool recoverable = ls == LBFGSERR_MAXIMUMLINESEARCH || ls == LBFGSERR_MINIMUMSTEP || ls == LBFGSERR_WIDTHTOOSMALL ||
+                                             ls == LBFGSERR_INCREASEGRADIENT || ls == LBFGSERR_MAXIMUMSTEP;
+                    if (P.nonsmooth_restarts > 0 && recoverable) {
+                        if (stored > 0 && restarts < P.nonsmooth_restarts) {
+                            // the quasi-Newton model is wrong across a kink: forget it and search along -g from here
+                            ++restarts;
+                            stored = 0;
+                            head = 0;
+                            for (int i = 0; i < n; ++i) d[i] = -g[i];
+                            step = 1.0 / std::sqrt(dotp(d.data(), d.data(), n));
+                            continue;
+                        }
+                        R.status = LBFGS_NOMOREPROGRESS;
+                        break;
+                    }
                     R.status = ls;
                     break;
                 }
+                restarts = 0;
                 if (progress && progress(puser, x, k)) { R.status = LBFGS_CANCELED; break; }
                 if (amax(g.data(), n) / std::max(1.0, amax(x, n)) < P.g_epsilon) { R.status = LBFGS_CONVERGENCE; break; }
                 if (P.past > 0) {
@@ -210,6 +230,7 @@ class Lbfgs {
 
     LbfgsParams P;
     std::vector<double> xp, g, gp, d, pf, S, Y, ys_hist, alpha;
+
 };
 
 }  // namespace host

@@ -1120,6 +1120,7 @@ void svsdf_default_lbfgs_params(svsdf_lbfgs_params *p) {
     p->max_iterations = d.max_iterations; p->max_linesearch = d.max_linesearch; p->min_step = d.min_step;
     p->max_step = d.max_step; p->f_dec_coeff = d.f_dec_coeff; p->s_curv_coeff = d.s_curv_coeff;
     p->cautious_factor = d.cautious_factor; p->machine_prec = d.machine_prec;
+    p->nonsmooth_restarts = 8;  // the SVSDF cost is non-smooth: restart across kinks, end with status 3 at a kink (svsdf.h)
 }
 
 static host::LbfgsParams to_host_params(const svsdf_lbfgs_params *params) {
@@ -1132,6 +1133,7 @@ static host::LbfgsParams to_host_params(const svsdf_lbfgs_params *params) {
     hp.min_step = params->min_step; hp.max_step = params->max_step; hp.f_dec_coeff = params->f_dec_coeff;
     hp.s_curv_coeff = params->s_curv_coeff; hp.cautious_factor = params->cautious_factor;
     hp.machine_prec = params->machine_prec;
+    hp.nonsmooth_restarts = params->nonsmooth_restarts;
     return hp;
 }
 

@@ -131,6 +131,12 @@ typedef struct {
     int max_linesearch;
     double min_step, max_step;
     double f_dec_coeff, s_curv_coeff, cautious_factor, machine_prec;
+    /* Non-smooth handling (the SVSDF cost has kinks and finite-difference gradients; the reference drives it with LMBM for
+       that reason, back_end_optimizer.cpp:29-36).  When the line search fails on a quasi-Newton direction the memory is
+       dropped and the search restarts along -g, at most this many times in a row without an accepted step; when it fails on
+       -g itself the run ends with status 3 (no decrease along the steepest-descent direction to line-search precision:
+       the counterpart of LMBM_NOMOREPROGRESS, lmbm.h:182).  0 = plain lbfgs_ref.hpp behaviour (negative line-search code). */
+    int nonsmooth_restarts;
 } svsdf_lbfgs_params;
 void svsdf_default_lbfgs_params(svsdf_lbfgs_params *p);
 
@@ -138,7 +144,7 @@ typedef struct {
     double final_cost;
     int iterations;     /* accepted line-search steps */
     int evaluations;    /* cost+gradient evaluations */
-    int status;         /* lbfgs_ref.hpp return code (0 convergence, 1 stop, <0 error) */
+    int status;         /* lbfgs_ref.hpp return code (0 convergence, 1 stop, 3 no more progress at a kink, <0 error) */
     double seconds;     /* wall-clock of the whole optimisation */
     double gpu_seconds; /* sum of device time of the cost kernels (CUDA events) */
 } svsdf_opt_stats;

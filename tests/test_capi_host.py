@@ -129,3 +129,28 @@ def test_product_never_touches_the_oracle():
                 if re.search(r"(from|import)\s+oracle|oracle_py|#include\s+\"[^\"]*oracle|libsvsdf_oracle", txt):
                     offenders.append(os.path.join(dp_, f))
     assert not offenders, offenders
+
+
+def test_lbfgs_nonsmooth_restarts_and_failed_first_evaluation():
+    """(i) On a cost with kinks the plain Lewis-Overton L-BFGS ends with a negative line-search code; with
+    nonsmooth_restarts it drops the quasi-Newton memory at the kink, continues along -g and ends with a non-negative status
+    (3 = no more progress at a kink) at a point at least as good.  (ii) A first evaluation that returns NaN is an error of
+    the run (LBFGSERR_INVALID_FUNCVAL = -1012), never 'convergence' (ADVICE r1)."""
+    from implicit_svsdf_planner_b200 import api
+
+    def fun(x):  # |x0| + |x1| with a subgradient that is wrong left of the kink: no step satisfies Armijo + weak Wolfe
+        return float(np.abs(x).sum()), np.ones_like(x)
+
+    x0 = np.array([1.0, 2.0])
+    p0 = api.default_lbfgs_params(mem_size=8, past=0, delta=0.0, g_epsilon=1e-9, max_iterations=50)
+    p0.nonsmooth_restarts = 0
+    rc0, xa, st0 = api.lbfgs_minimize(fun, x0, p0)
+    p1 = api.default_lbfgs_params(mem_size=8, past=0, delta=0.0, g_epsilon=1e-9, max_iterations=50)
+    assert p1.nonsmooth_restarts == 8  # library default
+    rc1, xb, st1 = api.lbfgs_minimize(fun, x0, p1)
+    assert rc0 in (-1009, -1011, -1007) and rc1 == 3, (rc0, rc1)
+    assert st1["final_cost"] <= st0["final_cost"] + 1e-12
+    assert abs(fun(xb)[0] - st1["final_cost"]) < 1e-12  # the reported cost is the cost of the returned iterate
+
+    rcn, _, _ = api.lbfgs_minimize(lambda x: (float("nan"), np.zeros_like(x)), x0, p1)
+    assert rcn == -1012
