@@ -85,7 +85,7 @@ EXPORTED_SYMBOLS = [
     "svsdf_default_config", "svsdf_create", "svsdf_destroy", "svsdf_last_error", "svsdf_shape_id", "svsdf_shape_bound_radius",
     "svsdf_set_points", "svsdf_set_points_device", "svsdf_set_traj", "svsdf_query", "svsdf_cost_grad",
     "svsdf_set_boundary", "svsdf_evaluate", "svsdf_last_costs", "svsdf_get_traj", "svsdf_default_lbfgs_params",
-    "svsdf_optimize", "svsdf_minco_forward", "svsdf_minco_propagate", "svsdf_forward_T", "svsdf_backward_T",
+    "svsdf_optimize", "svsdf_optimize_batch", "svsdf_cost_grad_batch", "svsdf_minco_forward", "svsdf_minco_propagate", "svsdf_forward_T", "svsdf_backward_T",
     "svsdf_shape_sdf", "svsdf_shape_grad1", "svsdf_cost_grad_device", "svsdf_kernel_launches",
     "svsdf_executed_evals", "svsdf_fp64_peak", "svsdf_device_ptr_points", "svsdf_lbfgs_minimize", "svsdf_last_kernel_ms", "svsdf_sincos", "svsdf_set_map", "svsdf_set_map_device",
     "svsdf_extract_points", "svsdf_get_points", "svsdf_read_obj", "svsdf_free",
@@ -230,6 +230,79 @@ def backward_T(T):
     tau = np.empty_like(T)
     lib().svsdf_backward_T(T.shape[0], _p(T), _p(tau))
     return tau
+
+
+class Problem(C.Structure):
+    """svsdf_problem (include/svsdf.h)."""
+    _fields_ = [
+        ("initS", dp), ("finalS", dp), ("opt_x", dp), ("points", dp), ("P", C.c_int64), ("stride", C.c_int),
+        ("waypoints_xy", dp), ("W", C.c_int), ("half", C.c_double), ("keepout_xy", dp), ("n_keepout", C.c_int),
+        ("clearance", C.c_double), ("T_out", dp), ("coeffs_out", dp),
+    ]
+
+
+NEXT_T = C.CFUNCTYPE(C.c_int, C.c_void_p)
+
+
+def optimize_batch(ctxs, problems, N, params=None, next_index=None):
+    """svsdf_optimize_batch over a pool of Contexts.  problems: list of dicts with init_s, final_s (3x3), x0 and either
+    points (P x stride) or waypoints (W x 2) + half [+ keepout (K x 2), clearance].  next_index: optional callable returning
+    the next problem index (< 0 or >= len(problems) stops a worker) — e.g. a counter shared by all ranks.
+    Returns (rc, x [n, nvar], stats list of dicts, status [n], points [n])."""
+    n = len(problems)
+    nvar = N + 3 * (N - 1)
+    arr = (Problem * max(n, 1))()
+    keep = []
+    X = np.zeros((n, nvar))
+    for k, pr in enumerate(problems):
+        i_s, f_s = _colmajor33(pr["init_s"]), _colmajor33(pr["final_s"])
+        X[k] = _f64(pr["x0"])
+        a = arr[k]
+        a.initS, a.finalS, a.opt_x = _p(i_s), _p(f_s), X[k].ctypes.data_as(dp)
+        keep += [i_s, f_s]
+        if pr.get("points") is not None:
+            pts = _f64(pr["points"])
+            a.points, a.P, a.stride = _p(pts), pts.shape[0], pts.shape[1]
+            keep.append(pts)
+        else:
+            w = _f64(pr["waypoints"]).reshape(-1, 2)
+            a.points, a.waypoints_xy, a.W, a.half = None, _p(w), w.shape[0], float(pr["half"])
+            keep.append(w)
+            ko = pr.get("keepout")
+            if ko is not None:
+                ko = _f64(ko).reshape(-1, 2)
+                a.keepout_xy, a.n_keepout, a.clearance = _p(ko), ko.shape[0], float(pr.get("clearance", 0.0))
+                keep.append(ko)
+    hs = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    stats = (OptStats * max(n, 1))()
+    status = np.zeros(n, dtype=np.int32)
+    npts = np.zeros(n, dtype=np.int64)
+    cb = NEXT_T(lambda _u: int(next_index())) if next_index is not None else None
+    L = lib()
+    L.svsdf_optimize_batch.restype = C.c_int
+    rc = L.svsdf_optimize_batch(hs, len(ctxs), arr, n, int(N), C.byref(params) if params is not None else None,
+                                cb if cb is not None else C.cast(None, NEXT_T), None, stats, status.ctypes.data_as(C.POINTER(C.c_int)),
+                                npts.ctypes.data_as(C.POINTER(C.c_int64)))
+    st = [dict(final_cost=s.final_cost, iterations=s.iterations, evaluations=s.evaluations, status=s.status, seconds=s.seconds,
+               gpu_seconds=s.gpu_seconds) for s in stats[:n]]
+    return rc, X, st, status, npts
+
+
+def cost_grad_batch(ctxs, point_sets, T, coeffs_colmajor, N):
+    """svsdf_cost_grad_batch: one cost+gradient evaluation per problem with host buffers.  point_sets: list of (P_k x stride)
+    arrays (same stride); T: [n, N]; coeffs_colmajor: [n, 18 N].  Returns (rc, cost [n], gradT [n, N], gradC [n, 18 N])."""
+    n = len(point_sets)
+    pts = [_f64(p) for p in point_sets]
+    stride = pts[0].shape[1]
+    ptrs = (dp * n)(*[_p(p) for p in pts])
+    P = np.array([p.shape[0] for p in pts], dtype=np.int64)
+    T = _f64(T).reshape(n, N)
+    co = _f64(coeffs_colmajor).reshape(n, 18 * N)
+    cost, gT, gC = np.zeros(n), np.zeros((n, N)), np.zeros((n, 18 * N))
+    hs = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    rc = lib().svsdf_cost_grad_batch(hs, len(ctxs), n, int(N), ptrs, P.ctypes.data_as(C.POINTER(C.c_int64)), stride, _p(T), _p(co),
+                                     _p(cost), _p(gT), _p(gC))
+    return rc, cost, gT, gC
 
 
 def shape_bound_radius(shape="star", poly_params=(0.0, 0.0, 0.0), polygon=None) -> float:

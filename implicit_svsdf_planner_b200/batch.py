@@ -178,39 +178,118 @@ def keepout_samples(b: np.ndarray, T: np.ndarray, n: int = 150) -> np.ndarray:
     return scenes.eval_traj_xy(b, T, np.linspace(0.0, float(T.sum()), n))[:, :2]
 
 
+def lpt_order(problems: np.ndarray) -> np.ndarray:
+    """Longest-processing-time-first order for the dynamic queue: longer start-goal distance = more query points and more
+    optimiser work, so long problems are handed out first and the short ones fill the tail."""
+    d = np.asarray(problems)[:, 2:4] - np.asarray(problems)[:, 0:2]
+    return np.argsort(-np.linalg.norm(d, axis=1), kind="stable")
+
+
+class WorkQueue:
+    """Problem indices handed out one at a time to whoever asks next — across every rank of the job (iteration
+    counts differ per problem, so a static split leaves GPUs idle).  The counter lives in the torch.distributed store
+    (an atomic add on the rank-0 store server, one TCP round trip per problem — microseconds against the ~0.1 s of a
+    problem); without a process group it is a local counter.  `order` maps the k-th ticket to a problem index (LPT)."""
+
+    def __init__(self, n: int, order=None, key: str = "svsdf_queue"):
+        import threading
+
+        self.n = int(n)
+        self.order = np.arange(self.n) if order is None else np.asarray(order)
+        self.key = key
+        self.taken = []
+        self._lock = threading.Lock()
+        self._local = 0
+        self.store = None
+        try:
+            import torch.distributed as dist
+
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                self.store = dist.distributed_c10d._get_default_store()
+        except Exception:
+            self.store = None
+
+    def next(self) -> int:
+        """Next problem index, or -1 when the queue is empty.  Thread-safe (called from the pool's worker threads)."""
+        with self._lock:
+            if self.store is not None:
+                t = int(self.store.add(self.key, 1)) - 1
+            else:
+                t = self._local
+                self._local += 1
+            if t >= self.n:
+                return -1
+            k = int(self.order[t])
+            self.taken.append(k)
+            return k
+
+
+def gather_rows(local: np.ndarray, mine, device=None) -> np.ndarray:
+    """Every rank contributes the rows it solved (`mine`: their indices); returns the full table on every rank.  Ownership
+    comes from the indices, not from the values (a solver result may legitimately contain NaN)."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return local
+    dev = device if device is not None else torch.device("cpu")
+    mask = np.zeros(local.shape[0])
+    mask[list(mine)] = 1.0
+    vals = np.where(mask[:, None] > 0, local, 0.0)
+    nan_mask = np.isnan(vals)
+    t = torch.from_numpy(np.where(nan_mask, 0.0, vals)).to(dev)
+    nn = torch.from_numpy(nan_mask.astype(np.float64)).to(dev)
+    m = torch.from_numpy(mask).to(dev)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    dist.all_reduce(nn, op=dist.ReduceOp.SUM)
+    dist.all_reduce(m, op=dist.ReduceOp.SUM)
+    cnt = m.cpu().numpy()
+    if not np.all(cnt == 1.0):
+        raise RuntimeError(f"every problem must be solved by exactly one rank (counts: min {cnt.min()}, max {cnt.max()})")
+    out = t.cpu().numpy()
+    out[nn.cpu().numpy() > 0] = np.nan
+    return out
+
+
 class BatchRunner:
     """Runs the problems of this rank and gathers the per-problem results.
 
     solve(scene, index) -> 1-D float array (fixed length) is injected: on a GPU box it wraps
     ``api.Context.optimize``; the gloo tests inject a CPU stand-in so the sharding / broadcast / gather logic is
-    exercised without CUDA."""
+    exercised without CUDA.  dynamic=False: contiguous static split (`partition`); dynamic=True: `WorkQueue` shared by all
+    ranks, LPT order."""
 
-    def __init__(self, solve: Callable[[scenes.Scene, int], np.ndarray], result_len: int):
+    def __init__(self, solve: Callable[[scenes.Scene, int], np.ndarray], result_len: int, dynamic: bool = False):
         self.solve = solve
         self.result_len = result_len
+        self.dynamic = dynamic
+        self.mine = []
 
     def run(self, gm: GridMap, problems: np.ndarray, N: int = 8, P: Optional[int] = None, device=None):
-        import torch
         import torch.distributed as dist
 
         world = dist.get_world_size() if dist.is_initialized() else 1
         rank = dist.get_rank() if dist.is_initialized() else 0
         n = problems.shape[0]
-        mine = partition(n, world, rank)
-        local = np.full((n, self.result_len), np.nan)
-        for k in mine:
+        local = np.zeros((n, self.result_len))
+
+        def one(k):
             sg = problems[k]
             sc = problem_scene(gm, sg[:2], sg[2:4], N=N, P=P, seed=scenes.SEED_BATCH + k)
             local[k] = self.solve(sc, k)
-        if world == 1:
-            return local
-        # gather: every rank contributes its rows; nan elsewhere -> nan-aware merge
-        dev = device if device is not None else torch.device("cpu")
-        t = torch.from_numpy(np.nan_to_num(local, nan=0.0)).to(dev)
-        m = torch.from_numpy((~np.isnan(local)).astype(np.float64)).to(dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        dist.all_reduce(m, op=dist.ReduceOp.SUM)
-        out = t.cpu().numpy()
-        cnt = m.cpu().numpy()
-        assert np.all(cnt == 1.0), "every problem must be solved by exactly one rank"
-        return out
+
+        if self.dynamic:
+            q = WorkQueue(n, lpt_order(problems))
+            if world > 1:
+                dist.barrier()  # nobody draws before every rank has built its queue object
+            while True:
+                k = q.next()
+                if k < 0:
+                    break
+                one(k)
+            self.mine = list(q.taken)
+        else:
+            self.mine = list(partition(n, world, rank))
+            for k in self.mine:
+                one(k)
+        return gather_rows(local, self.mine, device)

@@ -9,7 +9,9 @@
 #include <omp.h>
 #endif
 
+#include <atomic>
 #include <chrono>
+#include <thread>
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -496,6 +498,39 @@ double evaluate_impl(svsdf_ctx *ctx, const double *x, double *g, int n) {
 }
 
 }  // namespace
+
+// ---- batch variants: a pool of contexts, one worker thread each, dynamic hand-out of problem indices ------------------
+namespace {
+template <class Body>
+int run_pool(svsdf_ctx *const *ctxs, int n_ctx, int n_problems, svsdf_next_problem_t next, void *next_user, Body body) {
+    if (!ctxs || n_ctx < 1 || n_problems < 0) return SVSDF_ERR_INVALID;
+    for (int c = 0; c < n_ctx; ++c)
+        if (!ctxs[c]) return SVSDF_ERR_INVALID;
+    std::atomic<int> counter{0};
+    std::atomic<int> first_err{SVSDF_OK};
+    auto worker = [&](int c) {
+        for (;;) {
+            const int k = next ? next(next_user) : counter.fetch_add(1);
+            if (k < 0 || k >= n_problems) break;
+            const int rc = body(ctxs[c], k);
+            if (rc != SVSDF_OK) {
+                int expected = SVSDF_OK;
+                first_err.compare_exchange_strong(expected, rc);
+            }
+        }
+    };
+    if (n_ctx == 1) {
+        worker(0);
+    } else {
+        std::vector<std::thread> th;
+        th.reserve(n_ctx);
+        for (int c = 0; c < n_ctx; ++c) th.emplace_back(worker, c);
+        for (auto &t : th) t.join();
+    }
+    return first_err.load();
+}
+}  // namespace
+
 
 extern "C" {
 
@@ -1187,6 +1222,47 @@ int svsdf_optimize(svsdf_ctx *ctx, const double *initS, const double *finalS, do
     int ret = R.status;
     if (ret == 0) ret = 1;  // back_end_optimizer.cpp:66-69
     return ret;
+}
+
+int svsdf_optimize_batch(svsdf_ctx *const *ctxs, int n_ctx, const svsdf_problem *problems, int n_problems, int N,
+                         const svsdf_lbfgs_params *params, svsdf_next_problem_t next, void *next_user,
+                         svsdf_opt_stats *stats_out, int *status_out, int64_t *points_out) {
+    if (!problems && n_problems > 0) return SVSDF_ERR_INVALID;
+    return run_pool(ctxs, n_ctx, n_problems, next, next_user, [&](svsdf_ctx *ctx, int k) -> int {
+        const svsdf_problem &pr = problems[k];
+        if (!pr.initS || !pr.finalS || !pr.opt_x) return SVSDF_ERR_INVALID;
+        int rc;
+        int64_t np = 0;
+        if (pr.points) {
+            rc = svsdf_set_points(ctx, pr.points, pr.P, pr.stride);
+            np = pr.P;
+        } else {
+            rc = svsdf_extract_points(ctx, pr.waypoints_xy, pr.W, pr.half, pr.keepout_xy, pr.n_keepout, pr.clearance, &np);
+        }
+        if (rc != SVSDF_OK) {
+            if (status_out) status_out[k] = rc;
+            return rc;
+        }
+        if (points_out) points_out[k] = np;
+        svsdf_opt_stats st;
+        std::memset(&st, 0, sizeof(st));
+        const int ret = svsdf_optimize(ctx, pr.initS, pr.finalS, pr.opt_x, N, params, nullptr, nullptr, pr.T_out, pr.coeffs_out, &st);
+        if (stats_out) stats_out[k] = st;
+        if (status_out) status_out[k] = ret;
+        // solver codes (incl. negative line-search codes) are per-problem results; API / CUDA errors abort the call's status
+        return (ret <= SVSDF_ERR_INVALID && ret > -1000) ? ret : SVSDF_OK;
+    });
+}
+
+int svsdf_cost_grad_batch(svsdf_ctx *const *ctxs, int n_ctx, int n_problems, int N, const double *const *pts, const int64_t *P,
+                          int stride, const double *T, const double *coeffs, double *cost_io, double *gradT_io, double *gradC_io) {
+    if (n_problems > 0 && (!pts || !P || !T || !coeffs || !cost_io || !gradT_io || !gradC_io)) return SVSDF_ERR_INVALID;
+    return run_pool(ctxs, n_ctx, n_problems, nullptr, nullptr, [&](svsdf_ctx *ctx, int k) -> int {
+        int rc = svsdf_set_points(ctx, pts[k], P[k], stride);
+        if (rc != SVSDF_OK) return rc;
+        return svsdf_cost_grad(ctx, N, T + (size_t)k * N, coeffs + (size_t)k * 18 * N, cost_io + k, gradT_io + (size_t)k * N,
+                               gradC_io + (size_t)k * 18 * N);
+    });
 }
 
 int svsdf_minco_forward(const double *initS, const double *finalS, int N, const double *q, const double *T,

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import dataclasses
 import math
+import os
 
 import numpy as np
 
@@ -215,18 +216,33 @@ def _candidates(xs, ys, wps, half, path, clearance):
     return pts[d > clearance]
 
 
-def make_batch_problems(n_problems: int, seed: int = SEED_BATCH, extent=(2.0, 58.0)):
-    """Config 5: start/goal pairs.  The first min(n,1000) are laid out like src/coords.txt rows
-    (6 columns uniform[0,60]; cols 0-1 start xy, 3-4 goal xy) but regenerated from the seed because the
-    reference file cannot travel to the GPU box; the rest are uniform in the map."""
+COORDS_TXT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "coords.txt")
+
+
+def make_batch_problems(n_problems: int, seed: int = SEED_BATCH, extent=(2.0, 58.0), coords_path: str = COORDS_TXT):
+    """BASELINE config 5 start/goal pairs: the first min(n, 1000) come from the reference's own
+    `src/coords.txt` (1000 rows of 6 uniform[0, 60] numbers; columns 0-1 = start xy, 3-4 = goal xy; a copy travels as
+    tests/golden/coords.txt), clipped into `extent`; the rest are uniform in `extent` from mt19937_64(seed).  Pairs shorter
+    than 25 m are stretched to 25 m along their own direction (an 8-piece, 20 s trajectory over a few metres is degenerate).
+    Returns [n, 4] = (start x, start y, goal x, goal y)."""
     rng = _rng(seed)
     lo, hi = extent
     sg = rng.uniform(lo, hi, size=(n_problems, 4))
-    # reject degenerate (too short) pairs deterministically by stretching them
+    if coords_path and os.path.exists(coords_path) and n_problems > 0:
+        c = np.loadtxt(coords_path, delimiter=",")
+        m = min(n_problems, c.shape[0])
+        sg[:m, 0:2] = c[:m, 0:2]
+        sg[:m, 2:4] = c[:m, 3:5]
+        sg[:m] = np.clip(sg[:m], lo, hi)
     d = sg[:, 2:] - sg[:, :2]
     L = np.linalg.norm(d, axis=1)
     short = L < 25.0
-    sg[short, 2:] = sg[short, :2] + d[short] / np.maximum(L[short, None], 1e-9) * 25.0
+    u = np.where(L[:, None] > 1e-9, d / np.maximum(L[:, None], 1e-9), np.array([[1.0, 0.0]]))
+    sg[short, 2:] = sg[short, :2] + u[short] * 25.0
+    # a stretched goal may leave the map: reflect it back along the same direction
+    out = ((sg[:, 2:] < lo) | (sg[:, 2:] > hi)).any(axis=1)
+    sg[out, 2:] = sg[out, :2] - u[out] * 25.0
+    sg[:, 2:] = np.clip(sg[:, 2:], lo, hi)
     return sg
 
 

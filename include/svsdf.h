@@ -185,6 +185,44 @@ int svsdf_shape_grad1(svsdf_ctx *ctx, int64_t n, const double *rel, double *grad
 int svsdf_cost_grad_device(svsdf_ctx *ctx, int N, const double *T, const double *coeffs, int repeats,
                            float *ms_per_eval, double *out_host);
 
+/* ---- Batch variants (leading problem dimension; BASELINE config 5) -----------------------------------
+ * Independent problems are spread over a POOL of contexts (one worker thread per context; several contexts may sit on the
+ * same GPU — each has its own stream, so the host side of one problem (MINCO, line search) and the latency-bound tail of its
+ * kernels overlap the kernels of another — or on different GPUs of the process).  Problems are handed out dynamically: a
+ * worker takes the next index when it finishes one (`next`: optional source of indices shared with other processes, e.g. a
+ * counter in the torch.distributed store; return < 0 or >= n_problems to stop; NULL = internal counter 0, 1, 2, ...).
+ * Results do not depend on which context solved a problem (bit-reproducible kernels).
+ *
+ * svsdf_problem: one optimisation.  Query points are either given (points != NULL: P rows of `stride` doubles) or built on
+ * the device from the context's map around the waypoints (svsdf_extract_points semantics; the map must have been set on every
+ * context of the pool). */
+typedef struct {
+    const double *initS, *finalS;   /* 3x3 column-major boundary states */
+    double *opt_x;                  /* in: start, out: result; N + 3 (N - 1) entries */
+    const double *points;           /* explicit query points or NULL */
+    int64_t P;
+    int stride;
+    const double *waypoints_xy;     /* W x 2 (used when points == NULL) */
+    int W;
+    double half;
+    const double *keepout_xy;       /* optional keep-out samples (synthetic scenes), n_keepout x 2 */
+    int n_keepout;
+    double clearance;
+    double *T_out, *coeffs_out;     /* optional: final durations [N] and MINCO coefficients [18 N] */
+} svsdf_problem;
+typedef int (*svsdf_next_problem_t)(void *user);
+/* stats_out[n_problems] (optional), status_out[n_problems] (svsdf_optimize return values), points_out[n_problems] (optional:
+ * number of query points of each problem).  Returns SVSDF_OK when every problem ran (individual solver codes are in
+ * status_out), the first API error otherwise. */
+int svsdf_optimize_batch(svsdf_ctx *const *ctxs, int n_ctx, const svsdf_problem *problems, int n_problems, int N,
+                         const svsdf_lbfgs_params *params, svsdf_next_problem_t next, void *next_user,
+                         svsdf_opt_stats *stats_out, int *status_out, int64_t *points_out);
+/* One cost + gradient evaluation per problem with HOST buffers (the batch form of svsdf_set_points + svsdf_cost_grad):
+ * pts[k]: P[k] rows of `stride` doubles; T: [n][N]; coeffs: [n][18 N] column-major per problem; cost_io [n], gradT_io [n][N],
+ * gradC_io [n][18 N] accumulate like svsdf_cost_grad. */
+int svsdf_cost_grad_batch(svsdf_ctx *const *ctxs, int n_ctx, int n_problems, int N, const double *const *pts, const int64_t *P,
+                          int stride, const double *T, const double *coeffs, double *cost_io, double *gradT_io, double *gradC_io);
+
 /* ---- "next" row: query-point construction on the device --------------------------------------
  * R8  PlannerManager::generateTraj point collection  plan_manager/src/plan_manager.cpp:156-175
  *     PCSmapManager::getPointsInAABBOutOfLastOne       map_manager/include/map_manager/PCSmap_manager.h:184-219

@@ -47,6 +47,11 @@ def _worker(rank, world, port, tmpdir):
         np.save(os.path.join(tmpdir, f"occ_{rank}.npy"), occ)
         mine = list(batch.partition(7, world, rank))
         np.save(os.path.join(tmpdir, f"mine_{rank}.npy"), np.array(mine))
+        # dynamic work queue shared by the ranks (counter in the c10d store), LPT order
+        dyn = batch.BatchRunner(_fake_solve, 4, dynamic=True)
+        out_d = dyn.run(gm_local, problems, N=8, P=None)
+        np.save(os.path.join(tmpdir, f"outdyn_{rank}.npy"), out_d)
+        np.save(os.path.join(tmpdir, f"minedyn_{rank}.npy"), np.array(dyn.mine, dtype=np.int64))
     finally:
         dist.destroy_process_group()
 
@@ -103,3 +108,23 @@ def test_world_size_2_gloo_broadcast_shard_gather(tmp_path):
     ref = batch.BatchRunner(_fake_solve, 4).run(gm, problems, N=8, P=None)
     assert np.array_equal(ref, o0)
     assert np.array_equal(o0[:, 0], np.arange(7))
+    # dynamic queue: same table on both ranks, every problem handed out exactly once across the ranks, first ticket = longest
+    d0, d1 = np.load(tmp_path / "outdyn_0.npy"), np.load(tmp_path / "outdyn_1.npy")
+    assert np.array_equal(d0, d1) and np.array_equal(d0, ref)
+    t0, t1 = list(np.load(tmp_path / "minedyn_0.npy")), list(np.load(tmp_path / "minedyn_1.npy"))
+    assert sorted(t0 + t1) == list(range(7))
+    order = list(batch.lpt_order(problems))
+    assert order[0] in (t0[:1] + t1[:1])
+
+
+def test_config5_problem_set_uses_the_reference_coords_file():
+    sg = scenes.make_batch_problems(1200)
+    c = np.loadtxt(scenes.COORDS_TXT, delimiter=",")
+    assert c.shape == (1000, 6)  # src/coords.txt of the reference (copied as a fixture)
+    L = np.linalg.norm(sg[:, 2:] - sg[:, :2], axis=1)
+    assert (L >= 25.0 - 1e-9).mean() > 0.97 and sg.min() >= 2.0 and sg.max() <= 58.0
+    keep = np.linalg.norm(c[:, 3:5] - c[:, 0:2], axis=1) >= 25.0
+    inside = ((c[:, [0, 1, 3, 4]] >= 2.0) & (c[:, [0, 1, 3, 4]] <= 58.0)).all(axis=1)
+    ok = keep & inside
+    assert ok.sum() > 300 and np.array_equal(sg[:1000][ok], c[ok][:, [0, 1, 3, 4]])  # untouched rows are the file's rows
+    assert np.array_equal(sg, scenes.make_batch_problems(1200))  # deterministic
