@@ -88,7 +88,7 @@ EXPORTED_SYMBOLS = [
     "svsdf_optimize", "svsdf_optimize_batch", "svsdf_cost_grad_batch", "svsdf_minco_forward", "svsdf_minco_propagate", "svsdf_forward_T", "svsdf_backward_T",
     "svsdf_shape_sdf", "svsdf_shape_grad1", "svsdf_cost_grad_device", "svsdf_kernel_launches",
     "svsdf_executed_evals", "svsdf_fp64_peak", "svsdf_device_ptr_points", "svsdf_lbfgs_minimize", "svsdf_last_kernel_ms", "svsdf_sincos", "svsdf_set_map", "svsdf_set_map_device",
-    "svsdf_extract_points", "svsdf_get_points", "svsdf_read_obj", "svsdf_free",
+    "svsdf_extract_points", "svsdf_get_points", "svsdf_read_obj", "svsdf_free", "svsdf_mesh_fwn_host",
     "svsdf_front_init", "svsdf_front_get_kernels", "svsdf_front_cspace", "svsdf_front_check_kernel_value", "svsdf_front_expand", "svsdf_front_astar",
 ]
 
@@ -323,6 +323,27 @@ def shape_bound_radius(shape="star", poly_params=(0.0, 0.0, 0.0), polygon=None) 
     if rc != 0:
         raise SvsdfError(f"svsdf_shape_bound_radius failed with status {rc}")
     return out.value
+
+
+def mesh_fwn_host(V, F, Q=None):
+    """svsdf_mesh_fwn_host: (children [nn, 4] uint32, data [nn, 23, 4] float32, w [n]) of the library's own winding-number hierarchy."""
+    V = _f64(V).reshape(-1, 3)
+    F = np.ascontiguousarray(F, dtype=np.int32).reshape(-1, 3)
+    nn = C.c_int()
+    L = lib()
+    i32p = C.POINTER(C.c_int32)
+    rc = L.svsdf_mesh_fwn_host(_p(V), V.shape[0], F.ctypes.data_as(i32p), F.shape[0], C.byref(nn), 0, None, None, C.c_int64(0), None, None)
+    if rc != 0:
+        raise SvsdfError(f"svsdf_mesh_fwn_host failed with status {rc}")
+    ch = np.zeros((nn.value, 4), dtype=np.uint32)
+    data = np.zeros((nn.value, 23, 4), dtype=np.float32)
+    Q = _f64(Q).reshape(-1, 3) if Q is not None else np.zeros((0, 3))
+    w = np.zeros(Q.shape[0])
+    rc = L.svsdf_mesh_fwn_host(_p(V), V.shape[0], F.ctypes.data_as(i32p), F.shape[0], C.byref(nn), nn.value, ch.ctypes.data_as(C.c_void_p),
+                               data.ctypes.data_as(C.c_void_p), C.c_int64(Q.shape[0]), _p(Q), _p(w))
+    if rc != 0:
+        raise SvsdfError(f"svsdf_mesh_fwn_host failed with status {rc}")
+    return ch, data, w
 
 
 def read_obj(path: str):

@@ -40,6 +40,7 @@ HEADERS = [
     "host/minco.hpp",
     "host/lbfgs.hpp",
     "host/astar.hpp",
+    "host/fwn_bvh.hpp",
     "../../include/svsdf.h",
 ]
 

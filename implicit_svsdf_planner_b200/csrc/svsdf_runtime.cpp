@@ -22,6 +22,7 @@
 
 #include "../../include/svsdf.h"
 #include "host/astar.hpp"
+#include "host/fwn_bvh.hpp"
 #include "host/lbfgs.hpp"
 #include "host/minco.hpp"
 #include "svsdf_launch.h"
@@ -603,6 +604,20 @@ int svsdf_read_obj(const char *path, double **vertices_out, int *nv_out, int32_t
     *vertices_out = vo; *faces_out = fo; *nv_out = nv; *nf_out = nf;
     return SVSDF_OK;
 }
+int svsdf_mesh_fwn_host(const double *vertices, int nv, const int32_t *faces, int nf, int *n_nodes_out, int node_capacity,
+                        uint32_t *children_out, float *data_out, int64_t n, const double *q, double *w_out) {
+    if (!vertices || !faces || nv < 3 || nf < 1 || n < 0 || (n > 0 && (!q || !w_out))) return SVSDF_ERR_INVALID;
+    for (int64_t k = 0; k < 3 * (int64_t)nf; ++k)
+        if (faces[k] < 0 || faces[k] >= nv) return SVSDF_ERR_INVALID;
+    host::FwnBvh B;
+    B.build(vertices, nv, faces, nf);
+    if (n_nodes_out) *n_nodes_out = B.nn;
+    if (children_out && node_capacity >= B.nn) std::memcpy(children_out, B.child.data(), B.child.size() * sizeof(uint32_t));
+    if (data_out && node_capacity >= B.nn) std::memcpy(data_out, B.data.data(), B.data.size() * sizeof(float));
+    for (int64_t i = 0; i < n; ++i) w_out[i] = B.winding_number(q + 3 * i);
+    return SVSDF_OK;
+}
+
 void svsdf_free(void *p) { std::free(p); }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -8,6 +8,7 @@
 // Used only by tests/ (and tests/golden/make_fwn_golden.py) to pin the oracle's exact winding number against the
 // reference's float approximation of it.  No reference source is copied into this repository.
 #include <cstdint>
+#include <cstring>
 #include <vector>
 
 #include "igl/FastWindingNumberForSoups.h"
@@ -35,6 +36,22 @@ void *ref_fwn_create(const double *V, int nv, const int *F, int nf, int order) {
 }
 
 void ref_fwn_destroy(void *h) { delete (RefFwn *)h; }
+
+// Structure dump (compiled with -fno-access-control): the 4-way BVH the reference built and its per-node expansion data, so
+// that the product's own builder (csrc/host/fwn_bvh.hpp) can be compared node by node, not only through winding numbers.
+// children: [nn][4] raw child words (EMPTY = 0xffffffff, bit 31 = internal); boxdata: [nn][23][4] floats in BoxData member order
+// (myMaxPDist2, myAverageP[3], myN[3], myNijDiag[3], myNxy_Nyx, myNyz_Nzy, myNzx_Nxz, myNijkDiag[3], mySumPermuteNxyz,
+//  my2Nxxy_Nyxx, my2Nxxz_Nzxx, my2Nyyz_Nzyy, my2Nyyx_Nxyy, my2Nzzx_Nxzz, my2Nzzy_Nyzz), 4 lanes = the node's 4 children.
+int ref_fwn_num_nodes(void *h) { return (int)((RefFwn *)h)->ut_solid_angle.myTree.getNumNodes(); }
+void ref_fwn_dump(void *h, uint32_t *children, float *boxdata) {
+    RefFwn *r = (RefFwn *)h;
+    const int nn = (int)r->ut_solid_angle.myTree.getNumNodes();
+    const auto *nodes = r->ut_solid_angle.myTree.getNodes();
+    for (int i = 0; i < nn; ++i)
+        for (int c = 0; c < 4; ++c) children[4 * i + c] = nodes[i].child[c];
+    static_assert(sizeof(r->ut_solid_angle.myData[0]) == 23 * 16, "BoxData layout");
+    std::memcpy(boxdata, r->ut_solid_angle.myData.get(), (size_t)nn * 23 * 16);
+}
 
 void ref_fwn_eval(void *h, float accuracy_scale, int64_t n, const double *q, double *w_out) {
     RefFwn *r = (RefFwn *)h;
