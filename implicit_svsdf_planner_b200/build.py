@@ -29,7 +29,8 @@ UNITS = [
     ("svsdf_kernels_strict.cu", "svsdf_kernels_strict.o", ["-fmad=false"]),
     ("svsdf_extract.cu", "svsdf_extract.o", ["-fmad=false"]),  # cell centres must round like the host formula
     ("svsdf_frontend.cu", "svsdf_frontend.o", ["-fmad=false"]),  # shape kernels: same rounding as the strict functors
-    ("svsdf_runtime.cpp", "svsdf_runtime.o", ["-Xcompiler", "-fopenmp"]),  # host threads for the batch A* bookkeeping
+    # host threads for the batch A* bookkeeping; no a*b+c contraction in the float winding-number builder (host/fwn_bvh.hpp)
+    ("svsdf_runtime.cpp", "svsdf_runtime.o", ["-Xcompiler", "-fopenmp", "-Xcompiler", "-ffp-contract=off"]),
 ]
 HEADERS = [
     "svsdf_kernels.cuh",

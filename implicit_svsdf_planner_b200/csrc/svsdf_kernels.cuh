@@ -302,8 +302,8 @@ __device__ __forceinline__ OuterResult solve_outer(const TrajView &tv, const Sha
             if (__any_sync(FULL, f < min_dis || (f == min_dis && f < 1e9 && kl < kb))) {
                 min_dis = f;
                 kb = kl;
-                const double thr = f + S.rout;
-                thr2 = (thr >= 0.0) ? thr * thr : INF;
+                const double thr0 = f * S.prune_scale + S.rout, thr = fmax(thr0, S.prune_rmin);  // analytic shapes: f * 1 + rout, max with 0
+                thr2 = (thr0 >= 0.0) ? thr * thr : INF;
             }
         }
         seed = (kb >= 0) ? lds_f64(tv.slat + 8u * (uint32_t)kb) : 0.0;
@@ -626,8 +626,8 @@ __device__ __forceinline__ void thread_choice_t_init(const TrajView &tv, const S
         if (f < min_dis || (f == min_dis && k < kb)) {
             min_dis = f;
             kb = k;
-            const double thr = f + S.rout;               // < 0 cannot happen for a distance function; then no pruning
-            thr2 = (thr >= 0.0) ? thr * thr : INF;
+            const double thr0 = f * S.prune_scale + S.rout, thr = fmax(thr0, S.prune_rmin);  // analytic shapes: f * 1 + rout, max with 0
+            thr2 = (thr0 >= 0.0) ? thr * thr : INF;      // < 0 cannot happen for a distance function; then no pruning
         }
     }
     seed = (kb >= 0) ? lds_f64(tv.slat + 8u * (uint32_t)kb) : 0.0;

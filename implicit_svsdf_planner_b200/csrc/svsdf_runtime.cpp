@@ -48,7 +48,9 @@ struct svsdf_ctx {
     int64_t launches = 0;
 
     // query points
-    double *d_mesh_tri = nullptr;  // SH_MESH: 9 doubles per face
+    double *d_mesh_tri = nullptr;  // SH_MESH: kMeshStride doubles per face
+    unsigned int *d_fwn_child = nullptr;  // SH_MESH: the winding-number hierarchy (host/fwn_bvh.hpp)
+    float *d_fwn_data = nullptr, *d_fwn_cbox = nullptr, *d_fwn_trif = nullptr;
     // K5: A* front-end collision kernels
     bool front_ready = false;
     FrontParams front{};
@@ -166,6 +168,8 @@ void build_shape(const svsdf_config &cfg, ShapeParams &S) {
                     S.rot[3] == 1.0);
     S.radius = 1.0;
     S.rout = 1e300;
+    S.prune_scale = 1.0;
+    S.prune_rmin = 0.0;
     if (cfg.mesh_faces && cfg.mesh_nf > 0) {  // triangle-mesh functor requested: overrides the registry name
         S.id = SH_MESH;
         return;
@@ -916,6 +920,87 @@ int svsdf_create(const svsdf_config *cfg, svsdf_ctx **out) {
         ctx->shape.mesh_tri = ctx->d_mesh_tri;
         ctx->shape.mesh_nf = cfg->mesh_nf;
         ctx->shape.has_xform = 0;
+        // the winding-number hierarchy over the SAME transformed vertices (fast_winding_number.cpp:380-408 is handed V after
+        // the ctor's transform, Shape.hpp:303-309), built on the host and uploaded as four flat arrays
+        std::vector<double> Vt((size_t)cfg->mesh_nv * 3);
+        for (int i = 0; i < cfg->mesh_nv; ++i) {
+            const double *v = cfg->mesh_vertices + 3 * (size_t)i;
+            for (int j = 0; j < 3; ++j) Vt[3 * (size_t)i + j] = ((v[0] * R[j][0] + v[1] * R[j][1]) + v[2] * R[j][2]) + tr[j];
+        }
+        host::FwnBvh B;
+        B.build(Vt.data(), cfg->mesh_nv, cfg->mesh_faces, cfg->mesh_nf);
+        if (B.nn < 1 || B.depth() > kFwnMaxDepth) {
+            ctx->err = "svsdf_create: mesh hierarchy deeper than kFwnMaxDepth";
+            svsdf_destroy(ctx);
+            return SVSDF_ERR_INVALID;
+        }
+        std::vector<float> cb(B.cbox);
+        for (size_t k = 0; k < cb.size(); ++k) {  // outwards by two ulps: the float boxes then contain the double vertices
+            const bool is_min = (k % 6) < 3;
+            const float dir = is_min ? -std::numeric_limits<float>::infinity() : std::numeric_limits<float>::infinity();
+            if (std::isfinite(cb[k])) cb[k] = std::nextafter(std::nextafter(cb[k], dir), dir);
+        }
+        std::vector<float> tf((size_t)cfg->mesh_nf * 12, 0.0f);
+        for (int f = 0; f < cfg->mesh_nf; ++f)
+            for (int k = 0; k < 3; ++k)
+                for (int j = 0; j < 3; ++j) tf[12 * (size_t)f + 3 * k + j] = B.U[3 * (size_t)B.F[3 * f + k] + j];
+        const size_t b_child = B.child.size() * sizeof(uint32_t), b_data = B.data.size() * sizeof(float), b_box = cb.size() * sizeof(float),
+                     b_tri = tf.size() * sizeof(float);
+        auto up = [&](void **dst, const void *src, size_t bytes) -> cudaError_t {
+            cudaError_t e2 = cudaMalloc(dst, bytes);
+            if (e2 != cudaSuccess) return e2;
+            return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
+        };
+        if ((e = up((void **)&ctx->d_fwn_child, B.child.data(), b_child)) != cudaSuccess) return fail(e);
+        if ((e = up((void **)&ctx->d_fwn_data, B.data.data(), b_data)) != cudaSuccess) return fail(e);
+        if ((e = up((void **)&ctx->d_fwn_cbox, cb.data(), b_box)) != cudaSuccess) return fail(e);
+        if ((e = up((void **)&ctx->d_fwn_trif, tf.data(), b_tri)) != cudaSuccess) return fail(e);
+        // Far-field bound for choiceTInit's layer-1 pruning (thread_choice_t_init): sdf = (1 - 2 w) d with d >= |q| - Rv (Rv: the
+        // largest vertex norm; the query has z = 0, the origin is the body origin).  Beyond rho0 = max_i(|P_i| + 2 sqrt(maxPDist2_i))
+        // none of the root's children is entered, w is the sum of their four expansions / (4 pi), and each expansion is bounded
+        // term by term through the magnitudes of its coefficients (|q^| <= 1 componentwise) and |q - P_i| >= rho0 - |P_i|:
+        //   |order 0| <= |N|_1 m^2,  |order 1| <= (|tr| + 3 (sum of |Nij| rows)) m^3,  |order 2| <= (1.5 A + 7.5 B) m^4,  m = 1 / (rho0 - |P_i|).
+        // With omega that bound (padded 2 % for the float rounding of the evaluation), sdf >= (1 - 2 omega)(|q| - Rv) for |q| >= rho0.
+        {
+            double Rv = 0.0;
+            for (int i = 0; i < cfg->mesh_nv; ++i)
+                Rv = std::max(Rv, std::sqrt(Vt[3 * (size_t)i] * Vt[3 * (size_t)i] + Vt[3 * (size_t)i + 1] * Vt[3 * (size_t)i + 1] + Vt[3 * (size_t)i + 2] * Vt[3 * (size_t)i + 2]));
+            double rho0 = 0.0;
+            int nchild = 0;
+            for (int i = 0; i < 4; ++i) {
+                if (B.child[i] == host::FwnBvh::EMPTY) break;
+                ++nchild;
+                const double Pn = std::sqrt((double)B.row(0, 1)[i] * B.row(0, 1)[i] + (double)B.row(0, 2)[i] * B.row(0, 2)[i] + (double)B.row(0, 3)[i] * B.row(0, 3)[i]);
+                rho0 = std::max(rho0, Pn + 2.0 * std::sqrt(std::max(0.0, (double)B.row(0, 0)[i])));
+            }
+            rho0 = std::max(rho0, Rv) * (1.0 + 1e-4) + 1e-6;
+            double omega = 0.0;
+            bool finite = std::isfinite(rho0);
+            for (int i = 0; i < nchild && finite; ++i) {
+                auto a = [&](int r) { return std::fabs((double)B.row(0, r)[i]); };
+                const double Pn = std::sqrt((double)B.row(0, 1)[i] * B.row(0, 1)[i] + (double)B.row(0, 2)[i] * B.row(0, 2)[i] + (double)B.row(0, 3)[i] * B.row(0, 3)[i]);
+                const double m = 1.0 / (rho0 - Pn);
+                const double A0 = a(4) + a(5) + a(6);
+                const double A1 = std::fabs((double)B.row(0, 7)[i] + B.row(0, 8)[i] + B.row(0, 9)[i]) + 3.0 * (a(7) + a(8) + a(9) + a(10) + a(11) + a(12));
+                const double t0 = std::fabs((double)B.row(0, 20)[i] + B.row(0, 21)[i]) + std::fabs((double)B.row(0, 22)[i] + B.row(0, 17)[i]) +
+                                  std::fabs((double)B.row(0, 18)[i] + B.row(0, 19)[i]);
+                const double t1 = a(17) + a(18) + a(19) + a(20) + a(21) + a(22);
+                const double A2 = 1.5 * (3.0 * (a(13) + a(14) + a(15)) + t0) + 7.5 * (a(13) + a(14) + a(15) + a(16) + t1);
+                omega += A0 * m * m + A1 * m * m * m + A2 * m * m * m * m;
+                finite = finite && std::isfinite(omega);
+            }
+            omega = omega / (4.0 * 3.14159265358979323846) * 1.02 + 1e-6;
+            if (finite && omega < 0.45) {
+                ctx->shape.rout = Rv * (1.0 + 1e-9) + 1e-9;
+                ctx->shape.prune_scale = 1.0 / (1.0 - 2.0 * omega);
+                ctx->shape.prune_rmin = rho0;
+            }
+        }
+        ctx->shape.fwn_nn = B.nn;
+        ctx->shape.fwn_child = ctx->d_fwn_child;
+        ctx->shape.fwn_data = ctx->d_fwn_data;
+        ctx->shape.fwn_cbox = ctx->d_fwn_cbox;
+        ctx->shape.fwn_trif = ctx->d_fwn_trif;
     }
     *out = ctx;
     return SVSDF_OK;
@@ -926,7 +1011,7 @@ void svsdf_destroy(svsdf_ctx *ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->own_points) cudaFree(ctx->d_points);
-    cudaFree(ctx->d_mesh_tri);
+    cudaFree(ctx->d_mesh_tri); cudaFree(ctx->d_fwn_child); cudaFree(ctx->d_fwn_data); cudaFree(ctx->d_fwn_cbox); cudaFree(ctx->d_fwn_trif);
     cudaFree(ctx->d_front_bytes); cudaFree(ctx->d_front_rowmask); cudaFree(ctx->d_cspace); cudaFree(ctx->d_front_scratch);
     cudaFree(ctx->d_flag); cudaFree(ctx->d_inside_tstar); cudaFree(ctx->d_inside_list);
     cudaFree(ctx->d_gsip_contrib); cudaFree(ctx->d_gsip_piece); cudaFree(ctx->d_n_inside);

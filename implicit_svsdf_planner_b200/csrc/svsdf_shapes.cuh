@@ -346,115 +346,262 @@ struct ShapeFn<SH_POLYGON> {
 };
 
 // Triangle-mesh functor — BasicShape::getonlySDF_igl (Shape.hpp:332-340): sdf = (1 - 2 w) * sqrt(d2).
-//   w  = winding number: the reference asks igl::fast_winding_number (fast_winding_number.cpp:439-457), a float BVH whose
-//        leaves evaluate the per-triangle solid angle exactly (UTsignedSolidAngleTri, FastWindingNumberForSoups.h:6071-6110)
-//        and whose far clusters approximate the same sum; here: the sum itself, in double, same per-triangle formula.
+//   w  = igl::fast_winding_number(fwn_bvh, 2.0, p) (fast_winding_number.cpp:439-457): the HDK's UT_SolidAngle<float,float>,
+//        a 4-way hierarchy with order-2 expansions, evaluated in SINGLE precision.  The hierarchy is built on the host
+//        (host/fwn_bvh.hpp, bitwise the reference's tree and coefficients); fwn_solid_angle() below walks it exactly as
+//        computeSolidAngle's recursive traverseVector does (FastWindingNumberForSoups.h:7149-7284): per node the four child
+//        expansions summed left to right, then the descended children's results summed left to right in slot order — an
+//        explicit stack of frames stands in for the recursion.  Every float operation is a *_rn intrinsic (no FMA), atan2f
+//        is the pinned fdlibm code: w equals the reference's value BIT FOR BIT (tests/test_gpu_mesh.py).
 //   d2 = squared distance to the closest triangle: igl::AABB::squared_distance (AABB.cpp:1130-1200) is a pruned minimum over
-//        point_simplex_squared_distance (point_simplex_squared_distance.cpp:43-116, Ericson's closest point); here the plain
-//        minimum over all faces — the same number.
+//        point_simplex_squared_distance (point_simplex_squared_distance.cpp:43-116, Ericson's closest point), in double.
+//        closest_sqr_distance() prunes over the SAME 4-way tree's child boxes (rounded outwards, so they contain the double
+//        vertices): a subtree is skipped only when its box is provably farther than the best face so far, hence the result
+//        is the plain minimum over all faces — the same number the reference's own pruned search returns.
 // The query is (qx, qy, 0): the path zeroes the z of both the pose and the point (sw_manager.hpp:767,
-// back_end_optimizer.hpp:791).  One pass over the faces does both sums; every lane of a warp reads the same face at the
-// same time (uniform __ldg -> one L1 transaction per operand).
+// back_end_optimizer.hpp:791).
 template <>
 struct ShapeFn<SH_MESH> {
-    static __device__ __forceinline__ double solid_angle(double ax, double ay, double az, double bx, double by, double bz,
-                                                         double cx, double cy, double cz) {
-        const double al = sqrt((ax * ax + ay * ay) + az * az);
-        const double bl = sqrt((bx * bx + by * by) + bz * bz);
-        const double cl = sqrt((cx * cx + cy * cy) + cz * cz);
-        if (al == 0 || bl == 0 || cl == 0) return 0.0;
-        const double ia = 1.0 / al, ib = 1.0 / bl, ic = 1.0 / cl;
-        ax *= ia; ay *= ia; az *= ia;
-        bx *= ib; by *= ib; bz *= ib;
-        cx *= ic; cy *= ic; cz *= ic;
-        const double ux = bx - ax, uy = by - ay, uz = bz - az;
-        const double vx = cx - ax, vy = cy - ay, vz = cz - az;
-        const double nx = uy * vz - uz * vy, ny = uz * vx - ux * vz, nz = ux * vy - uy * vx;
-        const double num = (ax * nx + ay * ny) + az * nz;
-        if (num == 0) return 0.0;
-        const double dab = (ax * bx + ay * by) + az * bz;
-        const double dac = (ax * cx + ay * cy) + az * cz;
-        const double dbc = (bx * cx + by * cy) + bz * cz;
-        const double den = ((1.0 + dab) + dac) + dbc;
-        return 2.0 * atan2_portable(num, den);
+    // UTsignedSolidAngleTri (FastWindingNumberForSoups.h:6071-6110), float
+    static __device__ __forceinline__ float tri_solid_angle(const float4 *T, float qx, float qy, float qz) {
+        const float4 t0 = __ldg(T), t1 = __ldg(T + 1), t2 = __ldg(T + 2);  // a.xyz b.x | b.yz c.xy | c.z - - -
+        float a0 = fsub(t0.x, qx), a1 = fsub(t0.y, qy), a2 = fsub(t0.z, qz);
+        float b0 = fsub(t0.w, qx), b1 = fsub(t1.x, qy), b2 = fsub(t1.y, qz);
+        float c0 = fsub(t1.z, qx), c1 = fsub(t1.w, qy), c2 = fsub(t2.x, qz);
+        const float al = __fsqrt_rn(fadd(fadd(fmul(a0, a0), fmul(a1, a1)), fmul(a2, a2)));
+        const float bl = __fsqrt_rn(fadd(fadd(fmul(b0, b0), fmul(b1, b1)), fmul(b2, b2)));
+        const float cl = __fsqrt_rn(fadd(fadd(fmul(c0, c0), fmul(c1, c1)), fmul(c2, c2)));
+        if (al == 0.0f || bl == 0.0f || cl == 0.0f) return 0.0f;
+        const float ia = fdiv(1.0f, al), ib = fdiv(1.0f, bl), ic = fdiv(1.0f, cl);
+        a0 = fmul(a0, ia); a1 = fmul(a1, ia); a2 = fmul(a2, ia);
+        b0 = fmul(b0, ib); b1 = fmul(b1, ib); b2 = fmul(b2, ib);
+        c0 = fmul(c0, ic); c1 = fmul(c1, ic); c2 = fmul(c2, ic);
+        const float u0 = fsub(b0, a0), u1 = fsub(b1, a1), u2 = fsub(b2, a2);
+        const float v0 = fsub(c0, a0), v1 = fsub(c1, a1), v2 = fsub(c2, a2);
+        const float n0 = fsub(fmul(u1, v2), fmul(u2, v1)), n1 = fsub(fmul(u2, v0), fmul(u0, v2)), n2 = fsub(fmul(u0, v1), fmul(u1, v0));
+        const float num = fadd(fadd(fmul(a0, n0), fmul(a1, n1)), fmul(a2, n2));
+        if (num == 0.0f) return 0.0f;
+        const float dab = fadd(fadd(fmul(a0, b0), fmul(a1, b1)), fmul(a2, b2));
+        const float dac = fadd(fadd(fmul(a0, c0), fmul(a1, c1)), fmul(a2, c2));
+        const float dbc = fadd(fadd(fmul(b0, c0), fmul(b1, c1)), fmul(b2, c2));
+        const float den = fadd(fadd(fadd(1.0f, dab), dac), dbc);
+        return fmul(2.0f, atan2f_portable(num, den));
     }
-    // squared distance from p to triangle (a, b, c); ap = p - a etc. are passed in (shared with the solid angle)
+    // one node: the four children's order-2 expansions (computeSolidAngle's per-lane arithmetic, :7190-7255), summed left to
+    // right; bit i of `descend` = child i has to be entered.  Row r, lane i of the node record is D[4 * r + i].  The loop
+    // is NOT unrolled and this function has ONE call site: the traversal's code has to stay resident in the instruction cache
+    // while the lanes of a warp sit in different parts of it.
+    static __device__ __forceinline__ void node_terms(const float *D, float qx, float qy, float qz, float acc2, float &sum, unsigned &descend) {
+        descend = 0;
+        sum = 0.0f;
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {
+            const float *r = D + i;
+#define R_(k) __ldg(r + 4 * (k))
+            float q0 = fsub(qx, R_(1)), q1 = fsub(qy, R_(2)), q2 = fsub(qz, R_(3));
+            const float ql2 = fadd(fadd(fmul(q0, q0), fmul(q1, q1)), fmul(q2, q2));
+            float om = 0.0f;
+            // a child inside its own accuracy radius is entered whatever its expansion says (the reference evaluates all four
+            // lanes in SIMD and discards this one): skip the ~150 operations
+            bool use = !(ql2 <= fmul(R_(0), acc2));
+            if (use) {
+                const float m2 = fdiv(1.0f, ql2), m1 = __fsqrt_rn(m2);
+                q0 = fmul(q0, m1); q1 = fmul(q1, m1); q2 = fmul(q2, m1);
+                om = fmul(-m2, fadd(fadd(fmul(q0, R_(4)), fmul(q1, R_(5))), fmul(q2, R_(6))));
+                const float s0 = fmul(q0, q0), s1 = fmul(q1, q1), s2 = fmul(q2, q2);
+                const float m3 = fmul(m2, m1);
+                const float r7 = R_(7), r8 = R_(8), r9 = R_(9);
+                const float in1 = fadd(fadd(fadd(fadd(fadd(fmul(s0, r7), fmul(s1, r8)), fmul(s2, r9)), fmul(fmul(q0, q1), R_(10))),
+                                            fmul(fmul(q0, q2), R_(12))), fmul(fmul(q1, q2), R_(11)));
+                const float o1 = fmul(m3, fsub(fadd(fadd(r7, r8), r9), fmul(3.0f, in1)));
+                om = fadd(om, o1);
+                const float c0 = fmul(s0, q0), c1 = fmul(s1, q1), c2 = fmul(s2, q2);
+                const float m4 = fmul(m2, m2);
+                const float r13 = R_(13), r14 = R_(14), r15 = R_(15), r17 = R_(17), r18 = R_(18), r19 = R_(19), r20 = R_(20), r21 = R_(21),
+                            r22 = R_(22);
+                const float t00 = fadd(r20, r21), t01 = fadd(r22, r17), t02 = fadd(r18, r19);
+                const float t10 = fadd(fmul(q1, r17), fmul(q2, r18)), t11 = fadd(fmul(q2, r19), fmul(q0, r20)),
+                            t12 = fadd(fmul(q0, r21), fmul(q1, r22));
+                const float da = fadd(fadd(fmul(q0, fadd(fmul(3.0f, r13), t00)), fmul(q1, fadd(fmul(3.0f, r14), t01))),
+                                      fmul(q2, fadd(fmul(3.0f, r15), t02)));
+                const float db = fadd(fadd(fadd(fadd(fmul(c0, r13), fmul(c1, r14)), fmul(c2, r15)), fmul(fmul(fmul(q0, q1), q2), R_(16))),
+                                      fadd(fadd(fmul(s0, t10), fmul(s1, t11)), fmul(s2, t12)));
+                const float o2 = fmul(m4, fsub(fmul(1.5f, da), fmul(7.5f, db)));
+                om = fadd(om, o2);
+                use = isfinite(om);
+            }
+#undef R_
+            const float a = use ? om : 0.0f;
+            sum = (i == 0) ? a : fadd(sum, a);  // ((a0 + a1) + a2) + a3; all four entered -> 0, as the reference's early return
+            if (!use) descend |= 1u << i;
+        }
+    }
+    static __device__ __noinline__ float fwn_solid_angle(const ShapeParams &S, float qx, float qy, float qz) {
+        const float acc2 = 4.0f;  // accuracy_scale 2.0 (Shape.hpp:337), squared
+        const float4 *trif = reinterpret_cast<const float4 *>(S.fwn_trif);
+        // frame d: node, expansion sum, descend mask (bits 0-3) | next slot (bits 4-6), partial sum of the slots done so far
+        int f_node[kFwnMaxDepth];
+        float f_sum[kFwnMaxDepth], f_ps[kFwnMaxDepth];
+        unsigned f_st[kFwnMaxDepth];
+        int d = -1, next = 0;
+        float ret = 0.0f;
+        bool have_ret = false;
+#pragma unroll 1
+        for (;;) {
+            if (!have_ret) {  // enter node `next` as a new frame
+                ++d;
+                f_node[d] = next;
+                f_ps[d] = 0.0f;
+                node_terms(S.fwn_data + 92 * (size_t)next, qx, qy, qz, acc2, f_sum[d], f_st[d]);
+            }
+            const unsigned st = f_st[d];
+            int s = (int)(st >> 4);
+            float ps = f_ps[d];
+            if (have_ret) {  // a child frame has just returned into slot s
+                ps = (s == 0) ? ret : fadd(ps, ret);
+                ++s;
+                have_ret = false;
+            }
+            bool pushed = false;
+#pragma unroll 1
+            while (s < 4) {
+                float v = 0.0f;
+                if ((st >> s) & 1u) {
+                    const unsigned c = __ldg(S.fwn_child + 4 * (size_t)f_node[d] + s);
+                    if (c & 0x80000000u) {
+                        if (c == 0xffffffffu) break;  // no more children: the remaining slots are not summed
+                        if (d + 1 < kFwnMaxDepth) {
+                            f_st[d] = (st & 0xfu) | ((unsigned)s << 4);
+                            f_ps[d] = ps;
+                            next = (int)(c & 0x7fffffffu);
+                            pushed = true;
+                            break;
+                        }
+                    } else {
+                        v = tri_solid_angle(trif + 3 * (size_t)c, qx, qy, qz);
+                    }
+                }
+                ps = (s == 0) ? v : fadd(ps, v);
+                ++s;
+            }
+            if (pushed) continue;
+            ret = fadd(f_sum[d], ps);
+            if (d == 0) return ret;
+            --d;
+            have_ret = true;
+        }
+    }
+    // lower bound of the squared distance from (qx, qy, 0) to a child box (6 floats: min xyz, max xyz)
+    static __device__ __forceinline__ double box_lb2(const float *b, double qx, double qy) {
+        const float2 b01 = __ldg(reinterpret_cast<const float2 *>(b)), b23 = __ldg(reinterpret_cast<const float2 *>(b) + 1),
+                     b45 = __ldg(reinterpret_cast<const float2 *>(b) + 2);
+        const double dx = fmax(fmax((double)b01.x - qx, qx - (double)b23.y), 0.0);
+        const double dy = fmax(fmax((double)b01.y - qy, qy - (double)b45.x), 0.0);
+        const double dz = fmax(fmax((double)b23.x, -(double)b45.y), 0.0);
+        return (dx * dx + dy * dy) + dz * dz;
+    }
+    // Squared distance from p to triangle (a, b, c): ClosestBaryPtPointTriangle (point_simplex_squared_distance.cpp:43-106).
+    // The reference walks the seven Voronoi regions with early returns; here the region is decided first (same conditions,
+    // same order: A, B, AB, C, AC, BC, interior) and the ONE division the chosen region needs is done once — lane for lane
+    // the same IEEE operations as the early-return form (the oracle's), but a warp whose lanes fall into different regions
+    // no longer executes four divergent division sequences.
     static __device__ __forceinline__ double sqr_distance(double ax, double ay, double az, double bx, double by, double bz,
                                                           double cx, double cy, double cz, double px, double py, double pz) {
         const double abx = bx - ax, aby = by - ay, abz = bz - az;
         const double acx = cx - ax, acy = cy - ay, acz = cz - az;
         const double apx = px - ax, apy = py - ay, apz = pz - az;
-        double qx = ax, qy = ay, qz = az;
         const double d1 = (abx * apx + aby * apy) + abz * apz;
         const double d2 = (acx * apx + acy * apy) + acz * apz;
-        if (!(d1 <= 0.0 && d2 <= 0.0)) {
-            const double bpx = px - bx, bpy = py - by, bpz = pz - bz;
-            const double d3 = (abx * bpx + aby * bpy) + abz * bpz;
-            const double d4 = (acx * bpx + acy * bpy) + acz * bpz;
-            if (d3 >= 0.0 && d4 <= d3) {
-                qx = bx; qy = by; qz = bz;
-            } else {
-                const double vc = d1 * d4 - d3 * d2;
-                const bool a_ne_b = (ax != bx) || (ay != by) || (az != bz);
-                if (a_ne_b && vc <= 0.0 && d1 >= 0.0 && d3 <= 0.0) {
-                    const double v = d1 / (d1 - d3);
-                    qx = ax + v * abx; qy = ay + v * aby; qz = az + v * abz;
-                } else {
-                    const double cpx = px - cx, cpy = py - cy, cpz = pz - cz;
-                    const double d5 = (abx * cpx + aby * cpy) + abz * cpz;
-                    const double d6 = (acx * cpx + acy * cpy) + acz * cpz;
-                    if (d6 >= 0.0 && d5 <= d6) {
-                        qx = cx; qy = cy; qz = cz;
-                    } else {
-                        const double vb = d5 * d2 - d1 * d6;
-                        if (vb <= 0.0 && d2 >= 0.0 && d6 <= 0.0) {
-                            const double w = d2 / (d2 - d6);
-                            qx = ax + w * acx; qy = ay + w * acy; qz = az + w * acz;
-                        } else {
-                            const double va = d3 * d6 - d5 * d4;
-                            if (va <= 0.0 && (d4 - d3) >= 0.0 && (d5 - d6) >= 0.0) {
-                                const double w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
-                                qx = bx + w * (cx - bx); qy = by + w * (cy - by); qz = bz + w * (cz - bz);
-                            } else {
-                                const double denom = 1.0 / ((va + vb) + vc);
-                                const double v = vb * denom, w = vc * denom;
-                                qx = (ax + abx * v) + acx * w; qy = (ay + aby * v) + acy * w; qz = (az + abz * v) + acz * w;
-                            }
-                        }
-                    }
-                }
-            }
-        }
+        const double bpx = px - bx, bpy = py - by, bpz = pz - bz;
+        const double d3 = (abx * bpx + aby * bpy) + abz * bpz;
+        const double d4 = (acx * bpx + acy * bpy) + acz * bpz;
+        const double cpx = px - cx, cpy = py - cy, cpz = pz - cz;
+        const double d5 = (abx * cpx + aby * cpy) + abz * cpz;
+        const double d6 = (acx * cpx + acy * cpy) + acz * cpz;
+        const double vc = d1 * d4 - d3 * d2, vb = d5 * d2 - d1 * d6, va = d3 * d6 - d5 * d4;
+        const double e43 = d4 - d3, e56 = d5 - d6;
+        const bool a_ne_b = (ax != bx) || (ay != by) || (az != bz);
+        const bool rA = d1 <= 0.0 && d2 <= 0.0;
+        const bool rB = !rA && d3 >= 0.0 && d4 <= d3;
+        const bool rAB = !rA && !rB && a_ne_b && vc <= 0.0 && d1 >= 0.0 && d3 <= 0.0;
+        const bool done3 = rA || rB || rAB;
+        const bool rC = !done3 && d6 >= 0.0 && d5 <= d6;
+        const bool rAC = !done3 && !rC && vb <= 0.0 && d2 >= 0.0 && d6 <= 0.0;
+        const bool done5 = done3 || rC || rAC;
+        const bool rBC = !done5 && va <= 0.0 && e43 >= 0.0 && e56 >= 0.0;
+        const bool rIN = !done5 && !rBC;
+        const double num = rAB ? d1 : rAC ? d2 : rBC ? e43 : 1.0;
+        const double den = rAB ? (d1 - d3) : rAC ? (d2 - d6) : rBC ? (e43 + e56) : rIN ? ((va + vb) + vc) : 1.0;
+        const double r = num / den;
+        // edge regions: base + r * dir; interior: (a + ab * v) + ac * w with v = vb * r, w = vc * r
+        const double bsx = rBC ? bx : ax, bsy = rBC ? by : ay, bsz = rBC ? bz : az;
+        const double drx = rAB ? abx : rAC ? acx : (cx - bx), dry = rAB ? aby : rAC ? acy : (cy - by), drz = rAB ? abz : rAC ? acz : (cz - bz);
+        const double v = vb * r, w = vc * r;
+        const double c1 = rIN ? v : r;
+        const double ux = rIN ? abx : drx, uy = rIN ? aby : dry, uz = rIN ? abz : drz;
+        double qx = bsx + c1 * ux, qy = bsy + c1 * uy, qz = bsz + c1 * uz;  // a + v * ab  ==  ax + abx * v
+        if (rIN) { qx = qx + acx * w; qy = qy + acy * w; qz = qz + acz * w; }
+        if (rA) { qx = ax; qy = ay; qz = az; }
+        if (rB) { qx = bx; qy = by; qz = bz; }
+        if (rC) { qx = cx; qy = cy; qz = cz; }
         const double ex = px - qx, ey = py - qy, ez = pz - qz;
         return (ex * ex + ey * ey) + ez * ez;
     }
-    // One pass over the faces.  Record layout (kMeshStride doubles per face): a, b, c (9) and rmax = the largest distance
-    // from vertex a to a point of the face, max(|ab|, |ac|), padded upwards on the host.  By the triangle inequality every
-    // point of the face is at least |a - q| - rmax away from q, so when that bound (with a 1e-12 relative margin, four
-    // orders above the rounding of the quantities involved) exceeds the best squared distance so far the face cannot
-    // lower the minimum and its closest-point computation is skipped: a conservative prune, the minimum is unchanged
-    // bit for bit (the oracle takes the plain minimum over all faces).  Skipped only when every lane of the warp agrees.
-    static __device__ __forceinline__ double sdf(const ShapeParams &S, double qx, double qy) {
-        const double PI = 3.14159265358979323846;
-        const double qz = 0.0;
-        double omega = 0.0, best = __longlong_as_double(0x7ff0000000000000LL);
-        const double *t = S.mesh_tri;
+    // Nearest-first descent over the hierarchy's child boxes with an explicit stack of (node, lower bound).  A subtree or a
+    // face is skipped only if its bound exceeds the best squared distance so far by more than a 1e-12 relative margin (four
+    // orders above the rounding of the bound): conservative, so the minimum over the visited faces is the minimum over ALL
+    // faces, bit for bit (the oracle takes the plain minimum).
+    static __device__ __noinline__ double closest_sqr_distance(const ShapeParams &S, double qx, double qy) {
+        constexpr int kStack = 3 * kFwnMaxDepth + 4;
+        int st_node[kStack];
+        double st_lb[kStack];
+        int top = 0;
+        double best = __longlong_as_double(0x7ff0000000000000LL);
+        st_node[0] = 0; st_lb[0] = 0.0; top = 1;
+        while (top > 0) {
+            --top;
+            const int node = st_node[top];
+            if (st_lb[top] > best * (1.0 + 1e-12)) continue;
+            double lb[4];
+            unsigned ch[4];
+            int order[4] = {0, 1, 2, 3};
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                ch[s] = __ldg(S.fwn_child + 4 * (size_t)node + s);
+                lb[s] = (ch[s] == 0xffffffffu) ? __longlong_as_double(0x7ff0000000000000LL) : box_lb2(S.fwn_cbox + 24 * (size_t)node + 6 * s, qx, qy);
+            }
+            // sort the four slots by bound, farthest first (5-comparator network): the nearest is pushed last, popped first
+#define SVSDF_CSWAP(a, b) if (lb[order[a]] < lb[order[b]]) { const int t_ = order[a]; order[a] = order[b]; order[b] = t_; }
+            SVSDF_CSWAP(0, 1) SVSDF_CSWAP(2, 3) SVSDF_CSWAP(0, 2) SVSDF_CSWAP(1, 3) SVSDF_CSWAP(1, 2)
+#undef SVSDF_CSWAP
+            // faces first (they tighten the bound before anything is pushed)
 #pragma unroll 1
-        for (int f = 0; f < S.mesh_nf; ++f, t += kMeshStride) {
-            const double ax = __ldg(t), ay = __ldg(t + 1), az = __ldg(t + 2);
-            const double bx = __ldg(t + 3), by = __ldg(t + 4), bz = __ldg(t + 5);
-            const double cx = __ldg(t + 6), cy = __ldg(t + 7), cz = __ldg(t + 8);
-            const double rmax = __ldg(t + 9);
-            const double rax = ax - qx, ray = ay - qy, raz = az - qz;
-            omega += solid_angle(rax, ray, raz, bx - qx, by - qy, bz - qz, cx - qx, cy - qy, cz - qz);
-            const double lb = sqrt((rax * rax + ray * ray) + raz * raz) - rmax;  // lower bound of the distance to the face
-            const bool need = !(lb > 0.0 && lb * lb > best * (1.0 + 1e-12));
-            if (__any_sync(__activemask(), need)) {
-                const double d = sqr_distance(ax, ay, az, bx, by, bz, cx, cy, cz, qx, qy, qz);
-                if (d < best) best = d;
+            for (int k = 3; k >= 0; --k) {
+                const int s = order[k];
+                const unsigned c = ch[s];
+                if ((c & 0x80000000u) || lb[s] > best * (1.0 + 1e-12)) continue;
+                const double *t = S.mesh_tri + (size_t)c * kMeshStride;
+                const double2 v0 = __ldg(reinterpret_cast<const double2 *>(t)), v1 = __ldg(reinterpret_cast<const double2 *>(t) + 1),
+                              v2 = __ldg(reinterpret_cast<const double2 *>(t) + 2), v3 = __ldg(reinterpret_cast<const double2 *>(t) + 3);
+                const double cz = __ldg(t + 8);
+                const double dd = sqr_distance(v0.x, v0.y, v1.x, v1.y, v2.x, v2.y, v3.x, v3.y, cz, qx, qy, 0.0);
+                if (dd < best) best = dd;
+            }
+#pragma unroll 1
+            for (int k = 0; k < 4; ++k) {
+                const int s = order[k];
+                const unsigned c = ch[s];
+                if (c == 0xffffffffu || !(c & 0x80000000u) || lb[s] > best * (1.0 + 1e-12)) continue;
+                if (top < kStack) { st_node[top] = (int)(c & 0x7fffffffu); st_lb[top] = lb[s]; ++top; }
             }
         }
-        const double w = omega / (4.0 * PI);
+        return best;
+    }
+    static __device__ __forceinline__ double sdf(const ShapeParams &S, double qx, double qy) {
+        const double PI = 3.1415926535897932384626433832795;  // igl::PI
+        const float omega = fwn_solid_angle(S, (float)qx, (float)qy, 0.0f);
+        const double w = (double)omega / (4.0 * PI);
+        const double best = closest_sqr_distance(S, qx, qy);
         const double s = 1. - 2. * w;
         return s * sqrt(best);
     }

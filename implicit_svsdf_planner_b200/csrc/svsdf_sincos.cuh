@@ -138,5 +138,75 @@ __device__ __forceinline__ double atan2_portable(double y, double x) {
     }
 }
 
+// ---- single precision (the mesh functor's winding number is a FLOAT computation in the reference) -----------------------
+// Explicit round-to-nearest intrinsics: never contracted into FMAs, in either build.
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+// glibc's atanf / atan2f (fdlibm s_atanf.c / e_atan2f.c; "huge" threshold 2^25) — the same code as
+// host/fwn_bvh.hpp: atanf_portable / atan2f_portable, which tests compare with the C library bit for bit.
+__device__ __forceinline__ float atanf_portable(float x) {
+    const float hi[4] = {4.6364760399e-01f, 7.8539812565e-01f, 9.8279368877e-01f, 1.5707962513e+00f};
+    const float lo[4] = {5.0121582440e-09f, 3.7748947079e-08f, 3.4473217170e-08f, 7.5497894159e-08f};
+    const int hx = __float_as_int(x), ix = hx & 0x7fffffff;
+    int id;
+    if (ix >= 0x4c000000) {
+        if (ix > 0x7f800000) return fadd(x, x);
+        return hx > 0 ? fadd(hi[3], lo[3]) : fsub(-hi[3], lo[3]);
+    }
+    if (ix < 0x3ee00000) {
+        if (ix < 0x31000000) return x;
+        id = -1;
+    } else {
+        x = fabsf(x);
+        if (ix < 0x3f980000) {
+            if (ix < 0x3f300000) { id = 0; x = fdiv(fsub(fmul(2.0f, x), 1.0f), fadd(2.0f, x)); }
+            else { id = 1; x = fdiv(fsub(x, 1.0f), fadd(x, 1.0f)); }
+        } else {
+            if (ix < 0x401c0000) { id = 2; x = fdiv(fsub(x, 1.5f), fadd(1.0f, fmul(1.5f, x))); }
+            else { id = 3; x = fdiv(-1.0f, x); }
+        }
+    }
+    const float z = fmul(x, x), w = fmul(z, z);
+    float s1 = 1.6285819933e-02f;
+    s1 = fadd(4.9768779427e-02f, fmul(w, s1));
+    s1 = fadd(6.6610731184e-02f, fmul(w, s1));
+    s1 = fadd(9.0908870101e-02f, fmul(w, s1));
+    s1 = fadd(1.4285714924e-01f, fmul(w, s1));
+    s1 = fmul(z, fadd(3.3333334327e-01f, fmul(w, s1)));
+    float s2 = -3.6531571299e-02f;
+    s2 = fadd(-5.8335702866e-02f, fmul(w, s2));
+    s2 = fadd(-7.6918758452e-02f, fmul(w, s2));
+    s2 = fadd(-1.1111110449e-01f, fmul(w, s2));
+    s2 = fmul(w, fadd(-2.0000000298e-01f, fmul(w, s2)));
+    if (id < 0) return fsub(x, fmul(x, fadd(s1, s2)));
+    const float h = (id == 0) ? hi[0] : (id == 1) ? hi[1] : (id == 2) ? hi[2] : hi[3];
+    const float l = (id == 0) ? lo[0] : (id == 1) ? lo[1] : (id == 2) ? lo[2] : lo[3];
+    const float r = fsub(h, fsub(fsub(fmul(x, fadd(s1, s2)), l), x));
+    return hx < 0 ? -r : r;
+}
+__device__ __forceinline__ float atan2f_portable(float y, float x) {
+    const float pi_o_2 = 1.5707963705e+00f, pi = 3.1415927410e+00f, pi_lo = -8.7422776573e-08f;
+    const int hx = __float_as_int(x), ix = hx & 0x7fffffff, hy = __float_as_int(y), iy = hy & 0x7fffffff;
+    if (ix >= 0x7f800000 || iy >= 0x7f800000) return ::atan2f(y, x);  // inf / nan: not reached by the solid-angle code
+    if (hx == 0x3f800000) return atanf_portable(y);
+    const int m = ((hy >> 31) & 1) | ((hx >> 30) & 2);
+    if (iy == 0) return (m < 2) ? y : (m == 2 ? pi : -pi);
+    if (ix == 0) return hy < 0 ? -pi_o_2 : pi_o_2;
+    const int k = (iy - ix) >> 23;
+    float z;
+    if (k > 60) z = fadd(pi_o_2, fmul(0.5f, pi_lo));
+    else if (hx < 0 && k < -60) z = 0.0f;
+    else z = atanf_portable(fabsf(fdiv(y, x)));
+    switch (m) {
+        case 0: return z;
+        case 1: return -z;
+        case 2: return fsub(pi, fsub(z, pi_lo));
+        default: return fsub(fsub(z, pi_lo), pi);
+    }
+}
+
 }  // namespace dev
 }  // namespace svsdf

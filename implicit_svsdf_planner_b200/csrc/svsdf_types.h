@@ -38,7 +38,8 @@ enum ShapeId : int {
 
 constexpr int kMaxPolyEdges = 64;
 constexpr int kMeshStride = 10;          // doubles per face record: a, b, c, rmax (see ShapeFn<SH_MESH>)
-constexpr int kMaxMeshFaces = 1 << 20;  // SH_MESH: faces of the triangle soup (brute-force functor; see svsdf_shapes.cuh)
+constexpr int kMaxMeshFaces = 1 << 20;  // SH_MESH: faces of the triangle soup
+constexpr int kFwnMaxDepth = 24;        // SH_MESH: deepest hierarchy the device traversal's explicit stack holds (svsdf_create checks)
 constexpr int kMaxPieces = 64;       // pieces per trajectory supported by the per-warp accumulators
 constexpr int kWarpsPerBlock = 8;    // k_outer block = 256 threads
 constexpr int kGsipWarps = 22;       // k_gsip block = 704 threads: one warp per ring sample (<= 21 per round)
@@ -57,12 +58,21 @@ struct ShapeParams {
     double rout;        // conservative circumradius about the body origin (incl. |trans|): sdf(q) >= |q| - rout for every q.
                         // Lets choiceTInit's layer-1 scan skip lattice samples that provably cannot be the minimum
                         // (thread_choice_t_init).  >= 1e30 disables the pruning (mesh functor).
+    double prune_scale, prune_rmin;  // generalisation for functors that are only approximately distances far away (mesh: the float
+                        // winding number w scales the distance by 1 - 2w): sdf(q) >= (|q| - rout) / prune_scale for |q| >= prune_rmin.
+                        // Analytic shapes: 1 and 0.
     int poly_n;         // Polygon edge count
     int pad_;
     double poly_sx[kMaxPolyEdges], poly_sy[kMaxPolyEdges], poly_ex[kMaxPolyEdges], poly_ey[kMaxPolyEdges];
     const double *mesh_tri;  // SH_MESH: device pointer, kMeshStride doubles per face (a, b, c, rmax), vertices already R v + trans (Shape.hpp:296-302)
     int mesh_nf;
-    int pad2_;
+    int fwn_nn;              // SH_MESH: nodes of the 4-way winding-number hierarchy (host/fwn_bvh.hpp), 0 = none
+    // device copies of FwnBvh's arrays: child words [nn][4]; expansion rows [nn][23] float4 (one lane per child); child boxes
+    // [nn][4][6] float, rounded OUTWARDS by two ulps so that they contain the double vertices; leaf triangles in float [nf][12]
+    const unsigned int *fwn_child;
+    const float *fwn_data;
+    const float *fwn_cbox;
+    const float *fwn_trif;
 };
 
 // Trajectory blob: one contiguous, 16-byte aligned buffer that the kernels pull into shared memory with a

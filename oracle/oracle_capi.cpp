@@ -50,6 +50,14 @@ void orc_atan2(int64_t n, const double *y, const double *x, double *out) {
     for (int64_t i = 0; i < n; ++i) out[i] = psc::atan2(y[i], x[i]);
 }
 
+// atan2f: the pinned fdlibm code the winding-number traversal uses (host and device) beside the C library's
+void orc_atan2f_pair(int64_t n, const float *y, const float *x, float *out_portable, float *out_libm) {
+    for (int64_t i = 0; i < n; ++i) {
+        out_portable[i] = svsdf::host::FwnBvh::atan2f_portable(y[i], x[i]);
+        out_libm[i] = ::atan2f(y[i], x[i]);
+    }
+}
+
 // ---- triangle-mesh functor (BasicShape::getonlySDF_igl, Shape.hpp:332-340); V: nv x 3 row-major, F: nf x 3 ----
 static Shape make_mesh_shape(const double *poly_params, const double *V, int nv, const int *F, int nf) {
     Shape S;
@@ -58,7 +66,8 @@ static Shape make_mesh_shape(const double *poly_params, const double *V, int nv,
     S.set_mesh(V, nv, F, nf);
     return S;
 }
-// what: 0 sdf, 1 winding number, 2 squared distance, 3 FD gradient (out has 3 doubles per point)
+// what: 0 sdf, 1 winding number (the reference's float hierarchy), 2 squared distance, 3 FD gradient (out has 3 doubles per
+// point), 4 exact winding number (double sum over all faces), 5 sdf with the exact winding number
 void orc_mesh_eval(const double *poly_params, const double *V, int nv, const int *F, int nf, int what, int64_t n,
                    const double *rel, double *out) {
     Shape S = make_mesh_shape(poly_params, V, nv, F, nf);
@@ -68,6 +77,8 @@ void orc_mesh_eval(const double *poly_params, const double *V, int nv, const int
         if (what == 0) out[i] = shape_sdf(S, x, y, z);
         else if (what == 1) out[i] = mesh_winding(S, x, y, z);
         else if (what == 2) out[i] = mesh_sqr_distance(S, x, y, z);
+        else if (what == 4) out[i] = mesh_winding_exact(S, x, y, z);
+        else if (what == 5) out[i] = sd_mesh_exact(S, x, y, z);
         else shape_grad1(S, x, y, z, out + 3 * i);
     }
 }

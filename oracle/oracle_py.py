@@ -127,14 +127,25 @@ def _mesh_args(mesh):
 
 
 def mesh_eval(mesh, rel, what="sdf", poly_params=(0.0, 0.0, 0.0)):
-    """BasicShape::getonlySDF_igl restatement over body-frame points; what in sdf | winding | sqr_distance | grad1."""
+    """BasicShape::getonlySDF_igl restatement over body-frame points; what in sdf | winding | sqr_distance | grad1 (as the
+    reference computes them: float winding-number hierarchy) | winding_exact | sdf_exact (exact double sum over the faces)."""
     V, F = _mesh_args(mesh)
     rel = _f64(rel).reshape(-1, 3)
-    code = {"sdf": 0, "winding": 1, "sqr_distance": 2, "grad1": 3}[what]
+    code = {"sdf": 0, "winding": 1, "sqr_distance": 2, "grad1": 3, "winding_exact": 4, "sdf_exact": 5}[what]
     out = np.empty((rel.shape[0], 3)) if code == 3 else np.empty(rel.shape[0])
     pp = _f64(poly_params)
     lib().orc_mesh_eval(_p(pp), _p(V), V.shape[0], F.ctypes.data_as(C.c_void_p), F.shape[0], code, rel.shape[0], _p(rel), _p(out))
     return out
+
+
+def atan2f_pair(y, x):
+    """(pinned fdlibm atan2f, C library atan2f) on float32 arrays."""
+    y = np.ascontiguousarray(y, dtype=np.float32)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    a, b = np.empty_like(y), np.empty_like(y)
+    fp = C.POINTER(C.c_float)
+    lib().orc_atan2f_pair(C.c_int64(y.size), y.ctypes.data_as(fp), x.ctypes.data_as(fp), a.ctypes.data_as(fp), b.ctypes.data_as(fp))
+    return a, b
 
 
 def _u8p(a):

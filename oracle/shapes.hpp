@@ -18,6 +18,14 @@
 #include <vector>
 
 #include "portable_sincos.hpp"
+// The mesh functor's winding number is the reference's single-precision 4-way hierarchy with order-2 expansions.  That
+// hierarchy (SAH build, 23 coefficient rows per node, traversal) is restated ONCE in this repository, in the product's host
+// header below, and pinned there node by node / coefficient by coefficient / query by query against the reference's own
+// code compiled into oracle/_ref/libref_fwn.so (tests/test_oracle_mesh.py) and against tests/golden/fwn_ref.npz; the oracle
+// uses that host code (recursive traversal) as the checker of the device's explicit-stack traversal.
+#include <memory>
+
+#include "../implicit_svsdf_planner_b200/csrc/host/fwn_bvh.hpp"
 
 namespace oracle {
 
@@ -67,6 +75,7 @@ struct Shape {
     // triangle soup of the mesh functor: 9 doubles per face (a, b, c), vertices already moved by the base-class
     // constructor's R v + trans (Shape.hpp:287-302)
     std::vector<double> mesh_tri;
+    std::shared_ptr<svsdf::host::FwnBvh> fwn;  // igl::FastWindingNumberBVH of the transformed mesh (Shape.hpp:303-309)
 
     void set_poly_params(double p0, double p1, double p2_deg) {
         const double PI = 3.14159265358979323846;  // Shape.hpp:31
@@ -94,14 +103,17 @@ struct Shape {
     // BasicShape ctor, Shape.hpp:285-309: V <- hnormalized(homogeneous(V) * Trans^T), i.e. R v + trans per vertex;
     // V: nv x 3 row-major, F: nf x 3 (0-based)
     void set_mesh(const double *V, int nv, const int *F, int nf) {
+        std::vector<double> Vt((size_t)nv * 3);
+        for (int i = 0; i < nv; ++i) {
+            const double *v = V + 3 * (size_t)i;
+            for (int j = 0; j < 3; ++j) Vt[3 * (size_t)i + j] = ((v[0] * Rot[j][0] + v[1] * Rot[j][1]) + v[2] * Rot[j][2]) + trans[j];
+        }
         mesh_tri.assign((size_t)nf * 9, 0.0);
         for (int f = 0; f < nf; ++f)
-            for (int k = 0; k < 3; ++k) {
-                const double *v = V + 3 * (size_t)F[3 * f + k];
-                (void)nv;
-                for (int j = 0; j < 3; ++j)
-                    mesh_tri[(size_t)f * 9 + 3 * k + j] = ((v[0] * Rot[j][0] + v[1] * Rot[j][1]) + v[2] * Rot[j][2]) + trans[j];
-            }
+            for (int k = 0; k < 3; ++k)
+                for (int j = 0; j < 3; ++j) mesh_tri[(size_t)f * 9 + 3 * k + j] = Vt[3 * (size_t)F[3 * f + k] + j];
+        fwn = std::make_shared<svsdf::host::FwnBvh>();
+        fwn->build(Vt.data(), nv, F, nf);  // igl::fast_winding_number(V.cast<float>(), F, 2, fwn_bvh), Shape.hpp:306-308
     }
     void set_default_rect() {  // sw_manager.hpp:365-369
         const double rect[8] = {6, -0.1, 6, 0.1, -6, 0.1, -6, -0.1};
@@ -375,13 +387,12 @@ inline double sd_polygon(const Shape &S, double qx, double qy) {
 // ---- Triangle-mesh functor: BasicShape::getonlySDF_igl, Shape.hpp:332-340 ----
 //   sdf = (1 - 2 w) * sqrt(d2),  w = winding number of the mesh about the point, d2 = squared distance to the mesh.
 // The reference gets w from igl::fast_winding_number (fast_winding_number.cpp:439-457 -> HDK UT_SolidAngle<float,float>,
-// a float BVH whose leaves evaluate the exact per-triangle solid angle, UTsignedSolidAngleTri
-// FastWindingNumberForSoups.h:6071-6110, and whose far clusters use an order-2 Taylor approximation of the same sum) and
-// d2 from igl::AABB::squared_distance (AABB.cpp:1130-1200 -> point_simplex_squared_distance.cpp:43-116, Ericson's
-// closest point on a triangle).  Restated here as the quantities those trees approximate/accelerate: the exact
-// double-precision sum of per-triangle solid angles (same formula as the reference's leaf evaluation) and the minimum of
-// the per-triangle squared distances (the same number the AABB tree returns — pruning does not change a minimum).
-// tests/test_oracle_mesh.py measures the difference to the reference's own float FWN code compiled into oracle/_ref.
+// a float hierarchy whose leaves evaluate the per-triangle solid angle, UTsignedSolidAngleTri
+// FastWindingNumberForSoups.h:6071-6110, and whose far clusters use an order-2 Taylor approximation of the same sum): a
+// SINGLE-precision approximation, 2e-3 off the exact value on the reference's meshes, reproduced here through the shared host
+// hierarchy (mesh_winding); the exact double sum is kept as mesh_winding_exact for the closed-form tests.  d2 comes from
+// igl::AABB::squared_distance (AABB.cpp:1130-1200 -> point_simplex_squared_distance.cpp:43-116, Ericson's closest point
+// on a triangle), restated as the plain minimum of the per-triangle squared distances (pruning does not change a minimum).
 inline double tri_solid_angle(const double *t, double qx, double qy, double qz) {
     double ax = t[0] - qx, ay = t[1] - qy, az = t[2] - qz;
     double bx = t[3] - qx, by = t[4] - qy, bz = t[5] - qz;
@@ -458,7 +469,13 @@ inline double tri_sqr_distance(const double *t, double px, double py, double pz)
     const double ex = px - qx, ey = py - qy, ez = pz - qz;
     return (ex * ex + ey * ey) + ez * ez;
 }
+// what the reference computes: the float hierarchy, accuracy_scale 2 (Shape.hpp:337)
 inline double mesh_winding(const Shape &S, double qx, double qy, double qz) {
+    const double p[3] = {qx, qy, qz};
+    return S.fwn->winding_number(p, 2.0f);
+}
+// the quantity that hierarchy approximates: the exact double-precision sum over all faces (kept for the known-answer tests)
+inline double mesh_winding_exact(const Shape &S, double qx, double qy, double qz) {
     const double PI = 3.14159265358979323846;
     double omega = 0.0;
     const size_t nf = S.mesh_tri.size() / 9;
@@ -476,6 +493,12 @@ inline double mesh_sqr_distance(const Shape &S, double qx, double qy, double qz)
 }
 inline double sd_mesh(const Shape &S, double qx, double qy, double qz) {
     const double w = mesh_winding(S, qx, qy, qz);
+    const double s = 1. - 2. * w;
+    return s * std::sqrt(mesh_sqr_distance(S, qx, qy, qz));
+}
+
+inline double sd_mesh_exact(const Shape &S, double qx, double qy, double qz) {
+    const double w = mesh_winding_exact(S, qx, qy, qz);
     const double s = 1. - 2. * w;
     return s * std::sqrt(mesh_sqr_distance(S, qx, qy, qz));
 }

@@ -8,7 +8,10 @@ Runs in the build container only (needs /root/reference):  python tests/golden/m
      BasicShape's constructor does (order 2, Shape.hpp:312) and queried exactly as getonlySDF_igl does (accuracy_scale 2.0,
      Shape.hpp:337) at seeded points in the z = 0 plane (where the planner queries) and in 3-D.
   3. Inputs (V, F, Q) and the reference's outputs (w_ref) go to tests/golden/fwn_ref.npz.
-tests/test_oracle_mesh.py compares the oracle's exact winding number with w_ref (the reference's value is a float,
+  4. The hierarchy the reference built is dumped too (oracle/ref_fwn_shim.cpp: ref_fwn_dump): the child words of every node
+     and its 23 rows of expansion coefficients (tree_children, tree_data).
+tests/test_oracle_mesh.py requires the repo's own host builder (csrc/host/fwn_bvh.hpp) to reproduce tree, coefficients and
+w_ref BIT FOR BIT, and compares the exact double-precision winding number with w_ref (the reference's value is a float,
 order-2 approximation: the observed difference, <= 2.1e-3, is its approximation error — the exact value is an integer to
 1e-15 on these closed meshes).
 """
@@ -44,6 +47,26 @@ def ref_fwn(V, F, Q, order=2, accuracy=2.0):
     return w
 
 
+def ref_fwn_tree(V, F, order=2):
+    """(children [nn, 4] uint32, data [nn, 23, 4] float32) of the hierarchy the reference builds."""
+    dp = C.POINTER(C.c_double)
+    L = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_fwn.so"))
+    L.ref_fwn_create.restype = C.c_void_p
+    L.ref_fwn_create.argtypes = [dp, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    L.ref_fwn_num_nodes.argtypes = [C.c_void_p]
+    L.ref_fwn_dump.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.ref_fwn_destroy.argtypes = [C.c_void_p]
+    V = np.ascontiguousarray(V, dtype=np.float64)
+    F = np.ascontiguousarray(F, dtype=np.int32)
+    h = L.ref_fwn_create(V.ctypes.data_as(dp), V.shape[0], F.ctypes.data_as(C.c_void_p), F.shape[0], order)
+    nn = L.ref_fwn_num_nodes(h)
+    ch = np.zeros((nn, 4), np.uint32)
+    data = np.zeros((nn, 23, 4), np.float32)
+    L.ref_fwn_dump(h, ch.ctypes.data_as(C.c_void_p), data.ctypes.data_as(C.c_void_p))
+    L.ref_fwn_destroy(h)
+    return ch, data
+
+
 def main():
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"])
     rng = np.random.Generator(np.random.MT19937(20240511))
@@ -56,6 +79,7 @@ def main():
         Q[2000:] = rng.uniform(lo, hi, size=(1000, 3))
         out[name + "_V"], out[name + "_F"], out[name + "_Q"] = V, F, Q
         out[name + "_w_ref"] = ref_fwn(V, F, Q)
+        out[name + "_tree_children"], out[name + "_tree_data"] = ref_fwn_tree(V, F)
     np.savez_compressed(os.path.join(HERE, "fwn_ref.npz"), **out)
     for k, v in out.items():
         print(k, v.shape, v.dtype)

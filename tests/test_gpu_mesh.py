@@ -2,11 +2,12 @@
 Shape.hpp:332-340) through the C ABI: svsdf_config.mesh_* selects it, everything downstream (outer solve, GSIP branch,
 cost + gradient, callback, optimiser) is the same code as for the analytic shapes.
 
-Parity statement: the strict build performs, per face, the same IEEE operations in the same order as the oracle
-(oracle/shapes.hpp: exact solid-angle sum + Ericson closest point), so the functor value, its FD gradient and every
-per-point result of the outer solve are BIT-IDENTICAL; sums differ by summation order only.  How far that exact functor
-is from the reference's float fast-winding-number evaluation is pinned on the CPU side (tests/test_oracle_mesh.py,
-tests/golden/fwn_ref.npz)."""
+Parity statement: the winding number is the reference's SINGLE-precision 4-way hierarchy with order-2 expansions; the host
+builds it (csrc/host/fwn_bvh.hpp, bitwise the reference's tree and coefficients — tests/test_oracle_mesh.py) and the device
+walks it with an explicit stack in the recursion's summation order, every float operation an un-fused *_rn intrinsic: the
+value equals the reference's own compiled code BIT FOR BIT (tests/golden/fwn_ref.npz).  The closest-triangle distance is the
+plain double minimum (box-pruned over the same tree).  Hence the functor value, its FD gradient and every per-point result
+of the outer solve are BIT-IDENTICAL to the oracle's; sums differ by summation order only."""
 import os
 
 import numpy as np
@@ -50,6 +51,27 @@ def test_mesh_functor_is_bitwise_the_oracles(oracle_mod, which):
     # FMA-contracted build: same function to rounding
     ctx = api.Context("ignored", strict_fp=False, mesh=m)
     assert np.abs(ctx.shape_sdf(rel) - oracle_mod.mesh_eval(m, rel, "sdf")).max() < 1e-12
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", ["star", "sdHorseshoe"])
+def test_device_winding_number_is_bitwise_the_reference_golden(oracle_mod, name):
+    """(1 - 2 w_ref) sqrt(d2) with w_ref from the REFERENCE's own compiled igl/HDK code on its own shapes/*.obj: the device
+    functor returns exactly that, in both builds (the float traversal never contracts)."""
+    g = np.load(os.path.join(HERE, "golden", "fwn_ref.npz"))
+    m = (g[name + "_V"], g[name + "_F"])
+    Q, w_ref = g[name + "_Q"][:2000], g[name + "_w_ref"][:2000]  # the z = 0 queries (the plane the planner evaluates in)
+    assert np.all(Q[:, 2] == 0.0)
+    d2 = oracle_mod.mesh_eval(m, Q, "sqr_distance")
+    want = (1.0 - 2.0 * w_ref) * np.sqrt(d2)
+    ctx = api.Context("ignored", strict_fp=True, mesh=m)
+    got = ctx.shape_sdf(Q)
+    assert np.array_equal(got, want), int((got != want).sum())
+    ctx.close()
+    ctx = api.Context("ignored", strict_fp=False, mesh=m)
+    got = ctx.shape_sdf(Q)
+    w_back = (1.0 - got / np.sqrt(d2)) / 2.0
+    assert np.abs(w_back - w_ref).max() < 1e-12  # same float w; only the double distance may contract
     ctx.close()
 
 
