@@ -973,6 +973,9 @@ __global__ void k_pose_table(double *blob) {
 #ifndef SVSDF_ENGINE_ILP
 #define SVSDF_ENGINE_ILP 2   // samples per lane and round in the batched descent (1: descent_engine, 2: descent_engine2)
 #endif
+#ifndef SVSDF_MESH_MIN_CTAS
+#define SVSDF_MESH_MIN_CTAS 4  // measured on config 4m: 2 -> 245 ms, 3 -> 206 ms, 4 -> 198 ms (the traversal is latency bound; spills stay in L1)
+#endif
 #ifndef SVSDF_OUTER_MIN_CTAS
 #define SVSDF_OUTER_MIN_CTAS 3
 #endif
@@ -981,7 +984,7 @@ __global__ void k_pose_table(double *blob) {
 #endif
 // BATCHED selects the schedule at compile time (two kernels: each carries only its own evaluation sites)
 template <int SHAPE, bool XFORM, bool BATCHED>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, (SHAPE == SH_MESH) ? 2 : SVSDF_OUTER_MIN_CTAS)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, (SHAPE == SH_MESH) ? SVSDF_MESH_MIN_CTAS : SVSDF_OUTER_MIN_CTAS)
     k_outer(const __grid_constant__ KernelArgs A, const __grid_constant__ ShapeParams S) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t bar;

@@ -934,12 +934,27 @@ int svsdf_create(const svsdf_config *cfg, svsdf_ctx **out) {
             svsdf_destroy(ctx);
             return SVSDF_ERR_INVALID;
         }
-        std::vector<float> cb(B.cbox);
-        for (size_t k = 0; k < cb.size(); ++k) {  // outwards by two ulps: the float boxes then contain the double vertices
-            const bool is_min = (k % 6) < 3;
-            const float dir = is_min ? -std::numeric_limits<float>::infinity() : std::numeric_limits<float>::infinity();
-            if (std::isfinite(cb[k])) cb[k] = std::nextafter(std::nextafter(cb[k], dir), dir);
+        // child boxes for the closest-triangle descent: lo x, lo y, hi x, hi y two ulps outwards (the float boxes then contain
+        // the double vertices), squared z gap to the query plane z = 0 rounded down, pad
+        std::vector<float> cb(B.cbox.size(), 0.0f);
+        float boxmag = 0.0f;
+        {
+            const float ninf = -std::numeric_limits<float>::infinity(), pinf = std::numeric_limits<float>::infinity();
+            auto out = [&](float v, float dir) { return std::isfinite(v) ? std::nextafter(std::nextafter(v, dir), dir) : v; };
+            for (size_t k = 0; k + 5 < cb.size(); k += 6) {
+                const float *b = &B.cbox[k];  // min xyz, max xyz
+                const float lox = out(b[0], ninf), loy = out(b[1], ninf), loz = out(b[2], ninf), hix = out(b[3], pinf), hiy = out(b[4], pinf),
+                            hiz = out(b[5], pinf);
+                cb[k] = lox; cb[k + 1] = loy; cb[k + 2] = hix; cb[k + 3] = hiy;
+                const double gz = std::max(std::max((double)loz, -(double)hiz), 0.0);
+                float dz2 = (float)(gz * gz);
+                if ((double)dz2 > gz * gz) dz2 = std::nextafter(dz2, 0.0f);
+                cb[k + 4] = std::isfinite(dz2) ? dz2 : 0.0f;
+                for (int j = 0; j < 4; ++j)
+                    if (std::isfinite(cb[k + j])) boxmag = std::max(boxmag, std::fabs(cb[k + j]));
+            }
         }
+        ctx->shape.fwn_boxmag = boxmag;
         std::vector<float> tf((size_t)cfg->mesh_nf * 12, 0.0f);
         for (int f = 0; f < cfg->mesh_nf; ++f)
             for (int k = 0; k < 3; ++k)

@@ -491,14 +491,17 @@ struct ShapeFn<SH_MESH> {
             have_ret = true;
         }
     }
-    // lower bound of the squared distance from (qx, qy, 0) to a child box (6 floats: min xyz, max xyz)
-    static __device__ __forceinline__ double box_lb2(const float *b, double qx, double qy) {
-        const float2 b01 = __ldg(reinterpret_cast<const float2 *>(b)), b23 = __ldg(reinterpret_cast<const float2 *>(b) + 1),
-                     b45 = __ldg(reinterpret_cast<const float2 *>(b) + 2);
-        const double dx = fmax(fmax((double)b01.x - qx, qx - (double)b23.y), 0.0);
-        const double dy = fmax(fmax((double)b01.y - qy, qy - (double)b45.x), 0.0);
-        const double dz = fmax(fmax((double)b23.x, -(double)b45.y), 0.0);
-        return (dx * dx + dy * dy) + dz * dz;
+    // Single-precision LOWER bound of the squared distance from (qx, qy, 0) to a child box.  Record (6 floats, built on the
+    // host): lo x, lo y, hi x, hi y (rounded outwards so the box contains the double vertices), dz2 = the squared z gap of the
+    // box to the plane z = 0 rounded down, pad.  qf = float(q) is off by <= 2^-24 |q| and lo - qf rounds by <= 2^-24 (|lo| + |qf|):
+    // subtracting e = 2.4e-7 (|qf| + M) (M >= every |box coordinate|; twice the worst case) makes each gap a lower bound, and the
+    // factor (1 - 4e-7) covers the five roundings of the sum of squares.
+    static __device__ __forceinline__ float box_lb2(const float *b, float qxf, float qyf, float ex, float ey) {
+        const float2 lo = __ldg(reinterpret_cast<const float2 *>(b)), hi = __ldg(reinterpret_cast<const float2 *>(b) + 1);
+        const float dz2 = __ldg(b + 4);
+        const float dx = fmaxf(fmaxf(lo.x - qxf, qxf - hi.x) - ex, 0.0f);
+        const float dy = fmaxf(fmaxf(lo.y - qyf, qyf - hi.y) - ey, 0.0f);
+        return (dx * dx + dy * dy + dz2) * 0.9999996f;
     }
     // Squared distance from p to triangle (a, b, c): ClosestBaryPtPointTriangle (point_simplex_squared_distance.cpp:43-106).
     // The reference walks the seven Voronoi regions with early returns; here the region is decided first (same conditions,
@@ -547,53 +550,66 @@ struct ShapeFn<SH_MESH> {
         const double ex = px - qx, ey = py - qy, ez = pz - qz;
         return (ex * ex + ey * ey) + ez * ez;
     }
-    // Nearest-first descent over the hierarchy's child boxes with an explicit stack of (node, lower bound).  A subtree or a
-    // face is skipped only if its bound exceeds the best squared distance so far by more than a 1e-12 relative margin (four
-    // orders above the rounding of the bound): conservative, so the minimum over the visited faces is the minimum over ALL
-    // faces, bit for bit (the oracle takes the plain minimum).
+    // Nearest-first descent over the hierarchy's child boxes.  Per node: the four children's float lower bounds; faces whose
+    // bound does not exceed the best squared distance so far are evaluated (exact, double); of the internal children that
+    // survive, the nearest is entered directly and the others go on an explicit stack of (node, bound).  A subtree or a face is
+    // skipped only if its LOWER bound exceeds best * (1 + 1e-12) rounded up to float: conservative, so the minimum over the
+    // visited faces is the minimum over ALL faces, bit for bit (the oracle takes the plain minimum).  Children are picked from
+    // registers with selects (no dynamically indexed local arrays), and sqr_distance has one call site.
+    static __device__ __forceinline__ float sel4(int s, float a, float b, float c, float d) { return s == 0 ? a : s == 1 ? b : s == 2 ? c : d; }
+    static __device__ __forceinline__ unsigned sel4(int s, unsigned a, unsigned b, unsigned c, unsigned d) { return s == 0 ? a : s == 1 ? b : s == 2 ? c : d; }
     static __device__ __noinline__ double closest_sqr_distance(const ShapeParams &S, double qx, double qy) {
         constexpr int kStack = 3 * kFwnMaxDepth + 4;
         int st_node[kStack];
-        double st_lb[kStack];
+        float st_lb[kStack];
         int top = 0;
+        const float INF = __int_as_float(0x7f800000);
+        const float qxf = (float)qx, qyf = (float)qy;
+        const float ex = 2.4e-7f * (fabsf(qxf) + S.fwn_boxmag), ey = 2.4e-7f * (fabsf(qyf) + S.fwn_boxmag);
         double best = __longlong_as_double(0x7ff0000000000000LL);
-        st_node[0] = 0; st_lb[0] = 0.0; top = 1;
-        while (top > 0) {
-            --top;
-            const int node = st_node[top];
-            if (st_lb[top] > best * (1.0 + 1e-12)) continue;
-            double lb[4];
-            unsigned ch[4];
-            int order[4] = {0, 1, 2, 3};
-#pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                ch[s] = __ldg(S.fwn_child + 4 * (size_t)node + s);
-                lb[s] = (ch[s] == 0xffffffffu) ? __longlong_as_double(0x7ff0000000000000LL) : box_lb2(S.fwn_cbox + 24 * (size_t)node + 6 * s, qx, qy);
-            }
-            // sort the four slots by bound, farthest first (5-comparator network): the nearest is pushed last, popped first
-#define SVSDF_CSWAP(a, b) if (lb[order[a]] < lb[order[b]]) { const int t_ = order[a]; order[a] = order[b]; order[b] = t_; }
-            SVSDF_CSWAP(0, 1) SVSDF_CSWAP(2, 3) SVSDF_CSWAP(0, 2) SVSDF_CSWAP(1, 3) SVSDF_CSWAP(1, 2)
-#undef SVSDF_CSWAP
-            // faces first (they tighten the bound before anything is pushed)
+        float bestf = INF;  // >= best * (1 + 1e-12)
+        int node = 0;
 #pragma unroll 1
-            for (int k = 3; k >= 0; --k) {
-                const int s = order[k];
-                const unsigned c = ch[s];
-                if ((c & 0x80000000u) || lb[s] > best * (1.0 + 1e-12)) continue;
+        for (;;) {
+            if (node < 0) {
+                if (top == 0) break;
+                --top;
+                node = st_node[top];
+                if (st_lb[top] > bestf) { node = -1; continue; }
+            }
+            const uint4 cw = __ldg(reinterpret_cast<const uint4 *>(S.fwn_child) + node);
+            const float *cb = S.fwn_cbox + 24 * (size_t)node;
+            const float l0 = box_lb2(cb, qxf, qyf, ex, ey);
+            const float l1 = (cw.y == 0xffffffffu) ? INF : box_lb2(cb + 6, qxf, qyf, ex, ey);
+            const float l2 = (cw.z == 0xffffffffu) ? INF : box_lb2(cb + 12, qxf, qyf, ex, ey);
+            const float l3 = (cw.w == 0xffffffffu) ? INF : box_lb2(cb + 18, qxf, qyf, ex, ey);
+            // faces first (they tighten the bound before anything is entered)
+#pragma unroll 1
+            for (int s = 0; s < 4; ++s) {
+                const unsigned c = sel4(s, cw.x, cw.y, cw.z, cw.w);
+                if ((c & 0x80000000u) || sel4(s, l0, l1, l2, l3) > bestf) continue;
                 const double *t = S.mesh_tri + (size_t)c * kMeshStride;
                 const double2 v0 = __ldg(reinterpret_cast<const double2 *>(t)), v1 = __ldg(reinterpret_cast<const double2 *>(t) + 1),
                               v2 = __ldg(reinterpret_cast<const double2 *>(t) + 2), v3 = __ldg(reinterpret_cast<const double2 *>(t) + 3);
                 const double cz = __ldg(t + 8);
                 const double dd = sqr_distance(v0.x, v0.y, v1.x, v1.y, v2.x, v2.y, v3.x, v3.y, cz, qx, qy, 0.0);
-                if (dd < best) best = dd;
+                if (dd < best) { best = dd; bestf = __double2float_ru(dd * (1.0 + 1e-12)); }
             }
-#pragma unroll 1
-            for (int k = 0; k < 4; ++k) {
-                const int s = order[k];
-                const unsigned c = ch[s];
-                if (c == 0xffffffffu || !(c & 0x80000000u) || lb[s] > best * (1.0 + 1e-12)) continue;
-                if (top < kStack) { st_node[top] = (int)(c & 0x7fffffffu); st_lb[top] = lb[s]; ++top; }
-            }
+            // internal children still in range: nearest next, the rest stacked
+            const bool i0 = (cw.x & 0x80000000u) && l0 <= bestf, i1 = (cw.y & 0x80000000u) && cw.y != 0xffffffffu && l1 <= bestf,
+                       i2 = (cw.z & 0x80000000u) && cw.z != 0xffffffffu && l2 <= bestf, i3 = (cw.w & 0x80000000u) && cw.w != 0xffffffffu && l3 <= bestf;
+            const float m0 = i0 ? l0 : INF, m1 = i1 ? l1 : INF, m2 = i2 ? l2 : INF, m3 = i3 ? l3 : INF;
+            int near = -1;
+            float ml = INF;
+            if (i0) { near = 0; ml = m0; }
+            if (i1 && m1 < ml) { near = 1; ml = m1; }
+            if (i2 && m2 < ml) { near = 2; ml = m2; }
+            if (i3 && m3 < ml) { near = 3; ml = m3; }
+            if (i0 && near != 0 && top < kStack) { st_node[top] = (int)(cw.x & 0x7fffffffu); st_lb[top] = l0; ++top; }
+            if (i1 && near != 1 && top < kStack) { st_node[top] = (int)(cw.y & 0x7fffffffu); st_lb[top] = l1; ++top; }
+            if (i2 && near != 2 && top < kStack) { st_node[top] = (int)(cw.z & 0x7fffffffu); st_lb[top] = l2; ++top; }
+            if (i3 && near != 3 && top < kStack) { st_node[top] = (int)(cw.w & 0x7fffffffu); st_lb[top] = l3; ++top; }
+            node = (near < 0) ? -1 : (int)(sel4(near, cw.x, cw.y, cw.z, cw.w) & 0x7fffffffu);
         }
         return best;
     }

@@ -67,8 +67,11 @@ struct ShapeParams {
     const double *mesh_tri;  // SH_MESH: device pointer, kMeshStride doubles per face (a, b, c, rmax), vertices already R v + trans (Shape.hpp:296-302)
     int mesh_nf;
     int fwn_nn;              // SH_MESH: nodes of the 4-way winding-number hierarchy (host/fwn_bvh.hpp), 0 = none
-    // device copies of FwnBvh's arrays: child words [nn][4]; expansion rows [nn][23] float4 (one lane per child); child boxes
-    // [nn][4][6] float, rounded OUTWARDS by two ulps so that they contain the double vertices; leaf triangles in float [nf][12]
+    float fwn_boxmag;        // SH_MESH: >= |every x / y coordinate of the child boxes| (error term of the float box bounds)
+    int pad3_;
+    // device copies of FwnBvh's arrays: child words [nn][4]; expansion rows [nn][23][4] float (one lane per child); child boxes
+    // [nn][4][6] float: lo x, lo y, hi x, hi y rounded OUTWARDS by two ulps (they contain the double vertices), squared z gap to
+    // the plane z = 0 rounded down, pad; leaf triangles in float [nf][12]
     const unsigned int *fwn_child;
     const float *fwn_data;
     const float *fwn_cbox;

@@ -1,47 +1,74 @@
-"""Turns the raw evidence collected by scripts/collect_profiles.sh (gpurun_out/) into the tracked summaries under profiles/."""
-import collections, csv, json, os, re, shutil, subprocess, sys
+"""Turns the raw evidence collected by scripts/collect_profiles.sh (gpurun_out/) into the tracked summaries under profiles/.
+
+    python scripts/summarise_profiles.py r2
+
+The `ncu --set full` reports (40 MB each) do not travel back from the GPU box; collect_profiles.sh exports their raw-metric,
+details and SASS-source pages as CSV there, and this script reads those (or the report itself if it is present)."""
+import collections, csv, json, os, shutil, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "gpurun_out"); Pdir = os.path.join(ROOT, "profiles")
 os.makedirs(Pdir, exist_ok=True)
-R = sys.argv[1] if len(sys.argv) > 1 else "r1"
+R = sys.argv[1] if len(sys.argv) > 1 else "r2"
+
 
 def ncu_raw(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    csv_path = rep.replace(".ncu-rep", "_raw.csv")
+    if os.path.exists(csv_path):
+        out = open(csv_path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     return dict(zip(rows[0], rows[2])), dict(zip(rows[0], rows[1]))
 
+
 def ncu_details(rep):
+    csv_path = rep.replace(".ncu-rep", "_details.csv")
+    if os.path.exists(csv_path):
+        rows = list(csv.DictReader(open(csv_path)))
+        return "\n".join(f"    {r['Metric Name']:<44s}{r['Metric Unit']:>18s}{r['Metric Value']:>14s}" for r in rows if r.get("Metric Name"))
     return subprocess.run(["ncu", "-i", rep, "--page", "details"], capture_output=True, text=True).stdout
 
-# ---- launch list ----
-lines = open(os.path.join(G, f"launches_{R}.csv")).read().split("\n")
-start = [i for i, l in enumerate(lines) if l.startswith('"ID"')][0]
-rows = list(csv.DictReader(lines[start:]))
-agg = collections.OrderedDict()
-for r in rows:
-    agg.setdefault(r["Kernel Name"].split("(")[0].replace("void ", ""), []).append(float(r["Metric Value"]))
-ours = {k: v for k, v in agg.items() if k.startswith("strict::") and "fp64_peak" not in k}
-tot = sum(sum(v) for v in ours.values())
-shutil.copy(os.path.join(G, f"launches_{R}.csv"), os.path.join(Pdir, f"{R}_launches_bench.csv"))
-bench = json.loads(open(os.path.join(G, f"bench_{R}.json")).read().strip().split("\n")[-1])
-km = bench["kernel_ms"]; kms = sum(km.values())
-with open(os.path.join(Pdir, f"{R}_launches_bench_summary.md"), "w") as f:
-    f.write(f"# {R}: ncu launch list of `python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-lbfgs`\n\n")
-    f.write("`ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_%s.csv python bench.py ...`\n" % R)
-    f.write(f"(raw: `profiles/{R}_launches_bench.csv`).  Per-launch times under ncu are cold-cache and serialised, so the SHARES are compared\n")
-    f.write("with the CUDA-event breakdown that the un-profiled `bench.py` run prints (`kernel_ms`, right column).\n\n")
-    f.write("| kernel | launches | mean µs (ncu) | share (ncu) | share (CUDA events, bench.py) |\n|---|---|---|---|---|\n")
-    ev = {"strict::k_pose_table": km["k_pose_table"], "strict::k_outer<0, 0>": km["k_outer"], "strict::k_finalize": km["k_finalize"]}
-    for k, v in agg.items():
-        if k in ours:
-            e = ev.get(k)
-            es = f"{100*e/kms:.1f} %" if e is not None else ("%.1f %% (k_compact + k_gsip)" % (100 * km["k_compact+k_gsip"] / kms) if "gsip" in k else "(with k_gsip)")
-            f.write(f"| `{k}` | {len(v)} | {sum(v)/len(v)/1e3:.1f} | {100*sum(v)/tot:.1f} % | {es} |\n")
-        else:
-            f.write(f"| `{k}` | {len(v)} | {sum(v)/len(v)/1e3:.1f} | not part of the step (L2 flush / FP64 peak micro-benchmark) | |\n")
+
+# ---- launch list of the bench command ----
+def launch_list():
+    lp, bp = os.path.join(G, f"launches_{R}.csv"), os.path.join(G, f"bench_{R}.json")
+    if not (os.path.exists(lp) and os.path.exists(bp)):
+        print("no launch list / bench record for", R)
+        return
+    lines = open(lp).read().split("\n")
+    start = [i for i, l in enumerate(lines) if l.startswith('"ID"')][0]
+    rows = list(csv.DictReader(lines[start:]))
+    agg = collections.OrderedDict()
+    for r in rows:
+        agg.setdefault(r["Kernel Name"].split("(")[0].replace("void ", ""), []).append(float(r["Metric Value"]))
+    ours = {k: v for k, v in agg.items() if k.startswith("strict::") and "fp64_peak" not in k}
+    tot = sum(sum(v) for v in ours.values())
+    shutil.copy(lp, os.path.join(Pdir, f"{R}_launches_bench.csv"))
+    bench = json.loads(open(bp).read().strip().split("\n")[-1])
+    km = bench["kernel_ms"]; kms = sum(km.values())
+    with open(os.path.join(Pdir, f"{R}_launches_bench_summary.md"), "w") as f:
+        f.write(f"# {R}: ncu launch list of `python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-lbfgs`\n\n")
+        f.write("`ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_%s.csv python bench.py ...`\n" % R)
+        f.write(f"(raw: `profiles/{R}_launches_bench.csv`).  Per-launch times under ncu are cold-cache and serialised, so the SHARES are compared\n")
+        f.write("with the CUDA-event breakdown that the un-profiled `bench.py` run prints (`kernel_ms`, right column).\n\n")
+        f.write("| kernel | launches | mean µs (ncu) | share (ncu) | share (CUDA events, bench.py) |\n|---|---|---|---|---|\n")
+        for k, v in agg.items():
+            if k in ours:
+                if "k_pose_table" in k: es = f"{100*km['k_pose_table']/kms:.1f} %"
+                elif "k_outer" in k: es = f"{100*km['k_outer']/kms:.1f} %"
+                elif "k_finalize" in k: es = f"{100*km['k_finalize']/kms:.1f} %"
+                elif "gsip" in k: es = "%.1f %% (k_compact + k_gsip)" % (100 * km["k_compact+k_gsip"] / kms)
+                else: es = "(with k_gsip)"
+                f.write(f"| `{k}` | {len(v)} | {sum(v)/len(v)/1e3:.1f} | {100*sum(v)/tot:.1f} % | {es} |\n")
+            else:
+                f.write(f"| `{k}` | {len(v)} | {sum(v)/len(v)/1e3:.1f} | not part of the step (L2 flush / FP64 peak micro-benchmark) | |\n")
+
 
 # ---- full captures ----
-def summarise(rep, name, kernel_regex):
+def summarise(rep, name, kernel_regex, workload, reading):
+    if not (os.path.exists(rep) or os.path.exists(rep.replace(".ncu-rep", "_raw.csv"))):
+        print("no capture", rep)
+        return None
     raw, units = ncu_raw(rep)
     det = ncu_details(rep)
     keep = ["Duration", "Registers Per Thread", "Theoretical Occupancy", "Achieved Occupancy", "Executed Ipc Active", "Issue Slots Busy",
@@ -58,24 +85,42 @@ def summarise(rep, name, kernel_regex):
              if k.startswith("sm__inst_executed_pipe_") and k.endswith(".avg.pct_of_peak_sustained_active") and v not in ("", "n/a") and float(v) > 0.5}
     with open(os.path.join(Pdir, f"{R}_{name}_ncu_summary.md"), "w") as f:
         f.write(f"# {R}: `ncu --set full --clock-control none --import-source on -k regex:{kernel_regex} -s 2 -c 1` of `python scripts/prof_step.py`\n\n")
-        f.write("Workload: config 2 (star, 8-piece MINCO, 200 000 query points), strict build.  Numbers under the profiler are not bench values.\n\n```\n")
+        f.write(f"Kernel: `{raw.get('Kernel Name', kernel_regex)}`.  Workload: {workload}.  Numbers under the profiler are not bench values.\n\n```\n")
         f.write("\n".join(l.rstrip() for l in lines_) + "\n```\n\n")
-        f.write(f"DRAM traffic of this launch: read {dr} {ur}, write {dw} {uw}  => {traffic/1e6:.2f} MB "
-                "(algorithmic: 3.2 MB of query points + the 7 KB trajectory blob per CTA from L2)\n\n")
-        f.write("Pipe utilisation (`sm__inst_executed_pipe_*.avg.pct_of_peak_sustained_active`, > 0.5 %): "
+        f.write(f"DRAM traffic of this launch: read {dr} {ur}, write {dw} {uw}  => {traffic/1e6:.2f} MB\n\n")
+        for k in ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+                  "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__warps_active.avg.pct_of_peak_sustained_active"):
+            if k in raw: f.write(f"* `{k}`: {raw[k]}\n")
+        f.write("\nPipe utilisation (`sm__inst_executed_pipe_*.avg.pct_of_peak_sustained_active`, > 0.5 %): "
                 + ", ".join(f"{k} {v:.1f} %" for k, v in sorted(pipes.items(), key=lambda kv: -kv[1])) + "\n\n")
         f.write("Executed warp instructions: %s\n\n" % raw.get("smsp__inst_executed.sum"))
         f.write("Top warp stall reasons (`smsp__average_warps_issue_stalled_*_per_issue_active.ratio`):\n\n")
         for v, k in stalls:
             f.write(f"* {k.split('issue_stalled_')[1].replace('_per_issue_active.ratio','')}: {v:.2f}\n")
-        f.write("\nReading: DRAM and tensor pipes are idle; the FP64 pipe and the issue slots are the busy resources (FP64-compute / latency bound,\n"
-                "as DESIGN.md §3 predicts).\n")
+        f.write("\n" + reading + "\n")
+    for ext in ("_raw.csv", "_details.csv"):
+        src = rep.replace(".ncu-rep", ext)
+        if os.path.exists(src): shutil.copy(src, os.path.join(Pdir, f"{R}_{name}{ext.replace('.csv', '_ncu.csv')}"))
     return traffic
 
-t_outer = summarise(os.path.join(G, f"prof_outer_{R}.ncu-rep"), "k_outer", "k_outer")
-summarise(os.path.join(G, f"prof_gsip_{R}.ncu-rep"), "k_gsip", "k_gsip")
-json.dump({"kernel": "k_outer", "dram_bytes_per_launch": t_outer, "source": f"profiles/{R}_k_outer_ncu_summary.md (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture)"},
-          open(os.path.join(Pdir, f"{R}_k_outer_traffic.json"), "w"), indent=1)
+
+launch_list()
+W2 = "config 2 (star, 8-piece MINCO, 200 000 query points), strict build"
+t_outer = summarise(os.path.join(G, f"prof_outer_{R}.ncu-rep"), "k_outer", "k_outer", W2,
+                    "Reading: DRAM and tensor pipes are idle.  An FP64 warp instruction occupies the issue port of its scheduler for two cycles,\n"
+                    "so issue-active x (1 + FP64 share of the instruction mix) ~ 0.9: the kernel is bound by instruction issue / FP64 dispatch, not by\n"
+                    "latency or memory (DESIGN.md §3); fewer instructions per point is the only lever left (evaluations per point: 485 -> 259 this round).")
+summarise(os.path.join(G, f"prof_gsip_{R}.ncu-rep"), "k_gsip", "k_gsip", W2,
+          "Reading: 447 inside points, one CTA each, rounds of <= 21 samples: latency / imbalance bound (barrier and wait stalls), ~0.12 ms of a 1.03 ms step.")
+summarise(os.path.join(G, f"prof_outer_mesh_{R}.ncu-rep"), "k_outer_mesh", "k_outer",
+          "config 4m scene (the reference's star.obj through the triangle-mesh functor, 16-piece MINCO) at 20 000 query points, strict build",
+          "Reading: per functor evaluation the reference's float winding-number hierarchy costs ~45 child expansions + ~9 leaf triangles near the\n"
+          "shape (accuracy_scale 2) and the exact closest-triangle search ~12 boxes + a few double-precision triangle tests; lanes of a warp walk\n"
+          "different paths (active threads per instruction < 32).  Instruction-bound divergent traversal: DESIGN.md §3 (mesh functor).")
+if t_outer is not None:
+    json.dump({"kernel": "k_outer", "dram_bytes_per_launch": t_outer,
+               "source": f"profiles/{R}_k_outer_ncu_summary.md (dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture)"},
+              open(os.path.join(Pdir, f"{R}_k_outer_traffic.json"), "w"), indent=1)
 # ---- bench / configs / batch records ----
 for src, dst in ((f"bench_{R}.json", f"{R}_bench.json"), (f"bench_reference_{R}.json", f"{R}_bench_reference.json"), (f"configs_{R}.jsonl", f"{R}_configs_1_to_4.jsonl"),
                  (f"batch_1gpu_{R}.json", f"{R}_batch_1gpu.json"), (f"pytest_gpu_{R}.log", f"{R}_pytest_gpu.log")):
