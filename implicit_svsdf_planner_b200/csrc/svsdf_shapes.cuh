@@ -329,11 +329,24 @@ __device__ __forceinline__ PolyHit polygon_scan(const ShapeParams &S, double qx,
         if (dis < H.dis) {
             H.dis = dis; H.cx = cx; H.cy = cy;
         }
-        double ths = atan2_portable(sy - qy, sx - qx), the = atan2_portable(ey - qy, ex - qx);
-        ths = (ths < 0.0) ? (ths + 2 * PI) : ths;
-        the = (the < 0.0) ? (the + 2 * PI) : the;
-        double d1 = fabs(ths - the);
-        if (!(d1 < PI)) H.rs++;
+        // Crossing test (Shape.hpp:1461-1470): with both polar angles mapped to [0, 2 pi), |ths - the| >= pi.  In exact terms:
+        // a = s - q and b = e - q lie on different sides of the horizontal through q, and b is at least a half turn ahead of a
+        // (sin of the turn = cross(a, b) / |a||b| <= 0 when a is above, >= 0 when a is below); equal sides never reach pi.  The two
+        // atan2 calls are needed only where their rounding (a few 1e-16 rad) could decide: an offset exactly on the horizontal, or
+        // a and b within 1e-9 rad of (anti)parallel.  Everywhere else the sign tests give the same answer as the angles.
+        const double ax = sx - qx, ay = sy - qy, bx = ex - qx, by = ey - qy;
+        const double cr = ax * by - ay * bx;
+        bool crossing;
+        if (ay != 0.0 && by != 0.0 && fabs(cr) > 1e-9 * ((fabs(ax) + fabs(ay)) * (fabs(bx) + fabs(by)))) {
+            crossing = ((ay > 0.0) != (by > 0.0)) && ((ay > 0.0) ? (cr < 0.0) : (cr > 0.0));
+        } else {
+            double ths = atan2_portable(ay, ax), the = atan2_portable(by, bx);
+            ths = (ths < 0.0) ? (ths + 2 * PI) : ths;
+            the = (the < 0.0) ? (the + 2 * PI) : the;
+            const double d1 = fabs(ths - the);
+            crossing = !(d1 < PI);
+        }
+        if (crossing) H.rs++;
     }
     return H;
 }
