@@ -105,19 +105,24 @@ class ClockSampler:
 
 
 def build_problem(rank: int):
-    """Config 2 for rank 0; for other ranks another seeded problem of identical size (batch-of-problems mode)."""
+    """Config 2 for every rank: rank 0 the scene as BASELINE.json states it, the other ranks the SAME scene with its query points
+    cyclically shifted — an independent replica with its own buffers whose work equals config 2's exactly, so that the
+    per-GPU work is fixed as N grows (weak scaling) and the max over ranks measures the box, not which rank drew a harder scene.
+    (Batches of genuinely different problems are measured by scripts/run_batch.py, BASELINE config 5.)"""
+    import numpy as np
     from implicit_svsdf_planner_b200 import scenes
 
-    if rank == 0:
-        return scenes.make_scene(SHAPE, N_PIECES, P_POINTS)
-    return scenes.make_scene(SHAPE, N_PIECES, P_POINTS, seed_traj=scenes.SEED_TRAJ + 17 * rank, seed_map=scenes.SEED_MAP + 17 * rank)
+    sc = scenes.make_scene(SHAPE, N_PIECES, P_POINTS)
+    if rank > 0:
+        sc.points = np.ascontiguousarray(np.roll(sc.points, 7919 * rank, axis=0))  # cyclic shift: same neighbours, other buffers
+    return sc
 
 
 def workload_config(world: int) -> dict:
     """The `config` object of the JSON line: identical for both arms (the driver compares them)."""
     return {
         "workload": "config2: star, 8-piece MINCO, 200k query points, one cost+gradient evaluation per step"
-                    + ("" if world == 1 else f"; {world} independent problems of that size in flight, one per GPU, every rank cycling through all of them"),
+                    + ("" if world == 1 else f"; {world} independent replicas of it in flight (same scene, query points cyclically shifted), one per GPU, every rank cycling through all of them"),
         "shape": SHAPE, "pieces": N_PIECES, "points_per_gpu": P_POINTS, "problems": world,
         "l2": "GPU arm: flushed between timed iterations (320 MB memset, untimed), inputs are 3.2 MB; CPU arm: n/a",
         "parallelism": "one problem per GPU, no data-path collective" if world > 1 else "single GPU",
@@ -261,10 +266,9 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    # Batch-of-problems mode: the box works through `world` independent problems of config-2 size (problem 0 IS config 2);
-    # every rank visits all of them, starting at its own (step s -> problem (rank + s) % world), the way each GPU of a
-    # real batch (BASELINE config 5: 4096 problems) sees a mix of problems — so the max over ranks measures the system,
-    # not which rank drew the hardest scene.  At N = 1 this is config 2 alone.
+    # The box works through `world` independent replicas of config 2 (problem 0 IS config 2, the others hold the same scene with
+    # the query points cyclically shifted: equal work per GPU); every rank visits all of them, starting at its own (step s ->
+    # problem (rank + s) % world), each through its own context and device buffers.  At N = 1 this is config 2 alone.
     problems = [build_problem(r) for r in range(world)]
     sc = problems[rank]
     co = sc.coeffs_colmajor()

@@ -1074,7 +1074,7 @@ int svsdf_set_points(svsdf_ctx *ctx, const double *pts, int64_t P, int stride) {
     const int64_t nchunks = (P + chunk - 1) / chunk;
     int nth = (int)std::min<int64_t>(nchunks, 4);
 #ifdef _OPENMP
-    nth = std::max(1, std::min(nth, omp_get_max_threads()));
+    nth = std::max(1, std::min(nth, omp_get_num_procs()));  // not omp_get_max_threads(): launchers set OMP_NUM_THREADS = 1 per rank
 #else
     nth = 1;
 #endif
