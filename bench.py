@@ -262,8 +262,10 @@ def main():
 
     rank, world, local = dist_env()
     torch.cuda.set_device(local)
+    numa_cpus = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        numa_cpus = batch.bind_to_gpu_numa(local)  # before any pinned buffer exists (the e2e leg's staging memory)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     # The box works through `world` independent replicas of config 2 (problem 0 IS config 2, the others hold the same scene with
@@ -326,6 +328,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     value = world * sc.P * args.steps / (total_ms * 1e-3)
+    # per-rank view (diagnostic: the max over ranks above is set by the slowest GPU of the box)
+    per_rank = torch.zeros(world, 2, dtype=torch.float64, device=f"cuda:{local}")
+    per_rank[rank, 0] = my_ms / args.steps
+    per_rank[rank, 1] = float(clocks.get("sm_mhz") or 0.0)
+    if world > 1:
+        dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
+    per_rank = per_rank.cpu().numpy()
 
     # ---- end-to-end through the C ABI with host buffers ----
     for w in range(2):
@@ -405,9 +414,10 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "per_rank": {"ms_per_step": [float(v) for v in per_rank[:, 0]], "sm_mhz": [float(v) for v in per_rank[:, 1]]},
             "dtype": "f64", "data": "synthetic",
             "config": workload_config(world),
-            "impl_config": {"fp_mode": "strict (-fmad=false)" if strict else "fma-contracted (opt-in, not bit-exact)", "map_broadcast_bytes": map_bytes},
+            "impl_config": {"rank_cpu_affinity": (f"GPU-local NUMA CPUs ({numa_cpus})" if numa_cpus else "unchanged"), "fp_mode": "strict (-fmad=false)" if strict else "fma-contracted (opt-in, not bit-exact)", "map_broadcast_bytes": map_bytes},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": float(te.item()) / args.steps},
             "gpu_launches": launches, "clocks": clocks, "wall_ms_timed_region": 1e3 * (t_wall1 - t_wall0),

@@ -15,6 +15,8 @@ from __future__ import annotations
 import dataclasses
 from typing import Callable, Optional
 
+import os
+
 import numpy as np
 
 from . import scenes
@@ -127,6 +129,28 @@ def extract_query_points(gm: GridMap, waypoints: np.ndarray, half: float, keepou
             keep[s : s + 100_000] = (dx * dx + dy * dy > clearance * clearance).all(axis=1)
         pts = pts[keep]
     return pts
+
+
+def bind_to_gpu_numa(device_index: int) -> Optional[int]:
+    """Pin this process (and the threads it starts later) to the CPUs the driver reports as local to GPU `device_index`
+    (NVML's ideal CPU affinity: the NUMA node the GPU hangs off), so that the pinned staging buffers are first-touched in that
+    node's memory and the H2D copies do not cross sockets.  For multi-rank launches (one process per GPU); returns the number
+    of CPUs in the mask, or None when NVML / sched_setaffinity is unavailable (nothing is changed then)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return None
 
 
 def partition(n_problems: int, world: int, rank: int) -> range:

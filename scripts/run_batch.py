@@ -47,6 +47,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        batch.bind_to_gpu_numa(local)  # host workers and staging memory next to this rank's GPU
         dist.init_process_group("nccl", device_id=dev)
     extent, ks = 60.0, 17
     n = int(np.ceil(extent / args.res))
