@@ -88,7 +88,7 @@ EXPORTED_SYMBOLS = [
     "svsdf_optimize", "svsdf_optimize_batch", "svsdf_cost_grad_batch", "svsdf_minco_forward", "svsdf_minco_propagate", "svsdf_forward_T", "svsdf_backward_T",
     "svsdf_shape_sdf", "svsdf_shape_grad1", "svsdf_cost_grad_device", "svsdf_kernel_launches",
     "svsdf_executed_evals", "svsdf_fp64_peak", "svsdf_device_ptr_points", "svsdf_lbfgs_minimize", "svsdf_last_kernel_ms", "svsdf_sincos", "svsdf_set_map", "svsdf_set_map_device",
-    "svsdf_extract_points", "svsdf_get_points", "svsdf_read_obj", "svsdf_free", "svsdf_mesh_fwn_host",
+    "svsdf_extract_points", "svsdf_extract_points3d", "svsdf_set_map3d", "svsdf_get_points", "svsdf_read_obj", "svsdf_free", "svsdf_mesh_fwn_host",
     "svsdf_front_init", "svsdf_front_get_kernels", "svsdf_front_cspace", "svsdf_front_check_kernel_value", "svsdf_front_expand", "svsdf_front_astar",
 ]
 
@@ -143,6 +143,8 @@ def lib():
     L.svsdf_set_map.argtypes = [vp, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
     L.svsdf_set_map_device.argtypes = [vp, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double]
     L.svsdf_extract_points.argtypes = [vp, dp, C.c_int, C.c_double, dp, C.c_int, C.c_double, C.POINTER(C.c_int64)]
+    L.svsdf_extract_points3d.argtypes = [vp, dp, C.c_int, dp, dp, C.c_int, C.c_double, C.POINTER(C.c_int64)]
+    L.svsdf_set_map3d.argtypes = [vp, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, dp, C.c_double]
     L.svsdf_get_points.argtypes = [vp, dp, C.c_int64, C.POINTER(C.c_int64)]
     L.svsdf_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.svsdf_kernel_launches.argtypes = [vp, C.POINTER(C.c_int64)]
@@ -527,6 +529,26 @@ class Context:
         n = C.c_int64()
         self._ck(lib().svsdf_extract_points(self.h, _p(w), w.shape[0], float(half), _p(ko), 0 if ko is None else ko.shape[0],
                                             float(clearance), C.byref(n)), "svsdf_extract_points")
+        self.P = n.value
+        return n.value
+
+    def set_map3d(self, kernel_bytes, X, Y, Z, kernel_size, origin_xyz, res):
+        """The reference's 3-D packed map (generateMapKernel layout, PCSmap_manager.h:39-78)."""
+        kb = np.ascontiguousarray(kernel_bytes, dtype=np.uint8)
+        h = (int(kernel_size) - 1) // 2
+        if kb.size != (X + 2 * h) * (Y + 2 * h) * ((Z + 2 * h + 7) // 8):
+            raise ValueError("set_map3d: kernel_bytes has the wrong size for X, Y, Z, kernel_size")
+        o = _f64(origin_xyz).reshape(3)
+        self._ck(lib().svsdf_set_map3d(self.h, kb.ctypes.data_as(C.c_void_p), int(X), int(Y), int(Z), int(kernel_size), _p(o), float(res)),
+                 "svsdf_set_map3d")
+
+    def extract_points3d(self, waypoints_xyz, half_xyz, keepout_xy=None, clearance=0.0):
+        w = _f64(waypoints_xyz).reshape(-1, 3)
+        hx = _f64(half_xyz).reshape(3)
+        ko = _f64(keepout_xy).reshape(-1, 2) if keepout_xy is not None else None
+        n = C.c_int64()
+        self._ck(lib().svsdf_extract_points3d(self.h, _p(w), w.shape[0], _p(hx), _p(ko), 0 if ko is None else ko.shape[0],
+                                              float(clearance), C.byref(n)), "svsdf_extract_points3d")
         self.P = n.value
         return n.value
 

@@ -82,55 +82,6 @@ def make_random_map(extent: float = 60.0, res: float = 0.025, density: float = 0
     return GridMap(occ=occ, origin=np.zeros(2), res=res)
 
 
-def extract_query_points(gm: GridMap, waypoints: np.ndarray, half: float, keepout: Optional[np.ndarray] = None,
-                         clearance: float = 0.0) -> np.ndarray:
-    """getPointsInAABBOutOfLastOne over the waypoint sequence (plan_manager.cpp:156-167): occupied cells in each
-    waypoint's box that are outside the previous waypoint's box, de-duplicated by cell id, returned in ascending
-    (i * Y + j) order — the memory order of the packed map, which is what the device kernel (csrc/svsdf_extract.cu)
-    produces; the reference iterates an unordered_map, i.e. in unspecified order.  This numpy version is the host
-    restatement the device kernel is tested against.  keepout/clearance: synthetic-scene option, see problem_scene."""
-    X, Y = gm.shape
-    lo_w, hi_w = gm.origin, gm.origin + np.array([X, Y]) * gm.res
-
-    def box_idx(c):
-        c1 = np.clip(c - half, lo_w, hi_w)  # projInMap
-        c2 = np.clip(c + half, lo_w, hi_w)
-        i1 = np.floor((c1 - gm.origin) / gm.res).astype(int)
-        i2 = np.floor((c2 - gm.origin) / gm.res).astype(int)
-        return i1, i2
-
-    ids = []
-    prev = None
-    for w in np.asarray(waypoints, dtype=np.float64)[:, :2]:
-        i1, i2 = box_idx(w)
-        a1, a2 = np.clip(i1, 0, [X - 1, Y - 1]), np.clip(i2, 0, [X - 1, Y - 1])
-        sub = gm.occ[a1[0] : a2[0] + 1, a1[1] : a2[1] + 1]
-        ii, jj = np.nonzero(sub)
-        ii, jj = ii + a1[0], jj + a1[1]
-        if prev is not None:
-            p1, p2 = prev
-            outside = (ii > p2[0]) | (ii < p1[0]) | (jj > p2[1]) | (jj < p1[1])
-            ii, jj = ii[outside], jj[outside]
-        ids.append(ii.astype(np.int64) * Y + jj)
-        prev = (a1, a2)  # idcorner*_l are clamped indices too (Gridmap3D.cpp:150-172)
-    if not ids:
-        return np.zeros((0, 3))
-    uid = np.unique(np.concatenate(ids))
-    ij = np.stack([uid // Y, uid % Y], axis=1)
-    pts = np.zeros((uid.size, 3))
-    pts[:, :2] = gm.cell_centers(ij)
-    if keepout is not None and len(keepout):
-        ko = np.asarray(keepout, dtype=np.float64).reshape(-1, 2)
-        keep = np.ones(pts.shape[0], dtype=bool)
-        for s in range(0, pts.shape[0], 100_000):
-            blk = pts[s : s + 100_000, :2]
-            dx = blk[:, None, 0] - ko[None, :, 0]
-            dy = blk[:, None, 1] - ko[None, :, 1]
-            keep[s : s + 100_000] = (dx * dx + dy * dy > clearance * clearance).all(axis=1)
-        pts = pts[keep]
-    return pts
-
-
 def bind_to_gpu_numa(device_index: int) -> Optional[int]:
     """Pin this process (and the threads it starts later) to the CPUs the driver reports as local to GPU `device_index`
     (NVML's ideal CPU affinity: the NUMA node the GPU hangs off), so that the pinned staging buffers are first-touched in that
@@ -181,15 +132,17 @@ def broadcast_map(kernel: Optional[np.ndarray], device=None, src: int = 0):
     return buf
 
 
-def problem_scene(gm: GridMap, start, goal, N: int = 8, P: Optional[int] = None, seed: int = 0, clearance: float = 2.75) -> scenes.Scene:
-    """One start/goal problem on the shared map: seeded nominal spline, query points extracted from the map around its
-    waypoints, a corridor around the nominal path kept free (stand-in for the A* feasibility of the reference's front
-    end), optionally sub-sampled to exactly P points."""
+def problem_scene(gm: GridMap, start, goal, extract: Callable, N: int = 8, P: Optional[int] = None, seed: int = 0,
+                  clearance: float = 2.75) -> scenes.Scene:
+    """One start/goal problem on the shared map: seeded nominal spline, query points taken from the map around its waypoints by
+    `extract(gm, waypoints_xy, half, keepout_xy, clearance) -> [n, 3]` (on a GPU box: svsdf_extract_points through
+    api.Context, see scripts/run_batch.py; the CPU tests pass the oracle's restatement), a corridor around the nominal path
+    kept free (stand-in for the A* feasibility of the reference's front end), optionally sub-sampled to exactly P points."""
     init_s, final_s, q, T = scenes.make_trajectory("star", N, seed, start, goal)
     b = scenes.minco_dense(init_s, final_s, q, T)
     half = scenes.YAML["kernel_size"] * scenes.YAML["occupancy_resolution"] / 3.0
     wps = np.concatenate([init_s[:2, :1], q[:2], final_s[:2, :1]], axis=1).T
-    pts = extract_query_points(gm, wps, half, keepout=keepout_samples(b, T), clearance=clearance)
+    pts = extract(gm, wps, half, keepout_samples(b, T), clearance)
     if P is not None and pts.shape[0] > P:
         rng = np.random.Generator(np.random.MT19937(seed + 1))
         pts = pts[np.sort(rng.choice(pts.shape[0], size=P, replace=False))]
@@ -283,9 +236,10 @@ class BatchRunner:
     exercised without CUDA.  dynamic=False: contiguous static split (`partition`); dynamic=True: `WorkQueue` shared by all
     ranks, LPT order."""
 
-    def __init__(self, solve: Callable[[scenes.Scene, int], np.ndarray], result_len: int, dynamic: bool = False):
+    def __init__(self, solve: Callable[[scenes.Scene, int], np.ndarray], result_len: int, extract: Callable, dynamic: bool = False):
         self.solve = solve
         self.result_len = result_len
+        self.extract = extract  # query-point construction, see problem_scene
         self.dynamic = dynamic
         self.mine = []
 
@@ -299,7 +253,7 @@ class BatchRunner:
 
         def one(k):
             sg = problems[k]
-            sc = problem_scene(gm, sg[:2], sg[2:4], N=N, P=P, seed=scenes.SEED_BATCH + k)
+            sc = problem_scene(gm, sg[:2], sg[2:4], self.extract, N=N, P=P, seed=scenes.SEED_BATCH + k)
             local[k] = self.solve(sc, k)
 
         if self.dynamic:

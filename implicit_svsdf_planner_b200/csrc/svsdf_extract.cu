@@ -1,6 +1,6 @@
-// svsdf_extract.cu — K3: query-point construction on the device from the bit-packed 2-D map kernel.
+// svsdf_extract.cu — K3: query-point construction on the device from the bit-packed map kernel, one z layer per launch.
 //
-// Restates, for the z = 0 layer, what the reference does on the host before every optimisation
+// Restates what the reference does on the host before every optimisation
 //   PlannerManager::generateTraj                         src/plan_manager/src/plan_manager.cpp:156-175
 //   PCSmapManager::getPointsInAABBOutOfLastOne           src/map_manager/include/map_manager/PCSmap_manager.h:184-219
 //   projInMap / unifiedID                                PCSmap_manager.h:118-135
@@ -8,7 +8,10 @@
 // on the map representation the reference broadcasts to its front end, the byte-packed "map kernel"
 //   PCSmapManager::generateMapKernel2D                   PCSmap_manager.h:81-108  ((X+2h) x ceil((Y+2h)/8) bytes, MSB first).
 // A cell is a query point iff it is occupied and lies in the AABB of some waypoint w but outside the AABB of waypoint
-// w-1 (the reference visits, per waypoint, only the cells outside the previous box and de-duplicates by cell id).  The
+// w-1 (the reference visits, per waypoint, only the cells outside the previous box and de-duplicates by cell id; for the first
+// waypoint the "previous" box is the one around tmp_pos = (999, 999, 999), the map's far corner cell).  A 3-D map is handled
+// layer by layer (svsdf_extract_points3d): the host marks, per layer, which waypoint boxes contain it; occupied cells of several
+// layers above the same (x, y) come out as several points with that (x, y) — the cost loop zeroes z.  The
 // reference enumerates an unordered_map (unspecified order); here points come out in ascending (i * Y + j) order, which
 // is the memory order of the packed map, so loads are coalesced and the result is deterministic.
 //
@@ -46,10 +49,13 @@ __device__ __forceinline__ unsigned selected_cells(const ExtractArgs &E, int x, 
     const int ybase = 32 * wy - E.h;  // real y index of bit 0
     unsigned member = 0u;
     for (int w = 0; w < E.W; ++w) {
-        if (x < E.bx1[w] || x > E.bx2[w]) continue;
+        if (!E.act[w] || x < E.bx1[w] || x > E.bx2[w]) continue;
         unsigned m = interval_mask(E.by1[w] - ybase, E.by2[w] - ybase);
-        if (w > 0 && x >= E.bx1[w - 1] && x <= E.bx2[w - 1])  // "OutOfLastOne": skip the previous waypoint's box
-            m &= ~interval_mask(E.by1[w - 1] - ybase, E.by2[w - 1] - ybase);
+        if (E.excl[w]) {  // "OutOfLastOne": skip the cells of the previous waypoint's box (w = 0: the box around tmp_pos)
+            const int lx1 = w ? E.bx1[w - 1] : E.px1, lx2 = w ? E.bx2[w - 1] : E.px2;
+            const int ly1 = w ? E.by1[w - 1] : E.py1, ly2 = w ? E.by2[w - 1] : E.py2;
+            if (x >= lx1 && x <= lx2) m &= ~interval_mask(ly1 - ybase, ly2 - ybase);
+        }
         member |= m;
     }
     if (member == 0u) return 0u;

@@ -106,7 +106,8 @@ struct svsdf_ctx {
     bool own_map = true;
     size_t cap_map = 0;
     int map_X = 0, map_Y = 0, map_h = 0, map_row_bytes = 0;
-    double map_ox = 0, map_oy = 0, map_res = 0;
+    int map_Z = 1;             // z layers held on the device (svsdf_set_map3d), each in the 2-D layout; layer 0 first
+    double map_ox = 0, map_oy = 0, map_oz = 0, map_res = 0;
     int *d_block_counts = nullptr;
     int cap_block_counts = 0;
     int64_t *d_n_total = nullptr;
@@ -1442,7 +1443,8 @@ static int set_map_meta(svsdf_ctx *ctx, int X, int Y, int kernel_size, double ox
     }
     ctx->map_X = X; ctx->map_Y = Y; ctx->map_h = (kernel_size - 1) / 2;
     ctx->map_row_bytes = (Y + 2 * ctx->map_h + 7) / 8;
-    ctx->map_ox = ox; ctx->map_oy = oy; ctx->map_res = res;
+    ctx->map_ox = ox; ctx->map_oy = oy; ctx->map_oz = 0.0; ctx->map_res = res;
+    ctx->map_Z = 1;
     return SVSDF_OK;
 }
 
@@ -1479,37 +1481,88 @@ int svsdf_set_map_device(svsdf_ctx *ctx, const unsigned char *dev_kernel_bytes, 
     return SVSDF_OK;
 }
 
-int svsdf_extract_points(svsdf_ctx *ctx, const double *waypoints_xy, int W, double half, const double *keepout_xy,
-                         int n_keepout, double clearance, int64_t *n_points) {
-    if (!ctx || !waypoints_xy || W < 1 || W > kMaxWaypoints || n_keepout < 0 || n_keepout > kMaxKeepout ||
-        (n_keepout > 0 && !keepout_xy) || !(half >= 0.0))
-        return SVSDF_ERR_INVALID;
-    if (!ctx->d_map) { ctx->err = "svsdf_extract_points: map not set"; return SVSDF_ERR_NOT_READY; }
+// generateMapKernel's layout (PCSmap_manager.h:39-78: [(X + 2h)][(Y + 2h)][ceil((Z + 2h) / 8)] bytes, z bits MSB first) is re-packed on
+// the host, once per map, into Z layers of the 2-D layout the kernels read ([(X + 2h)][ceil((Y + 2h) / 8)], y bits MSB first); layer 0 is
+// what generateMapKernel2D would have produced, so the front-end kernels see the same map as with svsdf_set_map.
+int svsdf_set_map3d(svsdf_ctx *ctx, const unsigned char *kernel_bytes, int X, int Y, int Z, int kernel_size, const double *origin_xyz,
+                    double res) {
+    if (!ctx || !kernel_bytes || !origin_xyz || Z < 1 || Z > kMaxMapLayers) return SVSDF_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int rc = set_map_meta(ctx, X, Y, kernel_size, origin_xyz[0], origin_xyz[1], res);
+    if (rc) return rc;
+    const int h = ctx->map_h;
+    const size_t layer = (size_t)(X + 2 * h) * ctx->map_row_bytes;
+    const int zb = (Z + 2 * h + 7) / 8;
+    std::vector<unsigned char> L(layer * (size_t)Z, 0);
+    for (int x = 0; x < X; ++x)
+        for (int y = 0; y < Y; ++y) {
+            const unsigned char *col = kernel_bytes + ((size_t)(x + h) * (Y + 2 * h) + (size_t)(y + h)) * zb;
+            for (int z = 0; z < Z; ++z) {
+                const int fz = z + h;
+                if (col[fz / 8] & (0x80u >> (fz % 8))) {
+                    const int fy = y + h;
+                    L[(size_t)z * layer + (size_t)(x + h) * ctx->map_row_bytes + fy / 8] |= (unsigned char)(0x80u >> (fy % 8));
+                }
+            }
+        }
+    const size_t bytes = L.size();
+    if (!ctx->own_map) { ctx->d_map = nullptr; ctx->own_map = true; ctx->cap_map = 0; }
+    if (bytes > ctx->cap_map) {
+        cudaFree(ctx->d_map);
+        ctx->d_map = nullptr;
+        ctx->cap_map = 0;
+        CK(cudaMalloc(&ctx->d_map, bytes + 64));
+        ctx->cap_map = bytes + 64;
+    }
+    CK(cudaMemcpyAsync(ctx->d_map, L.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->map_Z = Z;
+    ctx->map_oz = origin_xyz[2];
+    return SVSDF_OK;
+}
+
+// Shared by the flat and the 3-D entry points.  wp: W x 3 waypoint centres, half: box half sizes (x, y, z).
+static int extract_impl(svsdf_ctx *ctx, const char *who, const double *wp, int W, const double *half, const double *keepout_xy,
+                        int n_keepout, double clearance, int64_t *n_points) {
+    if (!ctx->d_map) { ctx->err = std::string(who) + ": map not set"; return SVSDF_ERR_NOT_READY; }
     CK(cudaSetDevice(ctx->device));
     ExtractArgs E;
     std::memset(&E, 0, sizeof(E));
-    E.map = ctx->d_map;
     E.X = ctx->map_X; E.Y = ctx->map_Y; E.h = ctx->map_h; E.row_bytes = ctx->map_row_bytes;
     E.ox = ctx->map_ox; E.oy = ctx->map_oy; E.res = ctx->map_res;
     E.W = W;
-    const double lo[2] = {E.ox, E.oy};
-    const double hi[2] = {E.ox + (double)E.X * E.res, E.oy + (double)E.Y * E.res};  // boundary_xyzmax
-    const int size[2] = {E.X, E.Y};
-    int rxmin = E.X, rxmax = -1, rymin = E.Y, rymax = -1;
-    for (int w = 0; w < W; ++w) {
-        int idx[2][2];
-        for (int a = 0; a < 2; ++a) {
+    const int Z = ctx->map_Z;
+    const double lo[3] = {E.ox, E.oy, ctx->map_oz};
+    const double hi[3] = {E.ox + (double)E.X * E.res, E.oy + (double)E.Y * E.res, ctx->map_oz + (double)Z * E.res};  // boundary_xyzmax
+    const int size[3] = {E.X, E.Y, Z};
+    // clamped index box around a centre: corner = centre -+ half -> projInMap (PCSmap_manager.h:128-135) -> getGridIndex
+    // (Gridmap3D.cpp:137-174: floor, clamped to the last cell)
+    auto box = [&](const double *c, int idx[3][2]) {
+        for (int a = 0; a < 3; ++a)
             for (int side = 0; side < 2; ++side) {
-                double c = waypoints_xy[2 * w + a] + (side ? half : -half);  // corner1 = center - half, corner2 = center + half
-                c = c < lo[a] ? lo[a] : c;                                  // projInMap (PCSmap_manager.h:128-135)
-                c = c > hi[a] ? hi[a] : c;
-                int i = (int)std::floor((c - lo[a]) / E.res);               // getGridIndex (Gridmap3D.cpp:144-148)
+                double v = c[a] + (side ? half[a] : -half[a]);
+                v = v < lo[a] ? lo[a] : v;
+                v = v > hi[a] ? hi[a] : v;
+                int i = (int)std::floor((v - lo[a]) / E.res);
                 i = i < 0 ? 0 : i;
                 i = i >= size[a] ? size[a] - 1 : i;
                 idx[a][side] = i;
             }
-        }
+    };
+    int bz1[kMaxWaypoints + 1], bz2[kMaxWaypoints + 1];  // slot 0: the box around tmp_pos, slot w + 1: waypoint w
+    {
+        const double tmp_pos[3] = {999.0, 999.0, 999.0};  // plan_manager.cpp:152
+        int idx[3][2];
+        box(tmp_pos, idx);
+        E.px1 = idx[0][0]; E.px2 = idx[0][1]; E.py1 = idx[1][0]; E.py2 = idx[1][1];
+        bz1[0] = idx[2][0]; bz2[0] = idx[2][1];
+    }
+    int rxmin = E.X, rxmax = -1, rymin = E.Y, rymax = -1;
+    for (int w = 0; w < W; ++w) {
+        int idx[3][2];
+        box(wp + 3 * w, idx);
         E.bx1[w] = idx[0][0]; E.bx2[w] = idx[0][1]; E.by1[w] = idx[1][0]; E.by2[w] = idx[1][1];
+        bz1[w + 1] = idx[2][0]; bz2[w + 1] = idx[2][1];
         rxmin = std::min(rxmin, E.bx1[w]); rxmax = std::max(rxmax, E.bx2[w]);
         rymin = std::min(rymin, E.by1[w]); rymax = std::max(rymax, E.by2[w]);
     }
@@ -1522,20 +1575,35 @@ int svsdf_extract_points(svsdf_ctx *ctx, const double *waypoints_xy, int W, doub
     E.clearance = clearance;
     for (int q = 0; q < 2 * n_keepout; ++q) E.keepout[q] = keepout_xy[q];
     const int n_blocks = (int)((E.n_items + 255) / 256);
-    if (n_blocks + 1 > ctx->cap_block_counts) {
+    const size_t need_counts = (size_t)(n_blocks + 1) * (size_t)Z;
+    if (need_counts > (size_t)ctx->cap_block_counts) {
         cudaFree(ctx->d_block_counts);
         ctx->d_block_counts = nullptr;
         ctx->cap_block_counts = 0;
-        CK(cudaMalloc(&ctx->d_block_counts, (size_t)(n_blocks + 1024) * sizeof(int)));
-        ctx->cap_block_counts = n_blocks + 1024;
+        CK(cudaMalloc(&ctx->d_block_counts, (need_counts + 1024) * sizeof(int)));
+        ctx->cap_block_counts = (int)(need_counts + 1024);
     }
-    if (!ctx->d_n_total) CK(cudaMalloc(&ctx->d_n_total, sizeof(int64_t)));
-    CK(launch_extract_count(E, ctx->d_block_counts, n_blocks, ctx->d_n_total, ctx->stream));
-    ctx->launches += 2;
-    int64_t total = 0;
-    CK(cudaMemcpyAsync(&total, ctx->d_n_total, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
+    if (!ctx->d_n_total) CK(cudaMalloc(&ctx->d_n_total, kMaxMapLayers * sizeof(int64_t)));
+    const size_t layer = (size_t)(E.X + 2 * E.h) * E.row_bytes;
+    auto layer_args = [&](int k) {
+        ExtractArgs Ek = E;
+        Ek.map = ctx->d_map + (size_t)k * layer;
+        for (int w = 0; w < W; ++w) {
+            Ek.act[w] = (k >= bz1[w + 1] && k <= bz2[w + 1]) ? 1 : 0;
+            Ek.excl[w] = (k >= bz1[w] && k <= bz2[w]) ? 1 : 0;
+        }
+        return Ek;
+    };
+    for (int k = 0; k < Z; ++k) {
+        CK(launch_extract_count(layer_args(k), ctx->d_block_counts + (size_t)k * (n_blocks + 1), n_blocks, ctx->d_n_total + k, ctx->stream));
+        ctx->launches += 2;
+    }
+    int64_t totals[kMaxMapLayers];
+    CK(cudaMemcpyAsync(totals, ctx->d_n_total, (size_t)Z * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (total > 2000000000LL) { ctx->err = "svsdf_extract_points: too many points"; return SVSDF_ERR_INVALID; }
+    int64_t total = 0;
+    for (int k = 0; k < Z; ++k) total += totals[k];
+    if (total > 2000000000LL) { ctx->err = std::string(who) + ": too many points"; return SVSDF_ERR_INVALID; }
     if (!ctx->own_points) { ctx->d_points = nullptr; ctx->own_points = true; ctx->cap_points = 0; }
     if (total > ctx->cap_points || !ctx->d_points) {
         cudaFree(ctx->d_points);
@@ -1544,13 +1612,42 @@ int svsdf_extract_points(svsdf_ctx *ctx, const double *waypoints_xy, int W, doub
         CK(cudaMalloc(&ctx->d_points, (size_t)(total + 1024) * 2 * sizeof(double)));
         ctx->cap_points = total + 1024;
     }
-    CK(launch_extract_write(E, ctx->d_block_counts, n_blocks, ctx->d_points, total, ctx->stream));
-    ctx->launches += 1;
+    int64_t base = 0;
+    for (int k = 0; k < Z; ++k) {  // layer-major output: layer 0's cells in ascending (i * Y + j) order, then layer 1's, ...
+        CK(launch_extract_write(layer_args(k), ctx->d_block_counts + (size_t)k * (n_blocks + 1), n_blocks, ctx->d_points + 2 * base, totals[k], ctx->stream));
+        ctx->launches += 1;
+        base += totals[k];
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->P = total;
     ctx->last_n_inside = -1;
     if (n_points) *n_points = total;
     return ensure_scratch(ctx, total);
+}
+
+int svsdf_extract_points(svsdf_ctx *ctx, const double *waypoints_xy, int W, double half, const double *keepout_xy,
+                         int n_keepout, double clearance, int64_t *n_points) {
+    if (!ctx || !waypoints_xy || W < 1 || W > kMaxWaypoints || n_keepout < 0 || n_keepout > kMaxKeepout ||
+        (n_keepout > 0 && !keepout_xy) || !(half >= 0.0))
+        return SVSDF_ERR_INVALID;
+    if (ctx->map_Z != 1) { ctx->err = "svsdf_extract_points: the map has several z layers, use svsdf_extract_points3d"; return SVSDF_ERR_INVALID; }
+    // the flat case: one layer, every box spans it (centre z in the middle of the layer)
+    std::vector<double> wp((size_t)W * 3);
+    for (int w = 0; w < W; ++w) {
+        wp[3 * (size_t)w] = waypoints_xy[2 * w];
+        wp[3 * (size_t)w + 1] = waypoints_xy[2 * w + 1];
+        wp[3 * (size_t)w + 2] = ctx->map_oz + 0.5 * ctx->map_res;
+    }
+    const double h3[3] = {half, half, half};
+    return extract_impl(ctx, "svsdf_extract_points", wp.data(), W, h3, keepout_xy, n_keepout, clearance, n_points);
+}
+
+int svsdf_extract_points3d(svsdf_ctx *ctx, const double *waypoints_xyz, int W, const double *half_xyz, const double *keepout_xy,
+                           int n_keepout, double clearance, int64_t *n_points) {
+    if (!ctx || !waypoints_xyz || !half_xyz || W < 1 || W > kMaxWaypoints || n_keepout < 0 || n_keepout > kMaxKeepout ||
+        (n_keepout > 0 && !keepout_xy) || !(half_xyz[0] >= 0.0) || !(half_xyz[1] >= 0.0) || !(half_xyz[2] >= 0.0))
+        return SVSDF_ERR_INVALID;
+    return extract_impl(ctx, "svsdf_extract_points3d", waypoints_xyz, W, half_xyz, keepout_xy, n_keepout, clearance, n_points);
 }
 
 int svsdf_get_points(svsdf_ctx *ctx, double *xy_out, int64_t capacity, int64_t *n_points) {

@@ -146,6 +146,7 @@ struct KernelArgs {
 
 // K3 (svsdf_extract.cu): query-point extraction from the packed map kernel
 constexpr int kMaxWaypoints = 66;   // interior waypoints of <= 64 pieces (+ optional end points)
+constexpr int kMaxMapLayers = 64;   // z layers of a 3-D map (svsdf_set_map3d)
 constexpr int kMaxKeepout = 160;    // keep-out polyline samples (synthetic scenes only)
 struct ExtractArgs {
     const unsigned char *map;  // (X + 2h) x row_bytes, MSB-first bits along y (PCSmap_manager.h:81-108)
@@ -153,6 +154,12 @@ struct ExtractArgs {
     double ox, oy, res;        // boundary_xyzmin (x, y) and grid resolution
     int W;                     // number of waypoint boxes
     int bx1[kMaxWaypoints], bx2[kMaxWaypoints], by1[kMaxWaypoints], by2[kMaxWaypoints];  // clamped index boxes
+    // "OutOfLastOne": the box whose cells waypoint w skips is the box of waypoint w - 1; for w = 0 it is the box around
+    // tmp_pos = (999, 999, 999) (plan_manager.cpp:152), i.e. after projInMap the far corner cell of the map
+    int px1, px2, py1, py2;
+    // one launch handles ONE z layer of the map: act[w] = the layer lies in waypoint w's z range, excl[w] = it lies in the z range
+    // of the box waypoint w skips (a skipped cell must be inside the last box in all three dimensions, PCSmap_manager.h:207-209)
+    unsigned char act[kMaxWaypoints], excl[kMaxWaypoints];
     int rx1, wy1, nW;          // bounding rectangle: first row, first 32-cell word, words per row
     long long n_items;         // rows * nW
     int n_keepout;

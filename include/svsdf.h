@@ -241,8 +241,20 @@ int svsdf_set_map(svsdf_ctx *ctx, const unsigned char *kernel_bytes, int X, int 
                   double origin_y, double res);
 int svsdf_set_map_device(svsdf_ctx *ctx, const unsigned char *dev_kernel_bytes, int X, int Y, int kernel_size,
                          double origin_x, double origin_y, double res);
+/* The reference's 3-D map: generateMapKernel's layout (PCSmap_manager.h:39-78: (X + 2h) x (Y + 2h) x ceil((Z + 2h)/8) bytes, z bits
+ * MSB first), origin = boundary_xyzmin (x, y, z).  Re-packed into Z layers of the 2-D layout on upload; layer 0 is what
+ * svsdf_set_map would have been given (generateMapKernel2D), so the front-end entry points work on it unchanged.  Z <= 64. */
+int svsdf_set_map3d(svsdf_ctx *ctx, const unsigned char *kernel_bytes, int X, int Y, int Z, int kernel_size,
+                    const double *origin_xyz, double res);
+/* svsdf_extract_points on a 3-D map: waypoints_xyz W x 3, half_xyz = the box half sizes (bdx/3, bdy/3, bdz/3 in
+ * plan_manager.cpp:165).  Every occupied voxel of every layer inside a box (and outside the last box in at least one dimension)
+ * is a query point; voxels stacked above the same (x, y) give several points with that (x, y) — the cost loop zeroes z
+ * (back_end_optimizer.hpp:791).  Output order: layer by layer, ascending (i*Y + j) within a layer. */
+int svsdf_extract_points3d(svsdf_ctx *ctx, const double *waypoints_xyz, int W, const double *half_xyz, const double *keepout_xy,
+                           int n_keepout, double clearance, int64_t *n_points);
 /* Builds the context's resident query-point set from the map: occupied cells inside the AABB (half-size `half` in x and
- * y) of waypoint w and outside the AABB of waypoint w-1, de-duplicated, in ascending (i*Y + j) order.
+ * y) of waypoint w and outside the AABB of waypoint w-1 (for w = 0: outside the box around tmp_pos = (999, 999, 999),
+ * plan_manager.cpp:152, i.e. the map's far corner cell), de-duplicated, in ascending (i*Y + j) order.
  * waypoints_xy: W x 2.  keepout_xy / clearance (optional, n_keepout = 0 to disable; not part of the reference): drop
  * cells closer than `clearance` to any keep-out sample.  n_points receives the count. */
 int svsdf_extract_points(svsdf_ctx *ctx, const double *waypoints_xy, int W, double half, const double *keepout_xy,

@@ -14,6 +14,11 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from implicit_svsdf_planner_b200 import batch, scenes  # noqa: E402
+from oracle import k3_points  # noqa: E402  (the CPU restatement of the reference's point collection: the checker, tests only)
+
+
+def _extract(gm, wps, half, keepout=None, clearance=0.0):
+    return k3_points.query_points_2d(gm.occ, gm.origin, gm.res, wps, half, keepout, clearance)
 
 
 def _free_port():
@@ -41,14 +46,14 @@ def _worker(rank, world, port, tmpdir):
         occ = batch.unpack_map_kernel(t.numpy(), X, Y, 17)
         gm_local = batch.GridMap(occ=occ, origin=np.zeros(2), res=0.5)
         problems = scenes.make_batch_problems(7, seed=99)
-        runner = batch.BatchRunner(_fake_solve, 4)
+        runner = batch.BatchRunner(_fake_solve, 4, _extract)
         out = runner.run(gm_local, problems, N=8, P=None)
         np.save(os.path.join(tmpdir, f"out_{rank}.npy"), out)
         np.save(os.path.join(tmpdir, f"occ_{rank}.npy"), occ)
         mine = list(batch.partition(7, world, rank))
         np.save(os.path.join(tmpdir, f"mine_{rank}.npy"), np.array(mine))
         # dynamic work queue shared by the ranks (counter in the c10d store), LPT order
-        dyn = batch.BatchRunner(_fake_solve, 4, dynamic=True)
+        dyn = batch.BatchRunner(_fake_solve, 4, _extract, dynamic=True)
         out_d = dyn.run(gm_local, problems, N=8, P=None)
         np.save(os.path.join(tmpdir, f"outdyn_{rank}.npy"), out_d)
         np.save(os.path.join(tmpdir, f"minedyn_{rank}.npy"), np.array(dyn.mine, dtype=np.int64))
@@ -84,9 +89,9 @@ def test_query_point_extraction_dedups_and_skips_previous_box():
     occ = np.ones((40, 40), dtype=bool)
     gm = batch.GridMap(occ=occ, origin=np.zeros(2), res=1.0)
     half = 3.0
-    one = batch.extract_query_points(gm, np.array([[10.5, 10.5]]), half)
+    one = _extract(gm, np.array([[10.5, 10.5]]), half)
     assert one.shape[0] == 7 * 7 and np.all(one[:, 2] == 0)
-    two = batch.extract_query_points(gm, np.array([[10.5, 10.5], [12.5, 10.5]]), half)
+    two = _extract(gm, np.array([[10.5, 10.5], [12.5, 10.5]]), half)
     assert two.shape[0] == 7 * 7 + 2 * 7  # only the two new columns of the second box
     assert np.unique(two[:, :2], axis=0).shape[0] == two.shape[0]
     # cell centres: min + (idx + 0.5) * res
@@ -105,7 +110,7 @@ def test_world_size_2_gloo_broadcast_shard_gather(tmp_path):
     # multi-rank result == single-process result (problems are independent)
     gm = batch.make_random_map(extent=60.0, res=0.5, density=0.3, seed=123)
     problems = scenes.make_batch_problems(7, seed=99)
-    ref = batch.BatchRunner(_fake_solve, 4).run(gm, problems, N=8, P=None)
+    ref = batch.BatchRunner(_fake_solve, 4, _extract).run(gm, problems, N=8, P=None)
     assert np.array_equal(ref, o0)
     assert np.array_equal(o0[:, 0], np.arange(7))
     # dynamic queue: same table on both ranks, every problem handed out exactly once across the ranks, first ticket = longest
