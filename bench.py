@@ -105,24 +105,21 @@ class ClockSampler:
 
 
 def build_problem(rank: int):
-    """Config 2 for every rank: rank 0 the scene as BASELINE.json states it, the other ranks the SAME scene with its query points
-    cyclically shifted — an independent replica with its own buffers whose work equals config 2's exactly, so that the
-    per-GPU work is fixed as N grows (weak scaling) and the max over ranks measures the box, not which rank drew a harder scene.
-    (Batches of genuinely different problems are measured by scripts/run_batch.py, BASELINE config 5.)"""
-    import numpy as np
+    """Config 2 for every rank: each process builds the scene BASELINE.json states into its own host and device buffers — an
+    independent replica whose work equals config 2's exactly, so that the per-GPU work is fixed as N grows (weak scaling) and the
+    max over ranks measures the box.  (A cyclic shift of the point order was tried to make the replicas differ: it moves the batch
+    boundaries and costs the shifted ranks 3.5 % — a different workload, not a slower GPU.  Batches of genuinely different problems
+    are measured by scripts/run_batch.py, BASELINE config 5.)"""
     from implicit_svsdf_planner_b200 import scenes
 
-    sc = scenes.make_scene(SHAPE, N_PIECES, P_POINTS)
-    if rank > 0:
-        sc.points = np.ascontiguousarray(np.roll(sc.points, 7919 * rank, axis=0))  # cyclic shift: same neighbours, other buffers
-    return sc
+    return scenes.make_scene(SHAPE, N_PIECES, P_POINTS)
 
 
 def workload_config(world: int) -> dict:
     """The `config` object of the JSON line: identical for both arms (the driver compares them)."""
     return {
         "workload": "config2: star, 8-piece MINCO, 200k query points, one cost+gradient evaluation per step"
-                    + ("" if world == 1 else f"; {world} independent replicas of it in flight (same scene, query points cyclically shifted), one per GPU, every rank cycling through all of them"),
+                    + ("" if world == 1 else f"; {world} independent replicas of it in flight, one per GPU (own process, own host and device buffers)"),
         "shape": SHAPE, "pieces": N_PIECES, "points_per_gpu": P_POINTS, "problems": world,
         "l2": "GPU arm: flushed between timed iterations (320 MB memset, untimed), inputs are 3.2 MB; CPU arm: n/a",
         "parallelism": "one problem per GPU, no data-path collective" if world > 1 else "single GPU",
@@ -268,11 +265,9 @@ def main():
         numa_cpus = batch.bind_to_gpu_numa(local)  # before any pinned buffer exists (the e2e leg's staging memory)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    # The box works through `world` independent replicas of config 2 (problem 0 IS config 2, the others hold the same scene with
-    # the query points cyclically shifted: equal work per GPU); every rank visits all of them, starting at its own (step s ->
-    # problem (rank + s) % world), each through its own context and device buffers.  At N = 1 this is config 2 alone.
-    problems = [build_problem(r) for r in range(world)]
-    sc = problems[rank]
+    # Every rank runs its OWN replica of config 2 (own process, own host and device buffers, equal work): per-GPU work and per-rank
+    # working set are the same at every N (weak scaling), so the max over ranks measures the box.  At N = 1 this is config 2 alone.
+    sc = build_problem(rank)
     co = sc.coeffs_colmajor()
     # the only shared datum of the batch mode is the map: broadcast it once from rank 0 (NCCL) before timing
     map_bytes = None
@@ -281,17 +276,12 @@ def main():
         map_bytes = int(batch.broadcast_map(kern, device=torch.device("cuda", local)).numel())
 
     strict = os.environ.get("SVSDF_BENCH_FMA", "0") != "1"  # default: the bit-exact strict build
-    ctxs = []
-    for pr in problems:
-        c = api.Context(SHAPE, weight_p=pr.weight_p, safety_hor=pr.safety_hor, rho=pr.rho, device=local, strict_fp=strict)
-        c.set_points(pr.points)
-        ctxs.append(c)
-    cos = [pr.coeffs_colmajor() for pr in problems]
-    ctx = ctxs[rank]
+    ctx = api.Context(SHAPE, weight_p=sc.weight_p, safety_hor=sc.safety_hor, rho=sc.rho, device=local, strict_fp=strict)
+    ctx.set_points(sc.points)
+    ctxs = [ctx]
 
     def problem_of(step):
-        k = (rank + step) % world
-        return problems[k], ctxs[k], cos[k]
+        return sc, ctx, co
     flush = torch.empty(160 * 1024 * 1024, dtype=torch.float16, device=f"cuda:{local}")  # 320 MB > 126 MB L2
 
     def barrier():
@@ -300,7 +290,7 @@ def main():
             dist.barrier()
 
     # ---- device-resident throughput (value) ----
-    for w in range(max(args.warmup, world)):
+    for w in range(args.warmup):
         pr, c, cc = problem_of(w)
         c.cost_grad_device(pr.T, cc, repeats=1, fetch=False)
     launches0 = sum(c.kernel_launches() for c in ctxs)
