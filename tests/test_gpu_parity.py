@@ -506,12 +506,12 @@ def test_errors_are_reported_not_thrown(scene2k):
 # ----------------------------------------------------------------------------------------------------------------
 # Full-size (BASELINE config 2: 200k points) size-independent properties
 # ----------------------------------------------------------------------------------------------------------------
-def _full_size_check(oracle_mod, shape, N, P, mesh=None, spot=1500, cost_evals=True):
+def _full_size_check(oracle_mod, shape, N, P, mesh=None, spot=1500, cost_evals=True, scene_shape=None, polygon=None):
     """Size-independent properties at a BASELINE config's full size + a spot check of the FULL-SIZE run's per-point outputs
     (batched schedule) against the oracle."""
-    sc = scenes.make_scene(shape if shape in scenes.START_GOAL else "star", N, P)
+    sc = scenes.make_scene(scene_shape or (shape if shape in scenes.START_GOAL else "star"), N, P)
     co = sc.coeffs_colmajor()
-    ctx = api.Context(shape, mesh=mesh)
+    ctx = api.Context(shape, mesh=mesh, polygon=polygon)
     ctx.set_points(sc.points)
     c, gT, gC = ctx.cost_grad(sc.T, co)
     assert np.isfinite(c) and c > 0
@@ -533,7 +533,7 @@ def _full_size_check(oracle_mod, shape, N, P, mesh=None, spot=1500, cost_evals=T
     p_all = np.c_[sc.points[:, :2], np.zeros(sc.P)]
     s_g, t_g, g_g, r_g = ctx.query(sc.T, co, p_all)
     idx = np.sort(np.random.default_rng(5).choice(sc.P, size=spot, replace=False))
-    orc = oracle_mod.Oracle(shape, threads=oracle_mod.num_procs(), mesh=mesh)
+    orc = oracle_mod.Oracle(shape, threads=oracle_mod.num_procs(), mesh=mesh, polygon=polygon)
     orc.set_traj(sc.T, co)
     s_c, t_c, g_c, r_c = orc.query(p_all[idx])
     out = r_c == 0
@@ -558,3 +558,20 @@ def test_full_size_properties_200k(oracle_mod):
 def test_full_size_properties_config3_500k(oracle_mod):
     """BASELINE config 3: sdHorseshoe (concave), N = 16, 500 000 points."""
     _full_size_check(oracle_mod, "sdHorseshoe", 16, 500_000)
+
+
+def test_full_size_properties_config4_polygon_500k(oracle_mod):
+    """BASELINE config 4 as this release of the reference runs it: the outline of shapes/star.obj (40 vertices) through the Polygon
+    fallback functor, N = 16, 500 000 points (the crossing test's sign filter against the oracle's two atan2 per edge)."""
+    import json
+
+    xy = np.array(json.load(open(os.path.join(HERE, "golden", "obj_outlines.json")))["star"]["outline_xy"])
+    poly = xy[np.argsort(np.arctan2(xy[:, 1], xy[:, 0]))].reshape(-1)
+    _full_size_check(oracle_mod, "star_obj_outline_polygon", 16, 500_000, scene_shape="sdHorseshoe", polygon=poly)
+
+
+def test_full_size_properties_config4m_mesh_500k(oracle_mod):
+    """BASELINE config 4 through the triangle-mesh functor (getonlySDF_igl): the reference's shapes/star.obj (152 v / 300 f),
+    N = 16, 500 000 points — the float winding-number hierarchy and the pruned closest-triangle search at full size."""
+    g = np.load(os.path.join(HERE, "golden", "fwn_ref.npz"))
+    _full_size_check(oracle_mod, "star_obj_mesh_sdf", 16, 500_000, mesh=(g["star_V"], g["star_F"]), scene_shape="sdHorseshoe", spot=800)

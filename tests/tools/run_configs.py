@@ -4,7 +4,7 @@
   config 2: star, N=8, 200k points      (bench.py's workload; here: cost+grad and a full L-BFGS run, GPU and CPU)
   config 3: sdHorseshoe, N=16, 500k points
   config 4m: the reference's shapes/star.obj (152 v / 300 f, tests/golden/fwn_ref.npz) through the triangle-mesh functor
-            (BasicShape::getonlySDF_igl restated exactly), N=16, 500k
+            (BasicShape::getonlySDF_igl: the reference's float winding-number hierarchy reproduced bit for bit + exact closest triangle), N=16, 500k
   config 4: mesh shape: outline of the reference's shapes/star.obj (40 vertices) through the Polygon fallback functor (what this
             release of the reference uses for non-analytic shapes; the libigl path is unreachable there), N=16, 500k
 """
@@ -73,7 +73,7 @@ if __name__ == "__main__":
     if "1" in which: run("1", "star", 8, 2000, 2.75, 2000)
     if "2" in which: run("2", "star", 8, 200_000, 2.75, 50_000)
     if "3" in which: run("3", "sdHorseshoe", 16, 500_000, 2.15, 50_000)
-    if "4m" in which:  # the same mesh through the triangle-mesh functor (getonlySDF_igl restated exactly)
+    if "4m" in which:  # the same mesh through the triangle-mesh functor (getonlySDF_igl)
         g = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "golden", "fwn_ref.npz"))
         P4 = int(os.environ.get("SVSDF_MESH_P", "500000"))
         run("4m", "star_obj_mesh_sdf", 16, P4, 2.75, 3000, lbfgs_iters=int(os.environ.get("SVSDF_MESH_LBFGS", "4")), scene_shape="sdHorseshoe",
