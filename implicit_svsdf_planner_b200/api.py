@@ -48,6 +48,15 @@ class _Config(C.Structure):
     ]
 
 
+class MidConfig(C.Structure):
+    """svsdf_mid_config: the yaml keys OriTraj::setParam reads (mid_end.hpp:333-359)."""
+    _fields_ = [("rho_mid_end", C.c_double), ("vmax", C.c_double), ("omgmax", C.c_double), ("weight_v", C.c_double), ("weight_omg", C.c_double),
+                ("weight_pr", C.c_double), ("weight_ar", C.c_double), ("smoothingEps", C.c_double), ("integralIntervs", C.c_int),
+                ("vehicleMass", C.c_double), ("gravAcc", C.c_double), ("horizDrag", C.c_double), ("vertDrag", C.c_double), ("parasDrag", C.c_double),
+                ("speedEps", C.c_double), ("mem_size", C.c_int), ("past", C.c_int), ("min_step", C.c_double), ("g_epsilon", C.c_double),
+                ("relCostTolMidEnd", C.c_double), ("max_iterations", C.c_int), ("cancel_after", C.c_int)]
+
+
 class LbfgsParams(C.Structure):
     _fields_ = [
         ("mem_size", C.c_int),
@@ -88,7 +97,8 @@ EXPORTED_SYMBOLS = [
     "svsdf_optimize", "svsdf_optimize_batch", "svsdf_cost_grad_batch", "svsdf_minco_forward", "svsdf_minco_propagate", "svsdf_forward_T", "svsdf_backward_T",
     "svsdf_shape_sdf", "svsdf_shape_grad1", "svsdf_cost_grad_device", "svsdf_kernel_launches",
     "svsdf_executed_evals", "svsdf_fp64_peak", "svsdf_device_ptr_points", "svsdf_lbfgs_minimize", "svsdf_last_kernel_ms", "svsdf_sincos", "svsdf_set_map", "svsdf_set_map_device",
-    "svsdf_extract_points", "svsdf_extract_points3d", "svsdf_set_map3d", "svsdf_get_points", "svsdf_read_obj", "svsdf_free", "svsdf_mesh_fwn_host",
+    "svsdf_extract_points", "svsdf_extract_points3d", "svsdf_set_map3d", "svsdf_get_points",
+    "svsdf_mid_default_config", "svsdf_mid_cost", "svsdf_mid_get_ori_traj", "svsdf_read_obj", "svsdf_free", "svsdf_mesh_fwn_host",
     "svsdf_front_init", "svsdf_front_get_kernels", "svsdf_front_cspace", "svsdf_front_check_kernel_value", "svsdf_front_expand", "svsdf_front_astar",
 ]
 
@@ -145,6 +155,10 @@ def lib():
     L.svsdf_extract_points.argtypes = [vp, dp, C.c_int, C.c_double, dp, C.c_int, C.c_double, C.POINTER(C.c_int64)]
     L.svsdf_extract_points3d.argtypes = [vp, dp, C.c_int, dp, dp, C.c_int, C.c_double, C.POINTER(C.c_int64)]
     L.svsdf_set_map3d.argtypes = [vp, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, dp, C.c_double]
+    L.svsdf_mid_default_config.argtypes = [C.POINTER(MidConfig)]
+    L.svsdf_mid_default_config.restype = None
+    L.svsdf_mid_cost.argtypes = [C.POINTER(MidConfig), C.c_int, dp, dp, dp, dp, dp, dp, dp]
+    L.svsdf_mid_get_ori_traj.argtypes = [C.POINTER(MidConfig), C.c_int, dp, dp, dp, dp, dp, dp, dp, dp, dp, C.POINTER(C.c_int)]
     L.svsdf_get_points.argtypes = [vp, dp, C.c_int64, C.POINTER(C.c_int64)]
     L.svsdf_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.svsdf_kernel_launches.argtypes = [vp, C.POINTER(C.c_int64)]
@@ -717,3 +731,53 @@ class TrajOptimizer:
     def optimize_traj(self, init_s, final_s, opt_x, N, params=None, progress=None):
         self.pieceN = N
         return self.ctx.optimize(init_s, final_s, opt_x, N, params, progress)
+
+
+# ---- mid end (host only): OriTraj::costFunction / getOriTraj ----
+def mid_default_config(**over) -> MidConfig:
+    c = MidConfig()
+    lib().svsdf_mid_default_config(C.byref(c))
+    for k, v in over.items():
+        setattr(c, k, v)
+    return c
+
+
+def _mid_args(init_s, final_s, Q, rot_list):
+    i_s = np.ascontiguousarray(np.asarray(init_s, dtype=np.float64).T).reshape(-1)   # 3x3 column-major
+    f_s = np.ascontiguousarray(np.asarray(final_s, dtype=np.float64).T).reshape(-1)
+    Q = np.asarray(Q, dtype=np.float64).reshape(3, -1)                               # 3 x (N - 1)
+    q = np.ascontiguousarray(Q.T).reshape(-1)                                        # column-major
+    R = np.asarray(rot_list, dtype=np.float64).reshape(-1, 3, 3)
+    r = np.ascontiguousarray(np.transpose(R, (0, 2, 1))).reshape(-1)                 # each 3x3 column-major
+    return i_s, f_s, q, r, Q.shape[1] + 1
+
+
+def mid_cost(init_s, final_s, Q, rot_list, x, cfg: MidConfig = None):
+    """OriTraj::costFunction: (cost, gradient) at x = [tau, xi]."""
+    cfg = cfg or mid_default_config()
+    i_s, f_s, q, r, N = _mid_args(init_s, final_s, Q, rot_list)
+    x = _f64(x).reshape(-1)
+    assert x.size == N + 3 * (N - 1) and r.size == 9 * (N - 1)
+    cost = C.c_double()
+    g = np.zeros_like(x)
+    rc = lib().svsdf_mid_cost(C.byref(cfg), N, _p(i_s), _p(f_s), _p(q), _p(r), _p(x), C.byref(cost), _p(g))
+    if rc != 0:
+        raise SvsdfError(f"svsdf_mid_cost failed with {rc}")
+    return cost.value, g
+
+
+def mid_get_ori_traj(init_s, final_s, Q, T_init, rot_list, cfg: MidConfig = None):
+    """OriTraj::getOriTraj: (status, opt_x, T, coeffs [6N, 3], final_cost, iterations)."""
+    cfg = cfg or mid_default_config()
+    i_s, f_s, q, r, N = _mid_args(init_s, final_s, Q, rot_list)
+    T0 = _f64(T_init).reshape(-1)
+    assert T0.size == N
+    x = np.zeros(N + 3 * (N - 1))
+    T = np.zeros(N)
+    co = np.zeros(18 * N)
+    fc = C.c_double()
+    it = C.c_int()
+    rc = lib().svsdf_mid_get_ori_traj(C.byref(cfg), N, _p(i_s), _p(f_s), _p(q), _p(T0), _p(r), _p(x), _p(T), _p(co), C.byref(fc), C.byref(it))
+    if rc < 0 and rc > -1000:
+        raise SvsdfError(f"svsdf_mid_get_ori_traj failed with {rc}")
+    return rc, x, T, co.reshape(3, 6 * N).T.copy(), fc.value, it.value

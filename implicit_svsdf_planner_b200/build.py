@@ -42,6 +42,7 @@ HEADERS = [
     "host/lbfgs.hpp",
     "host/astar.hpp",
     "host/fwn_bvh.hpp",
+    "host/mid_end.hpp",
     "../../include/svsdf.h",
 ]
 

@@ -23,6 +23,7 @@
 #include "../../include/svsdf.h"
 #include "host/astar.hpp"
 #include "host/fwn_bvh.hpp"
+#include "host/mid_end.hpp"
 #include "host/lbfgs.hpp"
 #include "host/minco.hpp"
 #include "svsdf_launch.h"
@@ -624,6 +625,50 @@ int svsdf_mesh_fwn_host(const double *vertices, int nv, const int32_t *faces, in
 }
 
 void svsdf_free(void *p) { std::free(p); }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// mid end (host/mid_end.hpp): OriTraj's cost function and warm-start optimisation, host only
+// ---------------------------------------------------------------------------------------------------------------------
+void svsdf_mid_default_config(svsdf_mid_config *c) {
+    if (!c) return;
+    const host::MidEndConfig d;
+    c->rho_mid_end = d.rho_mid_end; c->vmax = d.vmax; c->omgmax = d.omgmax; c->weight_v = d.weight_v; c->weight_omg = d.weight_omg;
+    c->weight_pr = d.weight_pr; c->weight_ar = d.weight_ar; c->smoothingEps = d.smoothingEps; c->integralIntervs = d.integralIntervs;
+    c->vehicleMass = d.vehicleMass; c->gravAcc = d.gravAcc; c->horizDrag = d.horizDrag; c->vertDrag = d.vertDrag; c->parasDrag = d.parasDrag;
+    c->speedEps = d.speedEps; c->mem_size = d.mem_size; c->past = d.past; c->min_step = d.min_step; c->g_epsilon = d.g_epsilon;
+    c->relCostTolMidEnd = d.relCostTolMidEnd; c->max_iterations = d.max_iterations; c->cancel_after = d.cancel_after;
+}
+static host::MidEndConfig mid_cfg(const svsdf_mid_config *c) {
+    host::MidEndConfig d;
+    if (!c) return d;
+    d.rho_mid_end = c->rho_mid_end; d.vmax = c->vmax; d.omgmax = c->omgmax; d.weight_v = c->weight_v; d.weight_omg = c->weight_omg;
+    d.weight_pr = c->weight_pr; d.weight_ar = c->weight_ar; d.smoothingEps = c->smoothingEps; d.integralIntervs = c->integralIntervs;
+    d.vehicleMass = c->vehicleMass; d.gravAcc = c->gravAcc; d.horizDrag = c->horizDrag; d.vertDrag = c->vertDrag; d.parasDrag = c->parasDrag;
+    d.speedEps = c->speedEps; d.mem_size = c->mem_size; d.past = c->past; d.min_step = c->min_step; d.g_epsilon = c->g_epsilon;
+    d.relCostTolMidEnd = c->relCostTolMidEnd; d.max_iterations = c->max_iterations; d.cancel_after = c->cancel_after;
+    return d;
+}
+static bool mid_args_ok(const svsdf_mid_config *c, int N, const double *initS, const double *finalS, const double *Q, const double *rot) {
+    return N >= 2 && N <= kMaxPieces && initS && finalS && Q && rot && (!c || (c->integralIntervs >= 1 && c->smoothingEps > 0.0 && c->vehicleMass > 0.0));
+}
+int svsdf_mid_cost(const svsdf_mid_config *cfg, int N, const double *initS, const double *finalS, const double *Q, const double *rot_list,
+                   const double *x, double *cost_out, double *grad_out) {
+    if (!mid_args_ok(cfg, N, initS, finalS, Q, rot_list) || !x || !cost_out || !grad_out) return SVSDF_ERR_INVALID;
+    host::MidEnd M(mid_cfg(cfg));
+    M.setup(initS, finalS, N, Q, rot_list);
+    *cost_out = M.cost(x, grad_out);
+    return SVSDF_OK;
+}
+int svsdf_mid_get_ori_traj(const svsdf_mid_config *cfg, int N, const double *initS, const double *finalS, const double *Q,
+                           const double *T_init, const double *rot_list, double *opt_x_out, double *T_out, double *coeffs_out,
+                           double *final_cost_out, int *iterations_out) {
+    if (!mid_args_ok(cfg, N, initS, finalS, Q, rot_list) || !T_init || !opt_x_out) return SVSDF_ERR_INVALID;
+    for (int i = 0; i < N; ++i)
+        if (!(T_init[i] > 0.0)) return SVSDF_ERR_INVALID;
+    host::MidEnd M(mid_cfg(cfg));
+    M.setup(initS, finalS, N, Q, rot_list);
+    return M.optimize(T_init, opt_x_out, T_out, coeffs_out, final_cost_out, iterations_out);
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // K5: collision kernels of the A* front end (csrc/svsdf_frontend.cu)

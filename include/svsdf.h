@@ -192,6 +192,32 @@ int svsdf_shape_grad1(svsdf_ctx *ctx, int64_t n, const double *rel, double *grad
 int svsdf_cost_grad_device(svsdf_ctx *ctx, int N, const double *T, const double *coeffs, int repeats,
                            float *ms_per_eval, double *out_host);
 
+/* ---- Mid end (host only, no GPU and no context) ---------------------------------------------------------
+ * OriTraj (src/planner_algorithm/include/planner_algorithm/mid_end.hpp, src/mid_end.cpp): the warm-start optimisation between the A*
+ * front end and the SVSDF back end — MINCO energy + cubic pull of the inner waypoints towards their A* cells + trapezoid integral of
+ * the velocity / body-rate / attitude penalties through the multicopter flatness map (utils/flatness.hpp) + rho * sum(T).
+ * svsdf_mid_config mirrors the yaml keys OriTraj::setParam reads; svsdf_mid_default_config fills config/star.yaml's values.
+ * Layouts: initS / finalS 3x3 column-major; Q 3 x (N - 1) column-major (inner waypoints); rot_list (N - 1) rotation matrices, 3x3
+ * column-major each (recent_se3_path[ind].getRotMatrix(), plan_manager.cpp:159); x = [tau (N), xi (3 (N - 1))]. */
+typedef struct {
+    double rho_mid_end, vmax, omgmax, weight_v, weight_omg, weight_pr, weight_ar, smoothingEps;
+    int integralIntervs;
+    double vehicleMass, gravAcc, horizDrag, vertDrag, parasDrag, speedEps;
+    int mem_size, past;
+    double min_step, g_epsilon, relCostTolMidEnd;
+    int max_iterations, cancel_after; /* mid_end.cpp:51 (10000) and earlyExit's `k > 1e2` (mid_end.hpp:626) */
+} svsdf_mid_config;
+void svsdf_mid_default_config(svsdf_mid_config *cfg);
+/* OriTraj::costFunction (mid_end.hpp:277-325): cost and gradient at x. */
+int svsdf_mid_cost(const svsdf_mid_config *cfg, int N, const double *initS, const double *finalS, const double *Q, const double *rot_list,
+                   const double *x, double *cost_out, double *grad_out);
+/* OriTraj::getOriTraj (mid_end.cpp:3-92): T_init = config.inittime * ones(N) in the reference.  Returns the solver status (>= 0 success,
+ * 2 = stopped by the `k > cancel_after` rule); opt_x_out [N + 3 (N - 1)] is what the back end starts from (plan_manager.cpp:192-199),
+ * T_out [N], coeffs_out [18 N] (column-major 6N x 3) the resulting spline. */
+int svsdf_mid_get_ori_traj(const svsdf_mid_config *cfg, int N, const double *initS, const double *finalS, const double *Q,
+                           const double *T_init, const double *rot_list, double *opt_x_out, double *T_out, double *coeffs_out,
+                           double *final_cost_out, int *iterations_out);
+
 /* ---- Batch variants (leading problem dimension; BASELINE config 5) -----------------------------------
  * Independent problems are spread over a POOL of contexts (one worker thread per context; several contexts may sit on the
  * same GPU — each has its own stream, so the host side of one problem (MINCO, line search) and the latency-bound tail of its
