@@ -206,6 +206,29 @@ def extract(ref: str, out: str) -> None:
     ]
     files["opt_methods.inc"] = "".join(opt)
 
+    # ---- mid end (OriTraj): mid_end.hpp member functions + getOriTraj from mid_end.cpp; utils/flatness.hpp, utils/lbfgs.hpp and
+    # utils/minco.hpp are included whole by oracle/ref_mid_shim.cpp ----
+    mid = Source(os.path.join(ref, "src/planner_algorithm/include/planner_algorithm/mid_end.hpp"))
+    files["mid_methods.inc"] = "".join([
+        mid.block(r"^\s*static inline bool smoothedL1\(const double &x,", expect_lines=(60, 92)),
+        mid.block(r"^\s*static inline void forwardP\(const Eigen::VectorXd &xi,", expect_lines=(88, 104)),
+        mid.block(r"^\s*static inline void backwardP\(const Eigen::Matrix3Xd &P,", expect_lines=(100, 116)),
+        mid.block(r"^\s*static inline void forwardT\(const Eigen::VectorXd &tau,", expect_lines=(112, 130)),
+        mid.block(r"^\s*static inline void backwardT\(const Eigen::VectorXd &T,", expect_lines=(126, 146)),
+        mid.block(r"^\s*static inline void backwardGradT\(const Eigen::VectorXd &tau,", expect_lines=(140, 170)),
+        mid.block(r"^\s*static inline void backwardGradP\(const Eigen::VectorXd &xi,", expect_lines=(166, 184)),
+        mid.block(r"^\s*bool inline grad_cost_dir\(", expect_lines=(180, 212)),
+        mid.block(r"^\s*static inline void addPosePenalty \(", expect_lines=(210, 276)),
+        mid.block(r"^\s*static inline double costFunction\(void \*ptr,", expect_lines=(274, 328)),
+        mid.block(r"^\s*static inline double costaltitude\(", expect_lines=(370, 394)),
+        mid.block(r"^\s*static inline void gradaltitude\(", expect_lines=(390, 420)),
+        mid.block(r"^\s*static inline double WC2\(", expect_lines=(414, 436)),
+        mid.block(r"^\s*static inline void addTimeIntPenalty\(", expect_lines=(432, 606)),
+        mid.block(r"^\s*static inline int earlyExit\(void \*instance,", expect_lines=(598, 626)),
+    ])
+    midc = Source(os.path.join(ref, "src/planner_algorithm/src/mid_end.cpp"))
+    files["mid_getoritraj.inc"] = midc.block(r"^bool OriTraj::getOriTraj\(", expect_lines=(1, 95))
+
     for name, body in files.items():
         path = os.path.join(out, name)
         with open(path, "w", encoding="utf-8", errors="surrogateescape") as fh:

@@ -264,3 +264,45 @@ class RefPath:
         gP, gT = np.empty(3 * (N - 1)), np.empty(N)
         self.L.ref_minco_propagate(self.h, _p(gdC), _p(gdT), _p(gP), _p(gT))
         return gP.reshape(N - 1, 3).T.copy(), gT
+
+
+# ---- mid end: the reference's OriTraj (oracle/ref_mid_shim.cpp -> oracle/_ref/libref_mid.so) ----
+_MID = None
+
+
+def mid_available() -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", "libref_mid.so"))
+
+
+def _mid_lib():
+    global _MID
+    if _MID is None:
+        _MID = C.CDLL(os.path.join(_HERE, "_ref", "libref_mid.so"))
+    return _MID
+
+
+def mid_cost(cfg, N, init_cm, final_cm, Q_cm, rot_cm, x):
+    """OriTraj::costFunction of the reference.  cfg: a ctypes struct with svsdf_mid_config's layout; arrays flat, column-major as
+    the C ABI takes them."""
+    dp = C.POINTER(C.c_double)
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    x = f(x)
+    g = np.zeros_like(x)
+    cost = C.c_double()
+    a = [f(init_cm), f(final_cm), f(Q_cm), f(rot_cm)]
+    _mid_lib().ref_mid_cost(C.byref(cfg), C.c_int(N), *[v.ctypes.data_as(dp) for v in a], x.ctypes.data_as(dp), C.byref(cost), g.ctypes.data_as(dp))
+    return cost.value, g
+
+
+def mid_get_ori_traj(cfg, N, init_cm, final_cm, Q_cm, T_init, rot_cm):
+    """OriTraj::getOriTraj of the reference with its own patched L-BFGS: (ok, opt_x, T, coeffs [6N, 3], iterations)."""
+    dp = C.POINTER(C.c_double)
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    a = [f(init_cm), f(final_cm), f(Q_cm), f(T_init), f(rot_cm)]
+    x = np.zeros(N + 3 * (N - 1))
+    T = np.zeros(N)
+    co = np.zeros(18 * N)
+    it = C.c_int()
+    ok = _mid_lib().ref_mid_get_ori_traj(C.byref(cfg), C.c_int(N), *[v.ctypes.data_as(dp) for v in a], x.ctypes.data_as(dp), T.ctypes.data_as(dp),
+                                         co.ctypes.data_as(dp), C.byref(it))
+    return bool(ok), x, T, co.reshape(3, 6 * N).T.copy(), it.value
