@@ -81,6 +81,15 @@ def main():
         out[name + "_w_ref"] = ref_fwn(V, F, Q)
         out[name + "_tree_children"], out[name + "_tree_data"] = ref_fwn_tree(V, F)
     np.savez_compressed(os.path.join(HERE, "fwn_ref.npz"), **out)
+    # a deeper hierarchy (973 nodes over 2000 faces): shapes/sdArc.obj, own file and own stream so that fwn_ref.npz stays as it was
+    rng2 = np.random.Generator(np.random.MT19937(20240512))
+    V, F = scenes.load_obj(os.path.join(REF_SHAPES, "sdArc.obj"))
+    lo, hi = V.min(axis=0) - 1.5, V.max(axis=0) + 1.5
+    Q = np.zeros((3000, 3))
+    Q[:2000, :2] = rng2.uniform(lo[:2], hi[:2], size=(2000, 2))
+    Q[2000:] = rng2.uniform(lo, hi, size=(1000, 3))
+    np.savez_compressed(os.path.join(HERE, "fwn_ref_sdarc.npz"), sdArc_V=V, sdArc_F=F, sdArc_Q=Q, sdArc_w_ref=ref_fwn(V, F, Q),
+                        sdArc_tree_children=ref_fwn_tree(V, F)[0])
     for k, v in out.items():
         print(k, v.shape, v.dtype)
 

@@ -107,6 +107,19 @@ def test_portable_atan2f_is_the_c_library_atan2f(oracle_mod):
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
+def _fwn_gold(name):
+    g = np.load(os.path.join(HERE, "golden", "fwn_ref_sdarc.npz" if name == "sdArc" else "fwn_ref.npz"))
+    return g
+
+
+def test_deep_hierarchy_sdarc_2000_faces(oracle_mod):
+    """shapes/sdArc.obj: 2000 faces, 973 nodes — tree and winding numbers of the reference's compiled code, bit for bit."""
+    g = _fwn_gold("sdArc")
+    ch, data, w = api.mesh_fwn_host(g["sdArc_V"], g["sdArc_F"], g["sdArc_Q"])
+    assert np.array_equal(ch, g["sdArc_tree_children"]) and np.array_equal(w, g["sdArc_w_ref"])
+    assert np.array_equal(oracle_mod.mesh_eval((g["sdArc_V"], g["sdArc_F"]), g["sdArc_Q"][:500], "winding"), g["sdArc_w_ref"][:500])
+
+
 @pytest.mark.parametrize("name", ["star", "sdHorseshoe"])
 def test_winding_number_is_bitwise_the_reference_fwn_golden(oracle_mod, name):
     """w_ref, tree_children, tree_data were produced by the reference's own igl/HDK code on its own shapes/*.obj
