@@ -99,8 +99,16 @@ struct svsdf_ctx {
     double *d_q_points = nullptr, *d_q_sdf = nullptr, *d_q_ts = nullptr, *d_q_grad = nullptr;
     int *d_q_rounds = nullptr;
     int64_t cap_q = 0;
-    double *h_stage = nullptr;  // pinned staging for points upload / results download
+    double *h_stage = nullptr;  // pinned staging for results download and the small uploads of the other entry points
     size_t cap_stage = 0;
+    // svsdf_set_points has its own pinned stage and does NOT wait for its copies: the kernels that follow are ordered behind them
+    // on the context's stream, and the host goes on (builds the trajectory blob) while the DMA runs.  ev_pts marks the end of the
+    // last upload: the next svsdf_set_points (which overwrites the stage) and svsdf_device_ptr_points (which hands the buffer to
+    // other streams) wait on it.
+    double *h_pts_stage = nullptr;
+    size_t cap_pts_stage = 0;
+    cudaEvent_t ev_pts = nullptr;
+    bool pts_inflight = false;
 
     // packed map kernel (K3)
     unsigned char *d_map = nullptr;
@@ -1084,6 +1092,8 @@ void svsdf_destroy(svsdf_ctx *ctx) {
     if (ctx->h_blob) cudaFreeHost(ctx->h_blob);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->h_pts_stage) cudaFreeHost(ctx->h_pts_stage);
+    if (ctx->ev_pts) cudaEventDestroy(ctx->ev_pts);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (int k = 0; k < 5; ++k)
@@ -1110,9 +1120,22 @@ int svsdf_set_points(svsdf_ctx *ctx, const double *pts, int64_t P, int stride) {
         CK(cudaMalloc(&ctx->d_points, 1024 * 2 * sizeof(double)));
         ctx->cap_points = 1024;
     }
-    int rc = ensure_stage(ctx, (size_t)P * 2 * sizeof(double));
-    if (rc) return rc;
-    double *h = ctx->h_stage;
+    if (ctx->pts_inflight) {  // the previous upload still reads the stage
+        CK(cudaEventSynchronize(ctx->ev_pts));
+        ctx->pts_inflight = false;
+    }
+    if (!ctx->ev_pts) CK(cudaEventCreateWithFlags(&ctx->ev_pts, cudaEventDisableTiming));
+    const size_t need = (size_t)P * 2 * sizeof(double);
+    if (need > ctx->cap_pts_stage) {
+        if (ctx->h_pts_stage) cudaFreeHost(ctx->h_pts_stage);
+        ctx->h_pts_stage = nullptr;
+        ctx->cap_pts_stage = 0;
+        const size_t cap = need + need / 4 + 4096;
+        CK(cudaMallocHost(&ctx->h_pts_stage, cap));
+        ctx->cap_pts_stage = cap;
+    }
+    int rc = SVSDF_OK;
+    double *h = ctx->h_pts_stage;
     // pos_eva(2) = 0 (back_end_optimizer.hpp:791): only x, y are kept.  Packed into the pinned stage chunk by chunk by a few
     // host threads; every chunk is handed to the copy engine as soon as it is packed (packing of the next chunks overlaps the
     // DMA of the finished ones).  One thread for small inputs.
@@ -1153,9 +1176,11 @@ int svsdf_set_points(svsdf_ctx *ctx, const double *pts, int64_t P, int stride) {
         ctx->err = std::string("svsdf_set_points: cudaMemcpyAsync: ") + cudaGetErrorString((cudaError_t)first_err);
         return SVSDF_ERR_CUDA;
     }
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventRecord(ctx->ev_pts, ctx->stream));  // no wait here: see ev_pts
+    ctx->pts_inflight = true;
     ctx->P = P;
     ctx->last_n_inside = -1;
+    (void)rc;
     return ensure_scratch(ctx, P);
 }
 
@@ -1172,6 +1197,11 @@ int svsdf_set_points_device(svsdf_ctx *ctx, const double *dev_xy, int64_t P) {
 
 int svsdf_device_ptr_points(svsdf_ctx *ctx, const double **dev_xy) {
     if (!ctx || !dev_xy) return SVSDF_ERR_INVALID;
+    if (ctx->pts_inflight) {  // the pointer may be used on other streams: the upload has to be complete
+        CK(cudaSetDevice(ctx->device));
+        CK(cudaEventSynchronize(ctx->ev_pts));
+        ctx->pts_inflight = false;
+    }
     *dev_xy = ctx->d_points;
     return SVSDF_OK;
 }

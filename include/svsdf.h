@@ -98,7 +98,9 @@ int svsdf_mesh_fwn_host(const double *vertices, int nv, const int32_t *faces, in
 void svsdf_free(void *p);
 
 /* R6: parallel_points.  pts: P rows of `stride` doubles (x, y, [z ...]); z is ignored like the reference
- * does (back_end_optimizer.hpp:791).  Copies to device memory (host -> device inside this call). */
+ * does (back_end_optimizer.hpp:791).  `pts` is consumed before the call returns (packed into pinned memory by a few host threads, chunk
+ * by chunk, each chunk handed to the copy engine at once); the call does not wait for the host -> device transfer itself: whatever is
+ * called next on this context runs behind it on the context's stream. */
 int svsdf_set_points(svsdf_ctx *ctx, const double *pts, int64_t P, int stride);
 /* Same, but the points already live on the device as packed (x, y) pairs; no copy is made of host data. */
 int svsdf_set_points_device(svsdf_ctx *ctx, const double *dev_xy, int64_t P);
