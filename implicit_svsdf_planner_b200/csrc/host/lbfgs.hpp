@@ -25,6 +25,11 @@ struct LbfgsParams {
     double cautious_factor = 1.0e-6;
     double machine_prec = 1.0e-16;
     int nonsmooth_restarts = 0;   // see svsdf_lbfgs_params
+    // 1: behave like the reference's patched utils/lbfgs.hpp (the solver of its mid end): the line search accepts on the Armijo
+    // condition alone (the weak-Wolfe branch is `if (0)`, lbfgs.hpp:375) and a quasi-Newton direction with |d| >= 0.04 or d.g > 0 —
+    // or a skipped cautious update — is replaced by -g scaled to the previous direction's length after one more evaluation at the
+    // same point (lbfgs.hpp:759-779).
+    int reference_patch = 0;
 };
 
 enum LbfgsCode {
@@ -92,6 +97,7 @@ class Lbfgs {
         } else {
             double step = 1.0 / std::sqrt(dotp(d.data(), d.data(), n));
             int head = 0, stored = 0, restarts = 0;
+            double olddnorm = 1.0;
             k = 1;
             for (;;) {
                 std::copy(x, x + n, xp.begin());
@@ -157,7 +163,15 @@ class Lbfgs {
                         axpy(alpha[j] - beta, &S[(size_t)j * n], d.data(), n);
                         j = (j + 1) % m;
                     }
+                    // (`!(|d| < 0.04)` rather than the reference's `|d| >= 0.04`: a non-finite direction — a stored pair with y.s == 0
+                    // once the iterates stop moving — also takes the fallback instead of ending the run with a NaN cost)
+                    if (P.reference_patch && (!(std::sqrt(dotp(d.data(), d.data(), n)) < 0.04) || dotp(d.data(), g.data(), n) > 0))
+                        steepest_with_old_norm(x, n, eval, inst, R.evaluations, olddnorm);
+                } else if (P.reference_patch) {
+                    steepest_with_old_norm(x, n, eval, inst, R.evaluations, olddnorm);
+                    head = (head + 1) % m;  // the slot just written is skipped without counting as stored (lbfgs.hpp:776)
                 }
+                if (P.reference_patch) olddnorm = std::sqrt(dotp(d.data(), d.data(), n));
                 step = 1.0;
             }
         }
@@ -194,6 +208,20 @@ class Lbfgs {
         for (int i = 0; i < n; ++i) r = std::max(r, std::fabs(a[i]));
         return r;
     }
+    // the reference's fallback direction: re-evaluate at x (its own callback returns the same gradient again), d = -g / |g| * |d_prev|
+    void steepest_with_old_norm(const double *x, int n, lbfgs_eval_fn eval, void *inst, int &evals, double olddnorm) {
+        gp_scratch.assign(n, 0.0);
+        (void)eval(inst, x, gp_scratch.data(), n);
+        ++evals;
+        g = gp_scratch;
+        for (int i = 0; i < n; ++i) d[i] = -g[i];
+        const double z = dotp(d.data(), d.data(), n);
+        if (z > 0) {
+            const double nn = std::sqrt(z);
+            for (int i = 0; i < n; ++i) d[i] /= nn;
+        }
+        for (int i = 0; i < n; ++i) d[i] *= olddnorm;
+    }
     // Lewis–Overton: Armijo + weak Wolfe by bisection / doubling.
     int line_search(double *x, int n, double &f, double &stp, double stpmin, double stpmax, lbfgs_eval_fn eval,
                     void *inst, int &evals) {
@@ -211,7 +239,7 @@ class Lbfgs {
             if (f > finit + stp * dgtest) {
                 hi = stp;
                 bracketed = true;
-            } else if (dotp(g.data(), d.data(), n) < dstest) {
+            } else if (!P.reference_patch && dotp(g.data(), d.data(), n) < dstest) {
                 lo = stp;
             } else {
                 return count;
@@ -229,7 +257,7 @@ class Lbfgs {
     }
 
     LbfgsParams P;
-    std::vector<double> xp, g, gp, d, pf, S, Y, ys_hist, alpha;
+    std::vector<double> xp, g, gp, d, pf, S, Y, ys_hist, alpha, gp_scratch;
 
 };
 

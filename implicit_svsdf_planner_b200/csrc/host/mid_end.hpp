@@ -35,6 +35,7 @@ struct MidEndConfig {
     int mem_size = 16, past = 64;
     double min_step = 1.0e-32, g_epsilon = 0.0, relCostTolMidEnd = 1.0e-10;
     int max_iterations = 10000, cancel_after = 100;  // earlyExit: `return k > 1e2` (mid_end.hpp:610-627)
+    int solver = 0;  // 0: the reference's patched L-BFGS behaviour (same warm start as the reference); 1: this build's L-BFGS
 };
 
 // flatness.hpp:53-263.  forward() keeps its intermediates for backward(), exactly like the reference object.
@@ -341,7 +342,8 @@ class MidEnd {
         lp.g_epsilon = cfg.g_epsilon;
         lp.delta = cfg.relCostTolMidEnd;
         lp.max_iterations = cfg.max_iterations;
-        lp.nonsmooth_restarts = 8;  // C^1 only (WC2 window, cubic pull): a failed line search restarts from steepest descent, then status 3
+        lp.reference_patch = cfg.solver == 0 ? 1 : 0;
+        lp.nonsmooth_restarts = cfg.solver == 0 ? 0 : 8;  // own solver: a failed line search restarts from steepest descent, then status 3
         Lbfgs solver(lp);
         struct Hook { MidEnd *self; int cancel_after; int iters; } hook{this, cfg.cancel_after, 0};
         const LbfgsResult R = solver.minimize(

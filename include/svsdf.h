@@ -208,6 +208,8 @@ typedef struct {
     int mem_size, past;
     double min_step, g_epsilon, relCostTolMidEnd;
     int max_iterations, cancel_after; /* mid_end.cpp:51 (10000) and earlyExit's `k > 1e2` (mid_end.hpp:626) */
+    int solver;                       /* 0: the reference's patched L-BFGS behaviour (utils/lbfgs.hpp:375, 759-779) — the same warm start as
+                                         the reference; 1: this build's L-BFGS (Lewis-Overton line search, restarts) — converges further */
 } svsdf_mid_config;
 void svsdf_mid_default_config(svsdf_mid_config *cfg);
 /* OriTraj::costFunction (mid_end.hpp:277-325): cost and gradient at x. */

@@ -91,7 +91,7 @@ struct MidCfg {  // == svsdf_mid_config (include/svsdf.h)
     double vehicleMass, gravAcc, horizDrag, vertDrag, parasDrag, speedEps;
     int mem_size, past;
     double min_step, g_epsilon, relCostTolMidEnd;
-    int max_iterations, cancel_after;
+    int max_iterations, cancel_after, solver;
 };
 void configure(OriTraj &o, const MidCfg &c) {  // OriTraj::setParam (mid_end.hpp:333-359) without the ROS lines
     o.weightPR = c.weight_pr; o.weightAR = c.weight_ar; o.rho = c.rho_mid_end; o.vmax = c.vmax; o.omgmax = c.omgmax;

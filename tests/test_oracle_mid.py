@@ -51,29 +51,44 @@ def test_gradient_is_the_derivative_of_the_cost():
 
 @pytest.mark.parametrize("cname", list(mk.CONFIGS))
 @pytest.mark.parametrize("N", [2, 3, 6, 12])
-def test_warm_start_reaches_what_the_reference_reaches(gold, cname, N):
-    """getOriTraj: the reference runs its patched L-BFGS and stops it after 100 iterations (earlyExit: k > 1e2); this build runs its own
-    L-BFGS under the same rule.  Both minimise the same function from the same start: the result here must be at least as good as the
-    reference's (its cost evaluated by THIS cost function, which equals the reference's to 1e-13), and where both have converged the
-    durations agree."""
+def test_warm_start_is_the_reference_warm_start(gold, cname, N):
+    """getOriTraj with solver = 0 (default): the reference's patched L-BFGS behaviour (Armijo-only line search, quasi-Newton directions
+    of length >= 0.04 replaced by -g at the previous direction's length, stop after 100 iterations) restated in host/lbfgs.hpp.  Same
+    function, same rules: the iterates follow the reference's for 100 iterations — opt_x agrees to 1e-8 or better in 7 of the 8 golden
+    cases; in one the two runs part at a rounding-level accept / reject decision late in the run and end 2e-3 apart in x, 1.3e-5 in cost."""
     k = f"{cname}_N{N}_"
     cfg = api.mid_default_config(**mk.CONFIGS[cname])
+    assert cfg.solver == 0
     args = (gold[k + "init_s"], gold[k + "final_s"], gold[k + "Q"])
     rc, x, T, co, fc, it = api.mid_get_ori_traj(*args, np.ones(N), gold[k + "rots"], cfg)
-    assert rc >= 0 and it <= 101 and np.all(T > 0) and np.all(np.isfinite(co))
+    assert rc >= 0 and it == int(gold[k + "iterations"]) == 101
     c_ref, _ = api.mid_cost(*args, gold[k + "rots"], gold[k + "opt_x"], cfg)
-    c_own, g_own = api.mid_cost(*args, gold[k + "rots"], x, cfg)
-    assert abs(c_own - fc) <= 1e-12 * abs(fc)
-    assert fc <= c_ref * (1.0 + 1e-6), (fc, c_ref)
-    if abs(fc - c_ref) <= 1e-9 * abs(c_ref):  # both at the minimum
-        assert np.abs(T - gold[k + "T"]).max() <= 1e-5 * T.max()
+    dx = np.abs(x - gold[k + "opt_x"]).max()
+    assert dx <= 1e-6 or abs(fc - c_ref) <= 1e-4 * abs(c_ref), (dx, fc, c_ref)
+    assert abs(fc - c_ref) <= 1e-4 * abs(c_ref)
+    if dx <= 1e-6:
+        assert np.abs(T - gold[k + "T"]).max() <= 1e-6 and np.abs(co - gold[k + "coeffs"]).max() <= 1e-5 * np.abs(co).max()
     # the spline returned is the one of (T, inner points): boundary states and waypoints are interpolated
-    n6 = 6 * N
+    assert co.shape == (6 * N, 3)
     assert np.allclose(co[0], gold[k + "init_s"][:, 0]) and np.allclose(co[1], gold[k + "init_s"][:, 1])
     P = x[N:].reshape(N - 1, 3)
     for i in range(N - 1):
         assert np.allclose(co[6 * (i + 1)], P[i], atol=1e-9)
-    assert co.shape == (n6, 3)
+
+
+@pytest.mark.parametrize("cname", list(mk.CONFIGS))
+@pytest.mark.parametrize("N", [2, 3, 6, 12])
+def test_own_solver_reaches_at_least_what_the_reference_reaches(gold, cname, N):
+    """solver = 1: this build's L-BFGS (weak-Wolfe line search, restarts) under the same 100-iteration rule — never worse than the
+    reference's result (evaluated by the same cost function), usually converged well before the limit."""
+    k = f"{cname}_N{N}_"
+    cfg = api.mid_default_config(solver=1, **mk.CONFIGS[cname])
+    args = (gold[k + "init_s"], gold[k + "final_s"], gold[k + "Q"])
+    rc, x, T, co, fc, it = api.mid_get_ori_traj(*args, np.ones(N), gold[k + "rots"], cfg)
+    assert rc >= 0 and it <= 101 and np.all(T > 0) and np.all(np.isfinite(co))
+    c_ref, _ = api.mid_cost(*args, gold[k + "rots"], gold[k + "opt_x"], cfg)
+    c_own, _ = api.mid_cost(*args, gold[k + "rots"], x, cfg)
+    assert abs(c_own - fc) <= 1e-12 * abs(fc) and fc <= c_ref * (1.0 + 1e-6), (fc, c_ref)
 
 
 def test_live_reference_library_when_present(gold):
