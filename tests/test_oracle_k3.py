@@ -86,3 +86,23 @@ def test_packed_kernels_and_the_flat_case_agree_with_the_product_packing():
     gm1 = k3.gridmap_2d(occ[:, :, 0], gm.boundary_min[:2], 0.5)
     full = k3.query_points(gm1, np.c_[wps, np.full(3, 0.25)], [1.2] * 3)
     assert len(flat) == len(full) and {tuple(np.round(p[:2], 9)) for p in flat} == {tuple(np.round(p[:2], 9)) for p in full}
+
+
+def test_product_host_glue_of_the_plan_chain_equals_the_restatement():
+    """implicit_svsdf_planner_b200/plan.py (the product's numpy glue for one whole plan): map from cloud, 3-D packed map, waypoint rule."""
+    from implicit_svsdf_planner_b200 import plan
+
+    g, gm = star_map()
+    cm = plan.gridmap3d_from_cloud(g["points"], float(g["occupancy_resolution"]), int(g["sta_threshold"]))
+    assert np.array_equal(cm.occ, gm.occ) and np.array_equal(cm.boundary_min, gm.boundary_min) and np.array_equal(cm.boundary_max, gm.boundary_max)
+    assert np.array_equal(plan.pack_map_kernel3d(cm.occ, 17), k3.generate_map_kernel(gm, 17))
+    rng = np.random.default_rng(4)
+    for n in (3, 4, 7, 20, 64):
+        path = rng.uniform(0, 30, size=(n, 3))
+        for L, res in ((3.0, 1.0), (3.0, 0.25), (0.7, 1.0)):
+            idx, w = plan.waypoints_of_path(path, L, res)
+            assert np.array_equal(w, k3.waypoints_of_path(path, L, res)) and np.array_equal(path[idx], w)
+    # sta_threshold > 1: only voxels hit by several points stay
+    cm2 = plan.gridmap3d_from_cloud(g["points"], 1.0, 2)
+    gm2 = k3.gridmap_from_cloud(g["points"], 1.0, 2)
+    assert np.array_equal(cm2.occ, gm2.occ) and cm2.occ.sum() < cm.occ.sum()
