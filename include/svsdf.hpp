@@ -232,4 +232,38 @@ class TrajOptimizer {
     SweptVolumeManager::Ptr sv_manager;
 };
 
+// Mid end (planner_algorithm/mid_end.hpp, src/mid_end.cpp): host only, no context.
+class OriTraj {
+   public:
+    typedef std::shared_ptr<OriTraj> Ptr;
+    svsdf_mid_config conf;  // the yaml keys OriTraj::setParam reads (mid_end.hpp:333-359); defaults = config/star.yaml
+    double final_cost = 0.0;
+    int iter = 0;
+
+    OriTraj() { svsdf_mid_default_config(&conf); }
+    void setParam(const svsdf_mid_config &config) { conf = config; }
+
+    // getOriTraj(initS, finalS, Q, T, acc_list, rot_list, N, traj, opt_x) (mid_end.cpp:3-92).  Q: N - 1 waypoints; rot_list: N - 1
+    // rotation matrices, 3x3 column-major each; acc_list is unused by the reference's cost and not taken.  Returns true on
+    // success like the reference (solver status >= 0); opt_x, traj_T and traj_coeffs are written either way.
+    bool getOriTraj(const double *initS, const double *finalS, const std::vector<std::array<double, 3>> &Q, const std::vector<double> &T,
+                    const std::vector<std::array<double, 9>> &rot_list, const int N, std::vector<double> &traj_T, std::vector<double> &traj_coeffs,
+                    std::vector<double> &opt_x) {
+        if ((int)Q.size() != N - 1 || (int)rot_list.size() != N - 1 || (int)T.size() != N) return false;
+        opt_x.assign(N + 3 * (size_t)(N - 1), 0.0);
+        traj_T.assign(N, 0.0);
+        traj_coeffs.assign(18 * (size_t)N, 0.0);
+        const int ret = svsdf_mid_get_ori_traj(&conf, N, initS, finalS, N > 1 ? Q[0].data() : nullptr, T.data(), N > 1 ? rot_list[0].data() : nullptr,
+                                               opt_x.data(), traj_T.data(), traj_coeffs.data(), &final_cost, &iter);
+        return ret >= 0;
+    }
+    // costFunction(ptr, x, g, p_cost) (mid_end.hpp:277-325) for callers that bring their own solver
+    double costFunction(const double *initS, const double *finalS, const std::vector<std::array<double, 3>> &Q,
+                        const std::vector<std::array<double, 9>> &rot_list, const int N, const double *x, double *g) const {
+        double c = 0.0;
+        svsdf_mid_cost(&conf, N, initS, finalS, Q[0].data(), rot_list[0].data(), x, &c, g);
+        return c;
+    }
+};
+
 }  // namespace svsdf

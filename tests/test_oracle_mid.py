@@ -115,3 +115,31 @@ def test_mid_end_argument_checks():
         api.mid_cost(init_s, final_s, Q, rots, x, api.mid_default_config(integralIntervs=0))
     with pytest.raises(api.SvsdfError):
         api.mid_get_ori_traj(init_s, final_s, Q, np.array([1.0, -1.0, 1.0]), rots)
+
+
+def test_cpp_mirror_of_the_mid_end_runs_without_a_gpu(tmp_path):
+    """include/svsdf.hpp: svsdf::OriTraj over the C ABI, driven by tests/cpp/mid_main.cpp like plan_manager.cpp:176-192 drives the
+    original; linked against the shipped library, executed on the host (the mid end needs no GPU)."""
+    import subprocess
+
+    from implicit_svsdf_planner_b200 import build
+
+    root = os.path.dirname(HERE)
+    so = build.build()
+    exe = str(tmp_path / "mid_main")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "cpp", "mid_main.cpp"),
+                           so, "-Wl,-rpath," + os.path.dirname(so), "-o", exe])
+    N = 6
+    init_s, final_s, Q, rots, _ = mk.problem(N, 42)
+    i_s, f_s, q, r, _ = api._mid_args(init_s, final_s, Q, rots)
+    inp = tmp_path / "problem.txt"
+    inp.write_text(f"{N} 1.0\n" + " ".join(repr(float(v)) for v in np.r_[i_s, f_s, q, r]) + "\n")
+    out = subprocess.run([exe, str(inp)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().split("\n")
+    ok, fc, it = lines[0].split()
+    x = np.array([float(v) for v in lines[1].split()])
+    T = np.array([float(v) for v in lines[2].split()])
+    rc, x2, T2, co2, fc2, it2 = api.mid_get_ori_traj(init_s, final_s, Q, np.ones(N), rots)
+    assert ok == "1" and rc >= 0 and int(it) == it2 and float(fc) == fc2
+    assert np.array_equal(x, x2) and np.array_equal(T, T2)
