@@ -93,6 +93,7 @@ struct FwnBvh {
     }
 
     static void split(const Box &mm, const Box *boxes, uint32_t *ind, uint32_t n, uint32_t *&split_ind, Box *sb) {
+        if (n < 2) { sb[0] = mm; sb[1] = mm; split_ind = ind + n; return; }  // not reached: a node is split only when it holds >= 2 items
         if (n == 2) { sb[0] = boxes[ind[0]]; sb[1] = boxes[ind[1]]; split_ind = ind + 1; return; }
         constexpr uint32_t SMALL = 6, NSPANS = 16, NSPLITS = 15, MID = 32, MINFRAC = 16;
         if (n <= SMALL) {  // all (2^(n-1)) - 1 partitions with box 0 in part 0
