@@ -48,6 +48,15 @@ class _Config(C.Structure):
     ]
 
 
+class LmbmParams(C.Structure):
+    """svsdf_lmbm_params == lmbm::lmbm_parameter_t (lmbm.h:15-174)."""
+    _fields_ = [("timeout", C.c_float), ("bundle_size", C.c_int), ("ini_corrections", C.c_int), ("max_corrections", C.c_int),
+                ("exponent_distmeasure", C.c_int), ("max_iterations", C.c_int), ("max_evaluations", C.c_int), ("past", C.c_int),
+                ("verbose", C.c_int), ("update_method", C.c_int), ("scaling_strategy", C.c_int), ("delta_past", C.c_double),
+                ("f_rel_eps", C.c_double), ("f_lower_bound", C.c_double), ("terminate_param1", C.c_double), ("terminate_param2", C.c_double),
+                ("distance_measure", C.c_double), ("sufficient_dec", C.c_double), ("max_stepsize", C.c_double)]
+
+
 class MidConfig(C.Structure):
     """svsdf_mid_config: the yaml keys OriTraj::setParam reads (mid_end.hpp:333-359)."""
     _fields_ = [("rho_mid_end", C.c_double), ("vmax", C.c_double), ("omgmax", C.c_double), ("weight_v", C.c_double), ("weight_omg", C.c_double),
@@ -98,7 +107,8 @@ EXPORTED_SYMBOLS = [
     "svsdf_shape_sdf", "svsdf_shape_grad1", "svsdf_cost_grad_device", "svsdf_kernel_launches",
     "svsdf_executed_evals", "svsdf_fp64_peak", "svsdf_device_ptr_points", "svsdf_lbfgs_minimize", "svsdf_last_kernel_ms", "svsdf_sincos", "svsdf_set_map", "svsdf_set_map_device",
     "svsdf_extract_points", "svsdf_extract_points3d", "svsdf_set_map3d", "svsdf_get_points",
-    "svsdf_mid_default_config", "svsdf_mid_cost", "svsdf_mid_get_ori_traj", "svsdf_read_obj", "svsdf_free", "svsdf_mesh_fwn_host",
+    "svsdf_mid_default_config", "svsdf_mid_cost", "svsdf_mid_get_ori_traj",
+    "svsdf_lmbm_default_params", "svsdf_lmbm_open", "svsdf_lmbm_close", "svsdf_lmbm_last_error", "svsdf_lmbm_minimize", "svsdf_set_lmbm_library", "svsdf_read_obj", "svsdf_free", "svsdf_mesh_fwn_host",
     "svsdf_front_init", "svsdf_front_get_kernels", "svsdf_front_cspace", "svsdf_front_check_kernel_value", "svsdf_front_expand", "svsdf_front_astar",
 ]
 
@@ -155,6 +165,14 @@ def lib():
     L.svsdf_extract_points.argtypes = [vp, dp, C.c_int, C.c_double, dp, C.c_int, C.c_double, C.POINTER(C.c_int64)]
     L.svsdf_extract_points3d.argtypes = [vp, dp, C.c_int, dp, dp, C.c_int, C.c_double, C.POINTER(C.c_int64)]
     L.svsdf_set_map3d.argtypes = [vp, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, dp, C.c_double]
+    L.svsdf_lmbm_default_params.argtypes = [C.POINTER(LmbmParams)]
+    L.svsdf_lmbm_default_params.restype = None
+    L.svsdf_lmbm_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    L.svsdf_lmbm_close.argtypes = [C.c_void_p]
+    L.svsdf_lmbm_close.restype = None
+    L.svsdf_lmbm_last_error.restype = C.c_char_p
+    L.svsdf_lmbm_minimize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, dp, C.c_int, C.POINTER(LmbmParams), C.c_void_p, dp]
+    L.svsdf_set_lmbm_library.argtypes = [vp, C.c_char_p, C.POINTER(LmbmParams)]
     L.svsdf_mid_default_config.argtypes = [C.POINTER(MidConfig)]
     L.svsdf_mid_default_config.restype = None
     L.svsdf_mid_cost.argtypes = [C.POINTER(MidConfig), C.c_int, dp, dp, dp, dp, dp, dp, dp]
@@ -566,6 +584,11 @@ class Context:
         self.P = n.value
         return n.value
 
+    def set_lmbm_library(self, path, params: "LmbmParams" = None):
+        """svsdf_optimize / optimize_batch on this context run the reference's LMBM (own private instance) instead of L-BFGS; None: back."""
+        self._ck(lib().svsdf_set_lmbm_library(self.h, None if path is None else str(path).encode(), C.byref(params) if params is not None else None),
+                 "svsdf_set_lmbm_library")
+
     def get_points(self):
         n = C.c_int64()
         lib().svsdf_get_points(self.h, None, 0, C.byref(n))
@@ -781,3 +804,53 @@ def mid_get_ori_traj(init_s, final_s, Q, T_init, rot_list, cfg: MidConfig = None
     if rc < 0 and rc > -1000:
         raise SvsdfError(f"svsdf_mid_get_ori_traj failed with {rc}")
     return rc, x, T, co.reshape(3, 6 * N).T.copy(), fc.value, it.value
+
+
+# ---- the reference's LMBM library as a plug-in ----
+def lmbm_default_params(**over) -> LmbmParams:
+    p = LmbmParams()
+    lib().svsdf_lmbm_default_params(C.byref(p))
+    for k, v in over.items():
+        setattr(p, k, v)
+    return p
+
+
+class Lmbm:
+    """One instance of the reference's lmbm.so (svsdf_lmbm_open): private_copy=True loads a private copy of the file, so that several
+    instances can minimise concurrently from different threads (the library keeps its state in statics)."""
+
+    def __init__(self, path: str, private_copy: bool = True):
+        h = C.c_void_p()
+        rc = lib().svsdf_lmbm_open(str(path).encode(), int(bool(private_copy)), C.byref(h))
+        if rc != 0:
+            raise SvsdfError(f"svsdf_lmbm_open failed ({rc}): {lib().svsdf_lmbm_last_error().decode()}")
+        self.h = h
+
+    def minimize(self, fun, x0, params: LmbmParams = None):
+        """fun(x) -> (f, g).  Returns (lmbm status, x, f, evaluations)."""
+        x = _f64(x0).copy()
+        n_eval = [0]
+
+        def _eval(_inst, xp, gp, n):
+            xv = np.ctypeslib.as_array(xp, shape=(n,))
+            f, g = fun(xv.copy())
+            np.ctypeslib.as_array(gp, shape=(n,))[:] = g
+            n_eval[0] += 1
+            return float(f)
+
+        cb = EVAL_T(_eval)
+        fx = C.c_double()
+        rc = lib().svsdf_lmbm_minimize(self.h, C.cast(cb, C.c_void_p), None, _p(x), x.size, C.byref(params) if params is not None else None, None,
+                                       C.byref(fx))
+        return rc, x, fx.value, n_eval[0]
+
+    def close(self):
+        if self.h:
+            lib().svsdf_lmbm_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

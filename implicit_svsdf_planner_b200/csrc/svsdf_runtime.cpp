@@ -14,6 +14,8 @@
 #include <thread>
 #include <algorithm>
 #include <cmath>
+#include <dlfcn.h>
+#include <unistd.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -105,6 +107,8 @@ struct svsdf_ctx {
     // on the context's stream, and the host goes on (builds the trajectory blob) while the DMA runs.  ev_pts marks the end of the
     // last upload: the next svsdf_set_points (which overwrites the stage) and svsdf_device_ptr_points (which hands the buffer to
     // other streams) wait on it.
+    svsdf_lmbm *lmbm = nullptr;          // svsdf_set_lmbm_library: this context's private instance of the reference's LMBM
+    svsdf_lmbm_params lmbm_params;
     double *h_pts_stage = nullptr;
     size_t cap_pts_stage = 0;
     cudaEvent_t ev_pts = nullptr;
@@ -635,6 +639,81 @@ int svsdf_mesh_fwn_host(const double *vertices, int nv, const int32_t *faces, in
 void svsdf_free(void *p) { std::free(p); }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// The reference's LMBM library as a plug-in (lmbm.h:214-221).  Each handle is its own dlopen of (a private copy of) the file.
+// ---------------------------------------------------------------------------------------------------------------------
+struct svsdf_lmbm {
+    void *dl = nullptr;
+    // lmbm::lmbm_optimize(int, double*, double*, lmbm_evaluate_t, void*, lmbm_progress_t, lmbm_parameter_t*)
+    int (*optimize)(int, double *, double *, svsdf_eval_t, void *, svsdf_progress_t, svsdf_lmbm_params *) = nullptr;
+};
+static thread_local std::string g_lmbm_err;
+const char *svsdf_lmbm_last_error(void) { return g_lmbm_err.c_str(); }
+void svsdf_lmbm_default_params(svsdf_lmbm_params *p) {  // the member initialisers of lmbm::lmbm_parameter_t (lmbm.h:15-174)
+    if (!p) return;
+    p->timeout = 300.0f; p->bundle_size = 2; p->ini_corrections = 7; p->max_corrections = 15; p->exponent_distmeasure = 2;
+    p->max_iterations = 10000; p->max_evaluations = 20000; p->past = 10; p->verbose = -1; p->update_method = 0; p->scaling_strategy = 0;
+    p->delta_past = 1.0e-8; p->f_rel_eps = 1.0e+4; p->f_lower_bound = -1.0e+60; p->terminate_param1 = 1.0e-6; p->terminate_param2 = 1.0e-6;
+    p->distance_measure = 0.5; p->sufficient_dec = 1.0e-4; p->max_stepsize = 1.5;
+}
+int svsdf_lmbm_open(const char *path, int private_copy, svsdf_lmbm **out) {
+    if (!path || !out) return SVSDF_ERR_INVALID;
+    *out = nullptr;
+    std::string load = path;
+    bool temp = false;
+    if (private_copy) {  // a distinct file is a distinct library instance to the loader: own statics, own Fortran COMMON / SAVE data
+        FILE *src = std::fopen(path, "rb");
+        if (!src) { g_lmbm_err = std::string("svsdf_lmbm_open: cannot read ") + path; return SVSDF_ERR_INVALID; }
+        char tmpl[] = "/tmp/svsdf_lmbm_XXXXXX";
+        const int fd = mkstemp(tmpl);
+        if (fd < 0) { std::fclose(src); g_lmbm_err = "svsdf_lmbm_open: mkstemp failed"; return SVSDF_ERR_INVALID; }
+        char buf[1 << 16];
+        size_t nrd;
+        bool ok = true;
+        while ((nrd = std::fread(buf, 1, sizeof(buf), src)) > 0) ok = ok && (write(fd, buf, nrd) == (ssize_t)nrd);
+        std::fclose(src);
+        close(fd);
+        if (!ok) { unlink(tmpl); g_lmbm_err = "svsdf_lmbm_open: copy failed"; return SVSDF_ERR_INVALID; }
+        load = tmpl;
+        temp = true;
+    }
+    void *dl = dlopen(load.c_str(), RTLD_NOW | RTLD_LOCAL);
+    if (temp) unlink(load.c_str());  // the mapping stays valid
+    if (!dl) { g_lmbm_err = std::string("svsdf_lmbm_open: dlopen: ") + (dlerror() ? dlerror() : "?"); return SVSDF_ERR_INVALID; }
+    void *sym = dlsym(dl, "_ZN4lmbm13lmbm_optimizeEiPdS0_PFdPvPKdS0_iES1_PFiS1_S3_iEPNS_16lmbm_parameter_tE");
+    if (!sym) { dlclose(dl); g_lmbm_err = "svsdf_lmbm_open: lmbm::lmbm_optimize not found in the library"; return SVSDF_ERR_INVALID; }
+    svsdf_lmbm *h = new svsdf_lmbm();
+    h->dl = dl;
+    h->optimize = reinterpret_cast<decltype(h->optimize)>(sym);
+    *out = h;
+    return SVSDF_OK;
+}
+void svsdf_lmbm_close(svsdf_lmbm *h) {
+    if (!h) return;
+    if (h->dl) dlclose(h->dl);
+    delete h;
+}
+int svsdf_lmbm_minimize(svsdf_lmbm *h, svsdf_eval_t eval, void *instance, double *x, int n, const svsdf_lmbm_params *params,
+                        svsdf_progress_t progress, double *f_out) {
+    if (!h || !h->optimize || !eval || !x || n < 1) return SVSDF_ERR_INVALID;
+    svsdf_lmbm_params p;
+    if (params) p = *params; else svsdf_lmbm_default_params(&p);
+    double fx = 0.0;
+    // lmbm.cpp calls the progress function unconditionally (earlyexit_): never hand it a null pointer
+    const int ret = h->optimize(n, x, &fx, eval, instance, progress ? progress : +[](void *, const double *, const int) { return 0; }, &p);
+    if (f_out) *f_out = fx;
+    return ret;
+}
+int svsdf_set_lmbm_library(svsdf_ctx *ctx, const char *path, const svsdf_lmbm_params *params) {
+    if (!ctx) return SVSDF_ERR_INVALID;
+    if (ctx->lmbm) { svsdf_lmbm_close(ctx->lmbm); ctx->lmbm = nullptr; }
+    if (!path) return SVSDF_OK;
+    if (params) ctx->lmbm_params = *params; else svsdf_lmbm_default_params(&ctx->lmbm_params);
+    const int rc = svsdf_lmbm_open(path, 1, &ctx->lmbm);
+    if (rc) ctx->err = g_lmbm_err;
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // mid end (host/mid_end.hpp): OriTraj's cost function and warm-start optimisation, host only
 // ---------------------------------------------------------------------------------------------------------------------
 void svsdf_mid_default_config(svsdf_mid_config *c) {
@@ -1094,6 +1173,7 @@ void svsdf_destroy(svsdf_ctx *ctx) {
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->h_pts_stage) cudaFreeHost(ctx->h_pts_stage);
     if (ctx->ev_pts) cudaEventDestroy(ctx->ev_pts);
+    if (ctx->lmbm) svsdf_lmbm_close(ctx->lmbm);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     for (int k = 0; k < 5; ++k)
@@ -1389,8 +1469,22 @@ int svsdf_optimize(svsdf_ctx *ctx, const double *initS, const double *finalS, do
     ctx->gpu_ms_total = 0.0;
     ctx->time_kernels = true;
     auto t0 = std::chrono::steady_clock::now();
-    host::Lbfgs solver(hp);
-    host::LbfgsResult R = solver.minimize(opt_x, n, svsdf_evaluate, ctx, progress, user);
+    host::LbfgsResult R;
+    if (ctx->lmbm) {  // the reference's own LMBM drives the callback (back_end_optimizer.cpp:29-36); this context's private instance
+        struct Count { svsdf_ctx *ctx; int evals; svsdf_progress_t progress; void *user; int iters; } cnt{ctx, 0, progress, user, 0};
+        double fx = 0.0;
+        R.status = ctx->lmbm->optimize(
+            n, opt_x, &fx,
+            [](void *u, const double *xx, double *gg, const int nn) { Count *c = static_cast<Count *>(u); ++c->evals; return svsdf_evaluate(c->ctx, xx, gg, nn); }, &cnt,
+            [](void *u, const double *xx, const int k) { Count *c = static_cast<Count *>(u); c->iters = k; return c->progress ? c->progress(c->user, xx, k) : 0; },
+            &ctx->lmbm_params);
+        R.f = fx;
+        R.evaluations = cnt.evals;
+        R.iterations = cnt.iters;
+    } else {
+        host::Lbfgs solver(hp);
+        R = solver.minimize(opt_x, n, svsdf_evaluate, ctx, progress, user);
+    }
     auto t1 = std::chrono::steady_clock::now();
     ctx->time_kernels = false;
     // final trajectory from the returned iterate (optimize_traj_lmbm does the same on success and failure,

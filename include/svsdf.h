@@ -194,6 +194,31 @@ int svsdf_shape_grad1(svsdf_ctx *ctx, int64_t n, const double *rel, double *grad
 int svsdf_cost_grad_device(svsdf_ctx *ctx, int N, const double *T, const double *coeffs, int repeats,
                            float *ms_per_eval, double *out_host);
 
+/* ---- The reference's own outer solver as a plug-in ------------------------------------------------------------
+ * The back end of the reference is driven by LMBM, shipped as a prebuilt Fortran library (src/utils/include/utils/lmbm.so behind
+ * lmbm.h / lmbm.cpp).  It is not redistributed here, but a deployment that has it can plug it in: svsdf_lmbm_open loads the library from
+ * `path` — by default a PRIVATE COPY of the file, so that every handle has its own instance of the library's static state (lmbm.cpp:4-6
+ * keeps the callback in file-scope statics and the Fortran code keeps COMMON / SAVE data): handles can then run concurrently from
+ * different threads, which one shared instance cannot.  svsdf_lmbm_params mirrors lmbm::lmbm_parameter_t (lmbm.h:15-174);
+ * svsdf_lmbm_default_params fills the struct's member initialisers (what back_end_optimizer.cpp:29 uses). */
+typedef struct svsdf_lmbm svsdf_lmbm;
+typedef struct {
+    float timeout;
+    int bundle_size, ini_corrections, max_corrections, exponent_distmeasure, max_iterations, max_evaluations, past, verbose, update_method,
+        scaling_strategy;
+    double delta_past, f_rel_eps, f_lower_bound, terminate_param1, terminate_param2, distance_measure, sufficient_dec, max_stepsize;
+} svsdf_lmbm_params;
+void svsdf_lmbm_default_params(svsdf_lmbm_params *p);
+int svsdf_lmbm_open(const char *path, int private_copy, svsdf_lmbm **out);
+void svsdf_lmbm_close(svsdf_lmbm *h);
+const char *svsdf_lmbm_last_error(void);
+/* lmbm::lmbm_optimize(n, x, &fx, eval, instance, progress, &param) (lmbm.h:214-221); returns LMBM's code (>= 0 success). */
+int svsdf_lmbm_minimize(svsdf_lmbm *h, svsdf_eval_t eval, void *instance, double *x, int n, const svsdf_lmbm_params *params,
+                        svsdf_progress_t progress, double *f_out);
+/* Makes svsdf_optimize (and svsdf_optimize_batch for this context) run LMBM instead of the built-in L-BFGS: the context takes its own
+ * private instance of the library at `path` (NULL: back to L-BFGS).  params NULL = defaults. */
+int svsdf_set_lmbm_library(svsdf_ctx *ctx, const char *path, const svsdf_lmbm_params *params);
+
 /* ---- Mid end (host only, no GPU and no context) ---------------------------------------------------------
  * OriTraj (src/planner_algorithm/include/planner_algorithm/mid_end.hpp, src/mid_end.cpp): the warm-start optimisation between the A*
  * front end and the SVSDF back end — MINCO energy + cubic pull of the inner waypoints towards their A* cells + trapezoid integral of

@@ -154,3 +154,27 @@ def test_lbfgs_nonsmooth_restarts_and_failed_first_evaluation():
 
     rcn, _, _ = api.lbfgs_minimize(lambda x: (float("nan"), np.zeros_like(x)), x0, p1)
     assert rcn == -1012
+
+
+def test_lmbm_plugin_equals_the_library_and_private_copies_run_concurrently():
+    """svsdf_lmbm_open / svsdf_lmbm_minimize on the host (no GPU): same result as calling the reference's lmbm_optimize directly, and two
+    private copies minimise concurrently from two threads (the library keeps its callback and its Fortran state in statics — one shared
+    instance cannot).  Runs in a subprocess whose loader path holds a libgfortran.so.5 (tests/tools/lmbm_plugin_check.py)."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.exists(os.path.join(root, "oracle", "_ref", "lmbm.so")):
+        pytest.skip("oracle/_ref/lmbm.so absent (the reference binary is only available where /root/reference is)")
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "tools", "lmbm_plugin_check.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    rec = json.loads(out.stdout.strip().split("\n")[-1])
+    if "unavailable" in rec:
+        pytest.skip(rec["unavailable"])
+    assert rec["direct_equal"] and rec["concurrent_equal_alone"] and rec["status"] >= 0 and rec["f"] < 0.1 * rec["f_start"]
+    # a wrong path is an error with a message, not a crash
+    from implicit_svsdf_planner_b200 import api
+
+    with pytest.raises(api.SvsdfError):
+        api.Lmbm(os.path.join(root, "no_such_lmbm.so"))

@@ -44,3 +44,17 @@ def test_reference_lmbm_retraces_its_oracle_run_on_the_gpu(tmp_path):
     rec2 = run([])
     assert int(rec2["lmbm_return"]) == int(rec["lmbm_return"]) and rec2["f_final"] == rec["f_final"]
     assert rec2["iterations"] == rec["iterations"]
+
+
+@pytest.mark.skipif(not os.path.exists(LMBM), reason="oracle/_ref/lmbm.so absent (the reference binary is only available where /root/reference is)")
+def test_lmbm_as_the_contexts_own_solver_plugin():
+    """svsdf_set_lmbm_library: the context loads a private instance of the reference's library and svsdf_optimize runs it on
+    svsdf_evaluate — the same run, bit for bit, as handing the entry point to lmbm_optimize from outside."""
+    direct = run([])
+    if "unavailable" in direct:
+        pytest.skip(direct["unavailable"])
+    plug = run(["--plugin"])
+    assert int(plug["lmbm_return"]) == int(direct["lmbm_return"]) and plug["f_final"] == direct["f_final"]
+    assert plug["iterations"] == direct["iterations"]
+    assert plug["optimize_return"] == (1 if plug["lmbm_return"] == 0 else plug["lmbm_return"])  # 0 remapped to 1, back_end_optimizer.cpp:66-69
+    assert plug["f_final"] < 0.6 * plug["f_start"]

@@ -58,6 +58,8 @@ def main():
     ap.add_argument("--seed-map", type=int, default=777)
     ap.add_argument("--max-evals", type=int, default=400)
     ap.add_argument("--trace", default=None)
+    ap.add_argument("--plugin", action="store_true", help="go through the library's own plug-in (svsdf_set_lmbm_library + svsdf_optimize) "
+                                                          "instead of calling lmbm_optimize from here")
     args = ap.parse_args()
     if not os.path.exists(LMBM):
         print(json.dumps({"unavailable": "oracle/_ref/lmbm.so not present (built only where /root/reference exists)"}))
@@ -73,6 +75,18 @@ def main():
     opt.parallel_points = sc.points
     opt.setConditions(sc.init_s, sc.final_s, sc.N)
     f0, _ = opt.costFunction(sc.x0)
+    if args.plugin:
+        # the context loads its own private instance of the library and svsdf_optimize runs it on svsdf_evaluate (what a batch worker does)
+        lp = api.lmbm_default_params(max_evaluations=args.max_evals)
+        opt.ctx.set_lmbm_library(LMBM, lp)
+        t0 = time.perf_counter()
+        rc, x, T, b, st = opt.ctx.optimize(sc.init_s, sc.final_s, sc.x0, sc.N, None)
+        dt = time.perf_counter() - t0
+        f_end, _ = opt.costFunction(x)
+        print(json.dumps({"solver": "reference lmbm.so through svsdf_set_lmbm_library", "points": int(sc.P), "pieces": int(sc.N),
+                          "lmbm_return": int(st["status"]), "optimize_return": int(rc), "f_start": float(f0), "f_final": float(st["final_cost"]),
+                          "f_at_final_x": float(f_end), "iterations": int(st["iterations"]), "evaluations": int(st["evaluations"]), "seconds": dt}), flush=True)
+        return
     L = C.CDLL(LMBM)
     lmbm_optimize = getattr(L, SYM)
     lmbm_optimize.restype = C.c_int
