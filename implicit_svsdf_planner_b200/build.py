@@ -41,6 +41,7 @@ HEADERS = [
     "host/minco.hpp",
     "host/lbfgs.hpp",
     "host/astar.hpp",
+    "host/astar_flat.hpp",
     "host/fwn_bvh.hpp",
     "host/mid_end.hpp",
     "../../include/svsdf.h",

@@ -1,12 +1,14 @@
 // CPU check of the product's lock-step batch A* (implicit_svsdf_planner_b200/csrc/host/astar.hpp): the node test is supplied by the
 // CPU oracle here (tests may use the oracle; the product passes svsdf_front_expand), and every problem's path and expansion
 // count must equal the oracle's literal single-problem restatement of AstarPathSearch.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <random>
 #include <vector>
 
 #include "../../implicit_svsdf_planner_b200/csrc/host/astar.hpp"
+#include "../../implicit_svsdf_planner_b200/csrc/host/astar_flat.hpp"
 #include "../../oracle/frontend_oracle.hpp"
 
 int main(int argc, char **argv) {
@@ -51,6 +53,53 @@ int main(int argc, char **argv) {
         found += want_len > 0;
     }
     if (len[0] != 1) { bad++; std::printf("same-cell problem: len %d\n", len[0]); }
+    // the container-free bookkeeping (host/astar_flat.hpp: flat arrays + a binary heap ordered by (f, insertion number); the code a
+    // device-side search would run): one search at a time, same node test, must give the same paths and expansion counts
+    {
+        const int NS = X * Y;
+        std::vector<int8_t> id(NS + 1);
+        std::vector<double> g(NS + 1), f(NS + 1), yw(NS + 1);
+        std::vector<int32_t> father(NS + 1);
+        std::vector<svsdf::host::FlatHeapEntry> heap(4 * (size_t)(NS + 1));
+        const double xmax = ox + X * res, ymax = oy + Y * res;
+        int flat_bad = 0;
+        size_t max_heap = 0;
+        for (int q = 0; q < n; ++q) {
+            const double *s = &st[2 * q], *gq = &go[2 * q];
+            int flen = 0, fex = 0;
+            std::vector<double> fpath((size_t)max_path * 3, 0.0);
+            auto in_map = [&](const double *v) { return !(v[0] < ox || v[1] < oy || v[0] > xmax || v[1] > ymax); };
+            if (in_map(s) && in_map(gq)) {
+                std::fill(id.begin(), id.end(), 0);
+                std::fill(father.begin(), father.end(), -1);
+                svsdf::host::FlatSearch F;
+                F.X = X; F.Y = Y; F.NS = NS; F.id = id.data(); F.g = g.data(); F.f = f.data(); F.yaw = yw.data(); F.father = father.data();
+                F.heap = heap.data(); F.heap_cap = (int)heap.size();
+                F.begin(svsdf::host::astar_grid_index(s[0], ox, res, X), svsdf::host::astar_grid_index(s[1], oy, res, Y),
+                        svsdf::host::astar_grid_index(gq[0], ox, res, X), svsdf::host::astar_grid_index(gq[1], oy, res, Y));
+                int cx, cy;
+                double cyaw;
+                while (F.pop_next(1LL << 30, cx, cy, cyaw)) {
+                    unsigned char ok9[9];
+                    double yaw9[9];
+                    uint8_t parts[9];
+                    expand_node(S, SK, M, G, cx, cy, cyaw, ks, ok9, yaw9, parts);
+                    F.apply(cx, cy, ok9, yaw9);
+                    max_heap = std::max(max_heap, (size_t)F.heap_n);
+                }
+                if (F.status == 1) {
+                    flen = F.path(ox, oy, res, max_path, fpath.data());
+                    if (flen > max_path) flen = 0;
+                }
+                if (F.status < 0) { flat_bad++; std::printf("flat problem %d: heap overflow\n", q); }
+                fex = (int)F.expansions;
+            }
+            if (flen != len[q] || fex != ex[q]) { flat_bad++; std::printf("flat problem %d: len %d vs %d, expansions %d vs %d\n", q, flen, len[q], fex, ex[q]); continue; }
+            if (flen && std::memcmp(fpath.data(), &paths[(size_t)q * max_path * 3], (size_t)flen * 3 * sizeof(double)) != 0) { flat_bad++; std::printf("flat problem %d: path differs\n", q); }
+        }
+        std::printf("flat bookkeeping: %s (largest open list %zu entries of capacity %zu)\n", flat_bad ? "FAIL" : "identical", max_heap, heap.size());
+        bad += flat_bad;
+    }
     std::printf("%s problems %d found %d rounds %lld expansions %lld\n", bad ? "FAIL" : "OK", n, found, (long long)stats.rounds, (long long)stats.expansions);
     return bad ? 1 : 0;
 }

@@ -141,8 +141,9 @@ def test_astar_paths_are_valid_and_near_optimal(oracle_mod):
 
 
 def test_product_batch_astar_host_logic_equals_the_oracle(tmp_path):
-    """csrc/host/astar.hpp (the lock-step batch search the library runs on top of svsdf_front_expand) compiled for the host with
-    the oracle's node test plugged in: paths and expansion counts must equal the oracle's literal AstarPathSearch."""
+    """csrc/host/astar.hpp (the lock-step batch search the library runs on top of svsdf_front_expand) and csrc/host/astar_flat.hpp (the same
+    bookkeeping on flat arrays and a binary heap, device-compilable) compiled for the host with the oracle's node test plugged in: paths
+    and expansion counts must equal the oracle's literal AstarPathSearch."""
     import os
     import subprocess
 
@@ -151,4 +152,7 @@ def test_product_batch_astar_host_logic_equals_the_oracle(tmp_path):
     subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fopenmp", "-mfma", "-ffp-contract=off",
                            os.path.join(root, "tests", "cpp", "astar_host_main.cpp"), "-o", exe])
     out = subprocess.run([exe, "40"], capture_output=True, text=True)
-    assert out.returncode == 0 and out.stdout.startswith("OK"), out.stdout + out.stderr
+    lines = out.stdout.strip().split("\n")
+    assert out.returncode == 0 and lines[-1].startswith("OK"), out.stdout + out.stderr
+    # the container-free bookkeeping a device-side search would run (csrc/host/astar_flat.hpp) gives the same paths and counts
+    assert any(l.startswith("flat bookkeeping: identical") for l in lines), out.stdout
